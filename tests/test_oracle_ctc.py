@@ -1,0 +1,121 @@
+"""Oracle (CTC) cross-checks: brute-force enumeration, torch CTC, finite
+differences, decoder semantics.  CPU only.  (Parity unpinned by the reference:
+TF is not installed; these are the independent pins SURVEY 8c lists.)"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc as oc
+
+
+def test_loss_matches_bruteforce_enumeration():
+    rng = np.random.RandomState(0)
+    T, C, blank = 5, 4, 3
+    logits = rng.randn(T, C)
+    probs = oc.brute_force_label_probs(logits, blank)
+    assert abs(sum(probs.values()) - 1.0) < 1e-12
+    for lab in [(0, 1), (1, 1), (2,), (), (0, 1, 2), (0, 0, 0)]:
+        loss, _ = oc.ctc_loss_grad_single(logits, T, list(lab), blank)
+        p = probs.get(lab, 0.0)
+        if p == 0.0:
+            assert np.isinf(loss)
+        else:
+            assert abs(loss - (-np.log(p))) < 1e-10, lab
+
+
+def test_tf_style_known_answer_is_rederived():
+    # 5 frames x 6 classes (blank = 5), the shape of TF's ctc_loss_op_test: we do
+    # not trust remembered constants, we re-derive them by enumeration.
+    rng = np.random.RandomState(3)
+    logits = rng.randn(5, 6)
+    probs = oc.brute_force_label_probs(logits, 5)
+    for lab in [(0, 1, 2, 1, 0), (0, 1, 1, 0)]:
+        loss, _ = oc.ctc_loss_grad_single(logits, 5, list(lab), 5)
+        ref = -np.log(probs[lab]) if probs.get(lab, 0) > 0 else np.inf
+        assert np.isclose(loss, ref, rtol=1e-10) or (np.isinf(loss) and np.isinf(ref))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_loss_and_grad_match_torch(seed):
+    rng = np.random.RandomState(seed)
+    N, T, C = 4, 37, 28
+    logits = rng.randn(N, T, C).astype(np.float32) * 2
+    lens = np.array([37, 30, 21, 9])
+    labels = [rng.randint(0, 25, size=L) for L in (7, 12, 3, 4)]
+    labels[1][3] = labels[1][4]                        # a repeat
+    loss, grad = oc.ctc_loss_grad(logits, lens, labels)
+    tl = torch.tensor(logits, dtype=torch.float64, requires_grad=True)
+    lp = torch.log_softmax(tl, dim=2).transpose(0, 1)
+    tgt = torch.tensor(np.concatenate(labels), dtype=torch.long)
+    out = torch.nn.functional.ctc_loss(lp, tgt, torch.tensor(lens), torch.tensor([len(l) for l in labels]),
+                                       blank=C - 1, reduction="none", zero_infinity=False)
+    out.sum().backward()
+    np.testing.assert_allclose(loss, out.detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(grad, tl.grad.numpy(), atol=2e-6)
+    for n in range(N):                                 # zero grad past seq_len
+        assert np.all(grad[n, lens[n]:] == 0)
+
+
+def test_grad_finite_difference():
+    rng = np.random.RandomState(5)
+    T, C = 6, 5
+    logits = rng.randn(T, C)
+    lab = [1, 1, 3]
+    _, g = oc.ctc_loss_grad_single(logits, T, lab, C - 1)
+    eps = 1e-6
+    for (t, k) in [(0, 0), (2, 1), (5, 4), (3, 3)]:
+        lp, lm = logits.copy(), logits.copy()
+        lp[t, k] += eps
+        lm[t, k] -= eps
+        fd = (oc.ctc_loss_grad_single(lp, T, lab, C - 1)[0] -
+              oc.ctc_loss_grad_single(lm, T, lab, C - 1)[0]) / (2 * eps)
+        assert abs(fd - g[t, k]) < 1e-6
+
+
+def test_greedy_semantics():
+    blank = 3
+    def onehot(seq):
+        x = np.full((len(seq), 4), -5.0)
+        for t, k in enumerate(seq):
+            x[t, k] = 5.0
+        return x
+    assert oc.greedy_decode_single(onehot([0, 0, 3, 0, 1, 1, 3, 3, 2]), 9, blank) == [0, 0, 1, 2]
+    assert oc.greedy_decode_single(onehot([0, 0, 3, 0, 1, 1, 3, 3, 2]), 4, blank) == [0, 0]
+    assert oc.greedy_decode_single(onehot([3, 3]), 2, blank) == []
+    tie = np.zeros((1, 4))
+    assert oc.greedy_decode_single(tie, 1, blank) == [0]            # first max wins
+
+
+def test_beam_finds_most_probable_labelling_on_tiny_problems():
+    rng = np.random.RandomState(7)
+    for trial in range(20):
+        T, C = 4, 3
+        logits = rng.randn(T, C) * 2
+        probs = oc.brute_force_label_probs(logits, C - 1)
+        best = max(probs.items(), key=lambda kv: kv[1])[0]
+        got = oc.beam_decode_single(logits, T, C - 1, beam_width=100, merge_repeated=False)
+        assert tuple(got) == best, (trial, got, best)
+
+
+def test_beam_merge_repeated_quirk_and_width1():
+    rng = np.random.RandomState(11)
+    logits = rng.randn(30, 6) * 3
+    a = oc.beam_decode_single(logits, 30, 5, 50, merge_repeated=False)
+    b = oc.beam_decode_single(logits, 30, 5, 50, merge_repeated=True)
+    collapsed = [k for i, k in enumerate(a) if i == 0 or k != a[i - 1]]
+    assert b == collapsed
+    assert oc.beam_decode_single(logits, 0, 5, 10) == []
+    # a peaky posterior: beam == greedy
+    peaky = np.full((12, 6), -20.0)
+    seq = [0, 0, 5, 1, 5, 5, 2, 2, 5, 0, 5, 5]
+    for t, k in enumerate(seq):
+        peaky[t, k] = 20.0
+    assert oc.beam_decode_single(peaky, 12, 5, 8, merge_repeated=False) == \
+        oc.greedy_decode_single(peaky, 12, 5) == [0, 1, 2, 0]
+
+
+def test_ler():
+    assert oc.edit_distance([1, 2, 3], [1, 3]) == 1
+    assert oc.edit_distance([], [1, 2]) == 2
+    assert abs(oc.ler([[1, 2, 3, 4]], [[1, 2, 4]]) - 0.25) < 1e-12
+    assert abs(oc.ler([[1, 2], [3]], [[1, 2], [4]]) - 0.5) < 1e-12

@@ -1,0 +1,77 @@
+"""Oracle (MFCC) vs the golden vectors produced by the reference's own
+preprocessing/audio_utils.py (oracle/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mfcc as om
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "mfcc_reference.npz"))
+
+
+def _clip(seed, secs):
+    return np.random.RandomState(int(seed)).randn(int(np.floor(secs * 16000))).astype(np.float32)
+
+
+@pytest.mark.parametrize("i", range(len(G["clip_seeds"])))
+def test_oracle_matches_reference_golden(i):
+    seed, secs = int(G["clip_seeds"][i]), float(G["clip_seconds"][i])
+    sig = _clip(seed, secs)
+    got = {
+        "mfcc26": om.MFCC(num_cep=13, d=True, dd=False)(sig),
+        "mfcc39": om.MFCC()(sig),
+        "mfcc13_raw": om.MFCC(d=False, dd=False).cepstra(sig),
+        "logfbank40": om.LogFbank()(sig),
+    }
+    for k, v in got.items():
+        ref = G[f"{k}_{seed}"]
+        assert v.shape == ref.shape
+        np.testing.assert_allclose(v, ref, rtol=0, atol=1e-9)
+
+
+def test_filterbank_golden_and_shape():
+    fb = om.filterbanks()
+    assert fb.shape == (40, 257)
+    assert np.array_equal(fb, G["filterbank"])
+    starts = [int(np.nonzero(r)[0][0]) for r in fb[:5]]
+    assert starts == [1, 2, 4, 5, 7] or starts[0] >= 0   # bins start near DC
+
+
+def test_frame_count_rules():
+    # audio_utils.py:30-33
+    assert om.num_frames(160000, 400, 160) == 999
+    assert om.num_frames(400, 400, 160) == 1
+    assert om.num_frames(320, 400, 160) == 1
+    assert om.num_frames(401, 400, 160) == 2
+    assert om.round_half_up(0.025 * 16e3) == 400 and om.round_half_up(2.5) == 3
+
+
+def test_dct_matrix_is_scipy_dct():
+    from scipy.fftpack import dct
+    x = np.random.RandomState(0).randn(7, 40)
+    np.testing.assert_allclose(x @ om.dct2_ortho_matrix(40, 13).T,
+                               dct(x, type=2, axis=1, norm="ortho")[:, :13], atol=1e-12)
+
+
+def test_context_window_matches_reference_loop():
+    # audio.py:88-150 replayed naively
+    f = om.Feature(num_context=2, stride=2)
+    x = np.random.RandomState(1).randn(11, 3)
+    got = f._postprocessing(x)
+    xs = x[::2]
+    T, F = xs.shape
+    exp = np.zeros((T, F * 5))
+    for t in range(T):
+        for off in range(-2, 3):
+            if 0 <= t + off < T:
+                exp[t, (off + 2) * F:(off + 3) * F] = xs[t + off]
+    assert np.array_equal(got, exp)
+
+
+def test_pad_batch_contract():
+    # datasets/dataset_generator.py:223-235
+    a, b = np.ones((3, 2)), 2 * np.ones((5, 2))
+    x, n = om.pad_batch([a, b])
+    assert x.dtype == np.float32 and x.shape == (2, 5, 2)
+    assert n.tolist() == [3, 5] and np.all(x[0, 3:] == 0)
