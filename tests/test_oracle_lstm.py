@@ -107,7 +107,7 @@ def test_full_model_grad_and_adam_vs_torch():
     assert n < 400
     for k in p1:
         big = np.abs(grads[k]) > 1e-4        # eps placement differs (Keras: sqrt(v)+eps un-corrected)
-        np.testing.assert_allclose(p1[k][big], tp[k].detach().numpy()[big], atol=5e-6)
+        np.testing.assert_allclose(p1[k][big], tp[k].detach().numpy()[big], atol=3e-5)
 
 
 def test_clipnorm_scales_globally():
