@@ -1,0 +1,79 @@
+// C-ABI dispatch for the GEMM and BiLSTM entry points (see include/asr_b200.h).
+#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+namespace gemm_mma {
+int32_t run(int dtype_in, int dtype_out, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
+            void* C, int64_t ldc, const float* bias, float alpha, int accumulate, cudaStream_t st);
+}
+namespace gemm_tc {
+bool supports(int dtype_in, int dtype_out, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc);
+int32_t run(int dtype_in, int dtype_out, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
+            void* C, int64_t ldc, const float* bias, float alpha, int accumulate, cudaStream_t st);
+}
+namespace lstm32 {
+size_t scratch_bytes(int H);
+int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
+int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st);
+}
+namespace lstmtc {
+bool supports_fwd(const asr_lstm_fwd_args* a);
+bool supports_bwd(const asr_lstm_bwd_args* a);
+size_t scratch_bytes(int H);
+int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
+int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st);
+}
+
+// Engine selection is a *build/debug* switch, not a fallback: ASR_B200_GEMM=mma / ASR_B200_LSTM=fp32 pin
+// the cross-check engines (used by the tests); default is the tcgen05 engines wherever they take the shape.
+static int env_is(const char* name, const char* val) {
+  const char* e = getenv(name);
+  return e && strcmp(e, val) == 0;
+}
+
+extern "C" int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N, int32_t K, const void* A,
+                               int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
+                               float alpha, int32_t accumulate, void* stream) {
+  ASR_CHECK_ARG(A && B && C, "asr_gemm_tn: null operand");
+  ASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "asr_gemm_tn: bad shape %dx%dx%d", M, N, K);
+  ASR_CHECK_ARG(dtype_in >= 0 && dtype_in <= 1 && dtype_out >= 0 && dtype_out <= 2, "asr_gemm_tn: bad dtype");
+  ASR_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K && ldc >= N,
+                "asr_gemm_tn: K, lda, ldb must be multiples of 8 (16-byte rows)");
+  ASR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "asr_gemm_tn: operands must be 16-byte aligned");
+  ASR_CHECK_ARG(!accumulate || dtype_out == 0, "asr_gemm_tn: accumulate needs fp32 C");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!env_is("ASR_B200_GEMM", "mma") && gemm_tc::supports(dtype_in, dtype_out, M, N, K, lda, ldb, ldc))
+    return gemm_tc::run(dtype_in, dtype_out, M, N, K, A, lda, B, ldb, C, ldc, bias, alpha, accumulate, st);
+  return gemm_mma::run(dtype_in, dtype_out, M, N, K, A, lda, B, ldb, C, ldc, bias, alpha, accumulate, st);
+}
+
+extern "C" size_t asr_lstm_flags_bytes(void) {
+  // sized for the largest supported hidden size of either engine
+  const size_t a = lstm32::scratch_bytes(1024), b = lstmtc::scratch_bytes(1024);
+  return a > b ? a : b;
+}
+
+static int32_t check_common(int T, int N, int H) {
+  ASR_CHECK_ARG(T >= 1 && N >= 1 && H >= 1 && H <= 1024, "lstm: bad shape T=%d N=%d H=%d", T, N, H);
+  return ASR_OK;
+}
+
+extern "C" int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream) {
+  ASR_CHECK_ARG(a && a->zx && a->bias && a->flags, "asr_lstm_forward: null argument");
+  if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
+  ASR_CHECK_ARG(!a->training || (a->gates && a->cell), "asr_lstm_forward: training needs gates/cell buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!env_is("ASR_B200_LSTM", "fp32") && lstmtc::supports_fwd(a)) return lstmtc::forward(a, st);
+  ASR_CHECK_ARG(a->U, "asr_lstm_forward: fp32 engine needs U");
+  return lstm32::forward(a, st);
+}
+
+extern "C" int32_t asr_lstm_backward(const asr_lstm_bwd_args* a, void* stream) {
+  ASR_CHECK_ARG(a && a->dh && a->gates && a->cell && a->dbias && a->flags, "asr_lstm_backward: null argument");
+  if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!env_is("ASR_B200_LSTM", "fp32") && lstmtc::supports_bwd(a)) return lstmtc::backward(a, st);
+  ASR_CHECK_ARG(a->U, "asr_lstm_backward: fp32 engine needs U");
+  return lstm32::backward(a, st);
+}

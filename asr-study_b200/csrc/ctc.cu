@@ -1,0 +1,333 @@
+// K6 / K7 — CTC loss + gradient and best-path decode for sm_100a.
+//
+// asr_ctc_loss_grad: one CTA per utterance.
+//   phase 0  all warps: per-frame log-sum-exp of the logits (softmax normaliser)
+//   phase 1  warp 0 runs the alpha lattice forward in time, warp 1 runs the beta
+//            lattice backward, concurrently, in the log domain (lane = lattice
+//            state, log-sum-exp of the 3 predecessors), rows parked in an
+//            L2-resident workspace
+//   phase 2  all warps: per frame, reduce alpha+beta per class and write
+//            dloss/dlogits = softmax - occupancy
+// Replaces tf.nn.ctc_loss (core/ctc_utils.py:68-70): softmax inside, standard
+// merge-repeated topology, zero gradient for t >= seq_len.
+// asr_ctc_greedy replaces tf.nn.ctc_greedy_decoder (core/ctc_utils.py:42).
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int CTC_THREADS = 256;
+constexpr int CTC_WARPS = CTC_THREADS / 32;
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + log1pf(expf(fminf(a, b) - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+// NJ = states per lane (S <= 32*NJ)
+template <int NJ>
+__global__ void __launch_bounds__(CTC_THREADS)
+ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
+                     const int* __restrict__ in_len, const int* __restrict__ labels,
+                     const int* __restrict__ label_off, int s_max, int blank,
+                     float grad_scale, float* __restrict__ loss, float* __restrict__ grad,
+                     float* __restrict__ ws) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = min(max(in_len[n], 0), T);
+  const int l0 = label_off[n], L = label_off[n + 1] - l0;
+  const int S = 2 * L + 1;
+  const float NEG = -CUDART_INF_F;
+
+  float* w_alpha = ws + (size_t)n * ((size_t)2 * T * s_max + T);
+  float* w_beta = w_alpha + (size_t)T * s_max;
+  float* w_lse = w_beta + (size_t)T * s_max;
+
+  int* ext = reinterpret_cast<int*>(sm);            // [32*NJ]
+  float* rowA = sm + 32 * NJ;                        // [32*NJ + 2] alpha exchange (2 pad in front)
+  float* rowB = rowA + 32 * NJ + 2;                  // [32*NJ + 2] beta exchange (2 pad at end)
+  float* acc = rowB + 32 * NJ + 2;                   // [CTC_WARPS][C]
+  __shared__ float s_logp;
+
+  for (int s = tid; s < 32 * NJ; s += CTC_THREADS)
+    ext[s] = (s < S && (s & 1)) ? labels[l0 + (s >> 1)] : blank;
+
+  // ---- phase 0: softmax normaliser per frame ------------------------------------
+  for (int t = warp; t < len; t += CTC_WARPS) {
+    const float* row = logits + ((size_t)t * N + n) * C;
+    float m = NEG;
+    for (int k = lane; k < C; k += 32) m = fmaxf(m, row[k]);
+    m = asr::warp_max(m);
+    float s = 0.0f;
+    for (int k = lane; k < C; k += 32) s += expf(row[k] - m);
+    s = asr::warp_sum(s);
+    if (lane == 0) w_lse[t] = m + logf(s);
+  }
+  __syncthreads();
+
+  if (len == 0 || S > 32 * NJ) {   // degenerate: no frames (or label too long for this build)
+    if (tid == 0) loss[n] = CUDART_INF_F;
+    for (int i = tid; i < T * C; i += CTC_THREADS) grad[((size_t)(i / C) * N + n) * C + (i % C)] = 0.0f;
+    return;
+  }
+
+  // ---- phase 1: alpha (warp 0) and beta (warp 1) --------------------------------
+  if (warp == 0) {
+    bool skip[NJ];
+    int lab[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int s = j * 32 + lane;
+      lab[j] = ext[s];
+      skip[j] = (s >= 2) && (s < S) && (lab[j] != blank) && (lab[j] != ext[s - 2]);
+    }
+    float* prev = rowA + 2;
+    if (lane < 2) rowA[lane] = NEG;
+    float a[NJ], x[NJ];
+    {
+      const float* row = logits + (size_t)n * C;
+      const float z = w_lse[0];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int s = j * 32 + lane;
+        a[j] = (s < 2 && s < S) ? row[lab[j]] - z : NEG;
+        if (s < S) w_alpha[s] = a[j];
+      }
+    }
+    if (len > 1) {
+      const float* row = logits + ((size_t)1 * N + n) * C;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) x[j] = row[lab[j]];
+    }
+    for (int t = 1; t < len; ++t) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) prev[j * 32 + lane] = a[j];
+      __syncwarp();
+      const float z = w_lse[t];
+      float xn[NJ];
+      if (t + 1 < len) {
+        const float* row = logits + ((size_t)(t + 1) * N + n) * C;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) xn[j] = row[lab[j]];
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int s = j * 32 + lane;
+        const float p1 = prev[s - 1];
+        const float p2 = skip[j] ? prev[s - 2] : NEG;
+        const float v = lse3(a[j], p1, p2) + (x[j] - z);
+        a[j] = (s < S) ? v : NEG;
+        if (s < S) w_alpha[(size_t)t * s_max + s] = a[j];
+      }
+      __syncwarp();
+      if (t + 1 < len) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) x[j] = xn[j];
+      }
+    }
+    // log p(l|x) = lse(alpha[len-1][S-1], alpha[len-1][S-2])
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) prev[j * 32 + lane] = a[j];
+    __syncwarp();
+    if (lane == 0) s_logp = (S > 1) ? lse2(prev[S - 1], prev[S - 2]) : prev[S - 1];
+  } else if (warp == 1) {
+    bool skip[NJ];
+    int lab[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int s = j * 32 + lane;
+      lab[j] = ext[s];
+      // transition s -> s+2 allowed
+      skip[j] = (s + 2 < S) && (ext[s + 2] != blank) && (ext[s + 2] != lab[j]);
+    }
+    float* nxt = rowB;
+    if (lane < 2) rowB[32 * NJ + lane] = NEG;
+    float b[NJ], x[NJ];
+    {
+      const float* row = logits + ((size_t)(len - 1) * N + n) * C;
+      const float z = w_lse[len - 1];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int s = j * 32 + lane;
+        b[j] = (s < S && s >= S - 2) ? row[lab[j]] - z : NEG;
+        if (s < S) w_beta[(size_t)(len - 1) * s_max + s] = b[j];
+      }
+    }
+    if (len > 1) {
+      const float* row = logits + ((size_t)(len - 2) * N + n) * C;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) x[j] = row[lab[j]];
+    }
+    for (int t = len - 2; t >= 0; --t) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) nxt[j * 32 + lane] = b[j];
+      __syncwarp();
+      const float z = w_lse[t];
+      float xn[NJ];
+      if (t > 0) {
+        const float* row = logits + ((size_t)(t - 1) * N + n) * C;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) xn[j] = row[lab[j]];
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int s = j * 32 + lane;
+        const float p1 = nxt[s + 1];
+        const float p2 = skip[j] ? nxt[s + 2] : NEG;
+        const float v = lse3(b[j], p1, p2) + (x[j] - z);
+        b[j] = (s < S) ? v : NEG;
+        if (s < S) w_beta[(size_t)t * s_max + s] = b[j];
+      }
+      __syncwarp();
+      if (t > 0) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) x[j] = xn[j];
+      }
+    }
+  }
+  __syncthreads();
+
+  const float logp = s_logp;
+  if (tid == 0) loss[n] = -logp;
+  const bool feasible = logp > NEG;
+
+  // ---- phase 2: gradient ----------------------------------------------------------
+  float* my = acc + warp * C;
+  for (int t = warp; t < T; t += CTC_WARPS) {
+    float* g = grad + ((size_t)t * N + n) * C;
+    if (t >= len || !feasible) {
+      for (int k = lane; k < C; k += 32) g[k] = 0.0f;
+      continue;
+    }
+    const float* row = logits + ((size_t)t * N + n) * C;
+    const float z = w_lse[t];
+    for (int k = lane; k < C; k += 32) my[k] = 0.0f;
+    float v[NJ], m = NEG;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int s = j * 32 + lane;
+      v[j] = (s < S) ? w_alpha[(size_t)t * s_max + s] + w_beta[(size_t)t * s_max + s] : NEG;
+      m = fmaxf(m, v[j]);
+    }
+    m = asr::warp_max(m);
+    __syncwarp();
+    float bsum = 0.0f;
+    if (m > NEG) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int s = j * 32 + lane;
+        if (s < S) {
+          const float e = expf(v[j] - m);
+          if (s & 1) atomicAdd(my + ext[s], e);   // label states (odd s)
+          else bsum += e;                          // blank states (even s)
+        }
+      }
+    }
+    bsum = asr::warp_sum(bsum);
+    if (lane == 0) atomicAdd(my + blank, bsum);
+    __syncwarp();
+    for (int k = lane; k < C; k += 32) {
+      const float lp = row[k] - z;
+      float occ = 0.0f;
+      if (my[k] > 0.0f) occ = my[k] * expf(m - lp - logp);
+      g[k] = grad_scale * (expf(lp) - occ);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- best path ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ctc_greedy_kernel(const float* __restrict__ logits, int T, int N, int C,
+                  const int* __restrict__ in_len, int blank, int merge,
+                  int* __restrict__ out_labels, int* __restrict__ out_len) {
+  __shared__ int s_arg[256];
+  __shared__ int s_wsum[8];
+  __shared__ int s_base, s_carry;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = min(max(in_len[n], 0), T);
+  int* outp = out_labels + (size_t)n * T;
+  if (tid == 0) { s_base = 0; s_carry = -1; }
+  __syncthreads();
+  for (int c0 = 0; c0 < len; c0 += 256) {
+    const int t = c0 + tid;
+    int arg = -1;
+    if (t < len) {
+      const float* row = logits + ((size_t)t * N + n) * C;
+      float best = row[0];
+      arg = 0;
+      for (int k = 1; k < C; ++k) {
+        const float v = row[k];
+        if (v > best) { best = v; arg = k; }   // first maximum wins
+      }
+    }
+    s_arg[tid] = arg;
+    __syncthreads();
+    const int prev = (tid > 0) ? s_arg[tid - 1] : s_carry;
+    const int keep = (t < len) && (arg != blank) && !(merge && arg == prev);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int wpre = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) s_wsum[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) wbase += s_wsum[w];
+      tot += s_wsum[w];
+    }
+    const int base = s_base;
+    if (keep) outp[base + wbase + wpre] = arg;
+    __syncthreads();
+    if (tid == 0) { s_base = base + tot; s_carry = s_arg[min(255, len - 1 - c0)]; }
+    __syncthreads();
+  }
+  const int total = s_base;
+  for (int i = total + tid; i < T; i += 256) outp[i] = -1;
+  if (tid == 0) out_len[n] = total;
+}
+
+}  // namespace
+
+extern "C" size_t asr_ctc_workspace_bytes(int32_t T, int32_t N, int32_t max_label_len) {
+  if (T <= 0 || N <= 0 || max_label_len < 0) return 0;
+  const size_t s_max = 2 * (size_t)max_label_len + 1;
+  return (size_t)N * (2 * (size_t)T * s_max + T) * sizeof(float);
+}
+
+extern "C" int32_t asr_ctc_loss_grad(const float* logits, int32_t T, int32_t N, int32_t C, const int32_t* in_len,
+                                     const int32_t* labels, const int32_t* label_off, int32_t max_label_len,
+                                     int32_t blank, float grad_scale, float* loss, float* grad, void* ws,
+                                     void* stream) {
+  ASR_CHECK_ARG(logits && in_len && labels && label_off && loss && grad && ws, "asr_ctc_loss_grad: null argument");
+  ASR_CHECK_ARG(T >= 1 && N >= 1 && C >= 2 && blank >= 0 && blank < C, "asr_ctc_loss_grad: bad shape T=%d N=%d C=%d", T, N, C);
+  ASR_CHECK_ARG(max_label_len >= 0 && max_label_len <= 255, "asr_ctc_loss_grad: max_label_len %d > 255", max_label_len);
+  const int s_max = 2 * max_label_len + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s_max <= 128) {
+    const size_t smem = (size_t)(3 * 32 * 4 + 4 + CTC_WARPS * C) * sizeof(float);
+    ctc_loss_grad_kernel<4><<<N, CTC_THREADS, smem, st>>>(logits, T, N, C, in_len, labels, label_off, s_max, blank,
+                                                           grad_scale, loss, grad, (float*)ws);
+  } else {
+    const size_t smem = (size_t)(3 * 32 * 16 + 4 + CTC_WARPS * C) * sizeof(float);
+    ctc_loss_grad_kernel<16><<<N, CTC_THREADS, smem, st>>>(logits, T, N, C, in_len, labels, label_off, s_max, blank,
+                                                            grad_scale, loss, grad, (float*)ws);
+  }
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+extern "C" int32_t asr_ctc_greedy(const float* logits, int32_t T, int32_t N, int32_t C, const int32_t* in_len,
+                                  int32_t blank, int32_t merge_repeated, int32_t* out_labels, int32_t* out_len,
+                                  void* stream) {
+  ASR_CHECK_ARG(logits && in_len && out_labels && out_len, "asr_ctc_greedy: null argument");
+  ASR_CHECK_ARG(T >= 1 && N >= 1 && C >= 1, "asr_ctc_greedy: bad shape");
+  ctc_greedy_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(logits, T, N, C, in_len, blank, merge_repeated, out_labels,
+                                                          out_len);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}

@@ -1,0 +1,110 @@
+// precision / layout helpers between the hot-path kernels (sm_100a).
+#include "common.cuh"
+
+namespace {
+
+template <typename T> __device__ __forceinline__ T cvt(float v);
+template <> __device__ __forceinline__ __half cvt<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, T* __restrict__ dst, int64_t ld_dst, int64_t rows,
+                 int cols) {
+  const int64_t total = rows * ld_dst;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int c = (int)(i - r * ld_dst);
+    dst[i] = cvt<T>(c < cols ? src[r * ld_src + c] : 0.0f);
+  }
+}
+
+// 32x32 tiles through shared memory: coalesced on both sides
+template <typename T>
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ src, int64_t ld_src, T* __restrict__ dst, int64_t ld_dst, int64_t rows,
+                      int cols) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = r0 + k;
+    const int c = c0 + tx;
+    tile[k][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < rows) dst[(int64_t)c * ld_dst + r] = cvt<T>(tile[tx][k]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
+  // each CTA: 32 columns x a slab of rows; 8 warps stride the rows; atomics to out (pre-zeroed)
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int64_t slab = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t rb = blockIdx.y * slab, re = min(rows, rb + slab);
+  float acc = 0.0f;
+  if (c < cols)
+    for (int64_t r = rb + ty; r < re; r += 8) acc += src[r * ld + c];
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][tx];
+    atomicAdd(out + c, s);
+  }
+}
+
+inline int grid_1d(int64_t total) {
+  const int64_t b = (total + 255) / 256;
+  return (int)(b < 148 * 8 ? (b < 1 ? 1 : b) : 148 * 8);
+}
+
+}  // namespace
+
+extern "C" int32_t asr_cast_rows(const float* src, int64_t ld_src, void* dst16, int64_t ld_dst, int64_t rows,
+                                 int32_t cols, int32_t dtype, void* stream) {
+  ASR_CHECK_ARG(src && dst16 && rows > 0 && cols > 0 && ld_dst >= cols && ld_src >= cols, "asr_cast_rows: bad argument");
+  const int grid = grid_1d(rows * ld_dst);
+  if (dtype == 0)
+    cast_rows_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst16, ld_dst, rows, cols);
+  else
+    cast_rows_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst16, ld_dst,
+                                                                            rows, cols);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+extern "C" int32_t asr_cast_transpose(const float* src, int64_t ld_src, void* dst16, int64_t ld_dst, int64_t rows,
+                                      int32_t cols, int32_t dtype, void* stream) {
+  ASR_CHECK_ARG(src && dst16 && rows > 0 && cols > 0 && ld_dst >= rows && ld_src >= cols,
+                "asr_cast_transpose: bad argument");
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  ASR_CHECK_ARG(grid.y <= 65535, "asr_cast_transpose: too many columns");
+  if (dtype == 0)
+    cast_transpose_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst16, ld_dst, rows, cols);
+  else
+    cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst16,
+                                                                                 ld_dst, rows, cols);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+extern "C" int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_t cols, float* out, void* stream) {
+  ASR_CHECK_ARG(src && out && rows > 0 && cols > 0 && ld >= cols, "asr_colsum: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  ASR_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), st));
+  int gy = (int)((rows + 511) / 512);
+  if (gy > 296) gy = 296;
+  dim3 grid((cols + 31) / 32, gy);
+  colsum_kernel<<<grid, 256, 0, st>>>(src, ld, rows, cols, out);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}

@@ -1,0 +1,365 @@
+"""Device engine: stacked BiLSTM -> Dense -> CTC on libasr_b200 kernels.
+
+Host code is PyTorch only for device memory, streams and torch.distributed; all
+arithmetic is the hand-written CUDA behind include/asr_b200.h (no torch ops on
+the compute path, no autograd, no CPU fallback).
+
+Mirrors the graph the reference builds in core/models.py:217-281 (brsmv1) /
+:55-73 (graves2006) + ctc_model (:31-52) and the optimiser set-up of
+train.py:133-143.  Internal layout is time-major [T, N, *].
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from ._lib import LstmBwdArgs, LstmFwdArgs, cur_stream, lib, ptr
+
+F16, BF16 = 0, 1
+OUT_F32, OUT_F16, OUT_BF16 = 0, 1, 2
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+@dataclass
+class ModelSpec:
+    num_features: int = 26
+    num_hiddens: int = 512
+    num_layers: int = 3
+    num_classes: int = 28
+    weight_decay: float = 0.0        # l2 on W, U of every LSTM and the Dense kernel (models.py:263-264,279)
+    name: str = "brsmv1"
+
+
+class ParamBucket:
+    """One flat fp32 parameter vector (+ grad, Adam m/v, l2 mask) with named views.
+
+    Per layer the order is Wf, Wb, Uf, Ub, bf, bb so that [Uf|Ub] is a contiguous
+    [2,H,4H] block and [bf|bb] a contiguous [2,4H] block (what the kernels take).
+    """
+
+    def __init__(self, spec: ModelSpec, device):
+        self.spec = spec
+        H, C = spec.num_hiddens, spec.num_classes
+        shapes = []
+        D = spec.num_features
+        for l in range(spec.num_layers):
+            shapes += [(f"l{l}.Wf", (D, 4 * H)), (f"l{l}.Wb", (D, 4 * H)),
+                       (f"l{l}.Uf", (H, 4 * H)), (f"l{l}.Ub", (H, 4 * H)),
+                       (f"l{l}.bf", (4 * H,)), (f"l{l}.bb", (4 * H,))]
+            D = 2 * H
+        shapes += [("dense.W", (D, C)), ("dense.b", (C,))]
+        self.shapes = dict(shapes)
+        self.offsets, off = {}, 0
+        for k, s in shapes:
+            self.offsets[k] = off
+            off += int(np.prod(s))
+            off = (off + 3) // 4 * 4                       # keep every tensor 16-byte aligned
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.decay = torch.zeros(off, dtype=torch.uint8, device=device)
+        for k in self.shapes:
+            if k.endswith((".Wf", ".Wb", ".Uf", ".Ub")) or k == "dense.W":
+                self._view(self.decay, k).fill_(1)
+
+    def _view(self, flat, k):
+        o, s = self.offsets[k], self.shapes[k]
+        return flat[o:o + int(np.prod(s))].view(*s)
+
+    def p(self, k):
+        return self._view(self.flat, k)
+
+    def g(self, k):
+        return self._view(self.grad, k)
+
+    def load(self, params: dict):
+        for k, v in params.items():
+            self.p(k).copy_(torch.as_tensor(np.asarray(v, dtype=np.float32)))
+
+    def export(self, which="flat") -> dict:
+        src = getattr(self, which)
+        return {k: self._view(src, k).detach().cpu().numpy().copy() for k in self.shapes}
+
+
+class AcousticEngine:
+    """Forward / backward / optimiser step for one rank."""
+
+    def __init__(self, spec: ModelSpec, device="cuda:0", seed=4321, init_params: dict | None = None):
+        self.spec = spec
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        lib.load()
+        self.params = ParamBucket(spec, self.device)
+        if init_params is None:
+            init_params = self.keras_init(spec, seed)
+        self.params.load(init_params)
+        self.step_count = 0
+        self._ws = {}
+        self._shape = None
+        self._sqnorm = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._flags = torch.zeros(lib.asr_lstm_flags_bytes() // 4, dtype=torch.int32, device=self.device)
+        self._weights_version = -1
+
+    # ------------------------------------------------------------------ init
+    @staticmethod
+    def keras_init(spec: ModelSpec, seed: int) -> dict:
+        """Keras-1.2.2 initialisers for LSTM(consume_less='gpu') and Dense:
+        glorot_uniform W, orthogonal(1.1) U, zero b with forget slice = 1."""
+        rng = np.random.RandomState(seed)
+        H, out = spec.num_hiddens, {}
+
+        def glorot(shape):
+            lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+            return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+        def orth(shape):
+            a = rng.normal(0.0, 1.0, shape)
+            u, _, v = np.linalg.svd(a, full_matrices=False)
+            q = u if u.shape == tuple(shape) else v
+            return (1.1 * q.reshape(shape)).astype(np.float32)
+
+        D = spec.num_features
+        for l in range(spec.num_layers):
+            for d in ("f", "b"):
+                out[f"l{l}.W{d}"] = glorot((D, 4 * H))
+                out[f"l{l}.U{d}"] = orth((H, 4 * H))
+                b = np.zeros(4 * H, np.float32)
+                b[H:2 * H] = 1.0
+                out[f"l{l}.b{d}"] = b
+            D = 2 * H
+        out["dense.W"] = glorot((D, spec.num_classes))
+        out["dense.b"] = np.zeros(spec.num_classes, np.float32)
+        return out
+
+    # ------------------------------------------------------------- workspace
+    def _buf(self, name, shape, dtype, zero=False):
+        t = self._ws.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(n, dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    def _alloc(self, T, N, training):
+        sp = self.spec
+        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        R = T * N
+        w = {}
+        D0 = _pad8(sp.num_features)
+        w["x16"] = self._buf("x16", (R, D0), torch.float16, zero=True)
+        w["zx"] = self._buf("zx", (R, 8 * H), torch.float32)
+        for l in range(L):
+            w[f"h16.{l}"] = self._buf(f"h16.{l}", (R, 2 * H), torch.float16)
+        w["logits"] = self._buf("logits", (T, N, Cc), torch.float32)
+        if training:
+            w["xT16"] = self._buf("xT16", (sp.num_features, R), torch.bfloat16)
+            for l in range(L):
+                w[f"hT16.{l}"] = self._buf(f"hT16.{l}", (2 * H, R), torch.bfloat16)
+                w[f"gates.{l}"] = self._buf(f"gates.{l}", (R, 8 * H), torch.float32)
+                w[f"cell.{l}"] = self._buf(f"cell.{l}", (R, 2 * H), torch.float32)
+            w["dlogits"] = self._buf("dlogits", (T, N, Cc), torch.float32)
+            w["dl16"] = self._buf("dl16", (R, _pad8(Cc)), torch.bfloat16, zero=True)
+            w["dlT16"] = self._buf("dlT16", (Cc, R), torch.bfloat16)
+            w["dhA"] = self._buf("dhA", (R, 2 * H), torch.float32)
+            w["dhB"] = self._buf("dhB", (R, 2 * H), torch.float32)
+            w["dz16"] = self._buf("dz16", (R, 8 * H), torch.bfloat16)
+            w["dzT16"] = self._buf("dzT16", (8 * H, R), torch.bfloat16)
+            w["loss"] = self._buf("loss", (N,), torch.float32)
+        return w
+
+    # ---------------------------------------------------- weight operand prep
+    def _prep_weights(self, training):
+        """16-bit tensor-core operands derived from the fp32 masters (once per step)."""
+        sp, P = self.spec, self.params
+        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        st = cur_stream()
+        D = sp.num_features
+        for l in range(L):
+            Dp = _pad8(D)
+            wt = self._buf(f"WcatT16.{l}", (8 * H, Dp), torch.float16, zero=True)     # [8H, D]  fwd B operand
+            for i, d in enumerate("fb"):
+                lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wt[i * 4 * H:]), Dp, D, 4 * H, F16, st)
+            if training and l > 0:
+                wc = self._buf(f"Wcat16.{l}", (D, 8 * H), torch.bfloat16)              # [D, 8H]  dX B operand
+                for i, d in enumerate("fb"):
+                    lib.asr_cast_rows(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wc[:, i * 4 * H:]), 8 * H, D, 4 * H, BF16, st)
+            D = 2 * H
+        dp = _pad8(Cc)
+        wd = self._buf("WdT16", (Cc, 2 * H), torch.float16)                            # [C, 2H] logits B operand
+        lib.asr_cast_transpose(ptr(P.p("dense.W")), Cc, ptr(wd), 2 * H, 2 * H, Cc, F16, st)
+        if training:
+            wdb = self._buf("Wd16", (2 * H, dp), torch.bfloat16, zero=True)            # [2H, Cpad] dTop B operand
+            lib.asr_cast_rows(ptr(P.p("dense.W")), Cc, ptr(wdb), dp, 2 * H, Cc, BF16, st)
+
+    def _gemm(self, din, dout, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, alpha=1.0, acc=0):
+        lib.asr_gemm_tn(din, dout, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(Cm), ldc, ptr(bias), float(alpha), acc,
+                        cur_stream())
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, feats_tm: torch.Tensor, training=False) -> torch.Tensor:
+        """feats_tm: f32 [T, N, F] time-major on device -> logits f32 [T, N, C]."""
+        sp, P = self.spec, self.params
+        T, N, Fd = feats_tm.shape
+        assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
+        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        R = T * N
+        w = self._alloc(T, N, training)
+        self._w, self._T, self._N = w, T, N
+        st = cur_stream()
+        self._prep_weights(training)
+        feats_tm = feats_tm.contiguous()
+        D0 = _pad8(Fd)
+        lib.asr_cast_rows(ptr(feats_tm), Fd, ptr(w["x16"]), D0, R, Fd, F16, st)
+        if training:
+            lib.asr_cast_transpose(ptr(feats_tm), Fd, ptr(w["xT16"]), R, R, Fd, BF16, st)
+        x16, D = w["x16"], D0
+        for l in range(L):
+            self._gemm(F16, OUT_F32, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, w["zx"], 8 * H)
+            a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(w["zx"]).value,
+                            bias=ptr(P.p(f"l{l}.bf")).value, U=ptr(P.p(f"l{l}.Uf")).value, U16=None,
+                            h16=ptr(w[f"h16.{l}"]).value,
+                            hT16=ptr(w[f"hT16.{l}"]).value if training else None, h32=None,
+                            gates=ptr(w[f"gates.{l}"]).value if training else None,
+                            cell=ptr(w[f"cell.{l}"]).value if training else None,
+                            flags=ptr(self._flags).value)
+            lib.asr_lstm_forward(C.byref(a), st)
+            x16, D = w[f"h16.{l}"], 2 * H
+        self._gemm(F16, OUT_F32, R, Cc, 2 * H, x16, 2 * H, self._ws["WdT16"], 2 * H, w["logits"], Cc,
+                   bias=P.p("dense.b"))
+        return w["logits"]
+
+    # ------------------------------------------------------------------- CTC
+    def ctc(self, logits, in_len, labels_flat, label_off, max_label_len, grad_scale=1.0, want_grad=True):
+        T, N, Cc = logits.shape
+        w = self._w
+        wsb = lib.asr_ctc_workspace_bytes(T, N, max_label_len)
+        ws = self._buf("ctc_ws", (wsb // 4 + 1,), torch.float32)
+        loss = w.get("loss") if "loss" in w else self._buf("loss", (N,), torch.float32)
+        grad = w["dlogits"] if want_grad else self._buf("dlogits", (T, N, Cc), torch.float32)
+        lib.asr_ctc_loss_grad(ptr(logits), T, N, Cc, ptr(in_len), ptr(labels_flat), ptr(label_off), max_label_len,
+                              Cc - 1, float(grad_scale), ptr(loss), ptr(grad), ptr(ws), cur_stream())
+        return loss, grad
+
+    def greedy(self, logits, in_len, merge_repeated=True):
+        T, N, Cc = logits.shape
+        out = self._buf("greedy_out", (N, T), torch.int32)
+        out_len = self._buf("greedy_len", (N,), torch.int32)
+        lib.asr_ctc_greedy(ptr(logits), T, N, Cc, ptr(in_len), Cc - 1, int(merge_repeated), ptr(out), ptr(out_len),
+                           cur_stream())
+        return out, out_len
+
+    def beam(self, logits, in_len, beam_width=100, merge_repeated=True):
+        T, N, Cc = logits.shape
+        wsb = lib.asr_ctc_beam_workspace_bytes(T, N, Cc, beam_width)
+        ws = self._buf("beam_ws", (wsb // 4 + 1,), torch.int32)
+        out = self._buf("beam_out", (N, T), torch.int32)
+        out_len = self._buf("beam_len", (N,), torch.int32)
+        lib.asr_ctc_beam(ptr(logits), T, N, Cc, ptr(in_len), Cc - 1, beam_width, int(merge_repeated), ptr(out),
+                         ptr(out_len), ptr(ws), cur_stream())
+        return out, out_len
+
+    # --------------------------------------------------------------- backward
+    def backward(self, dlogits: torch.Tensor):
+        """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad."""
+        sp, P, w = self.spec, self.params, self._w
+        T, N = self._T, self._N
+        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        R = T * N
+        st = cur_stream()
+        cp = _pad8(Cc)
+        lib.asr_cast_rows(ptr(dlogits), Cc, ptr(w["dl16"]), cp, R, Cc, BF16, st)
+        lib.asr_cast_transpose(ptr(dlogits), Cc, ptr(w["dlT16"]), R, R, Cc, BF16, st)
+        lib.asr_colsum(ptr(dlogits), Cc, R, Cc, ptr(P.g("dense.b")), st)
+        top = L - 1
+        # dWd [2H, C] = topT [2H, R] . dlT [C, R]^T
+        self._gemm(BF16, OUT_F32, 2 * H, Cc, R, w[f"hT16.{top}"], R, w["dlT16"], R, P.g("dense.W"), Cc)
+        # dTop [R, 2H] = dl16 [R, Cpad] . Wd16 [2H, Cpad]^T
+        dh, other = w["dhA"], w["dhB"]
+        self._gemm(BF16, OUT_F32, R, 2 * H, cp, w["dl16"], cp, self._ws["Wd16"], cp, dh, 2 * H)
+        for l in range(L - 1, -1, -1):
+            a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(w[f"gates.{l}"]).value,
+                            cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value, U16=None,
+                            dz16=ptr(w["dz16"]).value, dzT16=ptr(w["dzT16"]).value, dz32=None,
+                            dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value)
+            lib.asr_lstm_backward(C.byref(a), st)
+            D = sp.num_features if l == 0 else 2 * H
+            xT = w["xT16"] if l == 0 else w[f"hT16.{l - 1}"]
+            hT = w[f"hT16.{l}"]
+            dzT = w["dzT16"]
+            for i, d in enumerate("fb"):
+                # dW_dir [D, 4H] = xT [D, R] . dzT_dir [4H, R]^T
+                self._gemm(BF16, OUT_F32, D, 4 * H, R, xT, R, dzT[i * 4 * H:], R, P.g(f"l{l}.W{d}"), 4 * H)
+                # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
+                if T > 1:
+                    Kk = (T - 1) * N
+                    hA = hT[i * H:(i + 1) * H]
+                    dzB = dzT[i * 4 * H:(i + 1) * 4 * H]
+                    if i == 0:   # forward direction: h_{t-1} with dz_t
+                        Ap, Bp = hA, dzB[:, N:]
+                    else:        # reverse direction: h_{t+1} with dz_t
+                        Ap, Bp = hA[:, N:], dzB
+                    lib.asr_gemm_tn(BF16, OUT_F32, H, 4 * H, Kk, C.c_void_p(Ap.data_ptr()), R,
+                                    C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, st)
+                else:
+                    P.g(f"l{l}.U{d}").zero_()
+            if l > 0:
+                # dX [R, 2H] = dz16 [R, 8H] . Wcat16 [2H, 8H]^T
+                self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w["dz16"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
+                           other, 2 * H)
+                dh, other = other, dh
+
+    # -------------------------------------------------------------- optimiser
+    def optimizer_step(self, lr=1e-3, clipnorm=400.0, beta1=0.9, beta2=0.999, eps=1e-8, opt="adam",
+                       momentum=0.9):
+        P, st = self.params, cur_stream()
+        wd = float(self.spec.weight_decay)
+        mask = ptr(P.decay) if wd else None
+        lib.asr_grad_sqnorm(ptr(P.grad), ptr(P.flat), mask, P.numel, 1.0, wd, ptr(self._sqnorm), st)
+        self.step_count += 1
+        if opt == "adam":
+            lib.asr_adam_step(ptr(P.flat), ptr(P.grad), ptr(P.m), ptr(P.v), mask, P.numel, 1.0, wd,
+                              ptr(self._sqnorm), float(clipnorm or 0.0), float(lr), beta1, beta2, eps,
+                              self.step_count, st)
+        else:
+            lib.asr_sgd_step(ptr(P.flat), ptr(P.grad), ptr(P.m), mask, P.numel, 1.0, wd, ptr(self._sqnorm),
+                             float(clipnorm or 0.0), float(lr), float(momentum), st)
+
+    def grad_norm(self) -> float:
+        return math.sqrt(float(self._sqnorm.item()))
+
+    def lstm_status(self) -> int:
+        """0 = ok; non-zero = a persistent kernel's watchdog fired (see ASR_ERR_TIMEOUT)."""
+        return int(self._flags[64].item())
+
+    # ------------------------------------------------------------ whole step
+    def train_step(self, feats_tm, in_len, labels_flat, label_off, max_label_len, global_batch=None,
+                   allreduce=None, **opt):
+        """One optimisation step on time-major features; returns the per-utterance CTC loss tensor [N]."""
+        N = feats_tm.shape[1]
+        logits = self.forward(feats_tm, training=True)
+        loss, dlogits = self.ctc(logits, in_len, labels_flat, label_off, max_label_len,
+                                 grad_scale=1.0 / float(global_batch or N))
+        self.backward(dlogits)
+        if allreduce is not None:
+            allreduce(self.params.grad)
+        self.optimizer_step(**opt)
+        return loss
+
+
+def pack_labels(labels, device):
+    """list of int sequences -> (flat i32, offsets i32 [N+1], max_len) on device
+    (the sparse-label contract of datasets/dataset_generator.py:237-251)."""
+    lens = [len(l) for l in labels]
+    off = np.zeros(len(labels) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(lens)
+    flat = np.concatenate([np.asarray(l, dtype=np.int32) for l in labels]) if sum(lens) else np.zeros(1, np.int32)
+    return (torch.as_tensor(flat, device=device), torch.as_tensor(off, device=device), int(max(lens) if lens else 0))

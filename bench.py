@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — utterances/sec of the acoustic training hot path on B200 (BASELINE.json metric).
+
+Workload (configs[1] / C2): synthetic 16 kHz 10 s clips -> 26-dim MFCC (fused kernel) ->
+3 x BiLSTM-512 -> Dense-28 -> CTC loss+grad -> BPTT -> global-norm clip + Adam, batch 32 per GPU.
+N > 1: data parallel (configs[2] shape), one NCCL all-reduce of the flat gradient bucket per step.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference        # CPU arm: oracle port of the reference path on the host cores
+
+Prints ONE JSON line (see the task contract): value = device-resident throughput,
+e2e = through the public API with host pcm (pinned) -> H2D -> step -> D2H loss every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SECONDS, FS = 10.0, 16000
+F, H, L, C = 26, 512, 3, 28
+T_FRAMES = 999
+GFLOP_TRAIN_PER_UTT = 88.80     # fwd+dX+dW LSTM GEMMs + Dense, T=999
+METRIC = "utterances/sec (10 s, 26-MFCC, 3xBiLSTM-512, CTC)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(n, seed):
+    from oracle.model import synth_clip, synth_labels   # the *spec* of the synthetic workload (datasets/dummy.py)
+    pcm = np.stack([synth_clip(seed, i, SECONDS, FS) for i in range(n)])
+    labels = synth_labels(seed + 7, n, 50)
+    return pcm, labels
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_step(pcm, labels, params, state):
+    from oracle import mfcc as omf
+    from oracle import model as om
+    feat = omf.MFCC(num_cep=13, d=True, dd=False)
+    x, lens = omf.pad_batch([feat(c) for c in pcm])
+    _, ctc, grads, _ = om.loss_and_grads(params, x, lens, labels, weight_decay=1e-4, dtype=np.float32)
+    om.clip_adam_step(params, grads, state, lr=1e-3, clipnorm=400.0)
+    return float(ctc.mean())
+
+
+def cpu_arm(n_sample, steps, warmup):
+    from oracle import model as om
+    params = om.init_params(F, H, L, C, seed=4321)
+    pcm, labels = synth_batch(n_sample, 1234)
+    state = {}
+    for _ in range(warmup):
+        cpu_step(pcm, labels, params, state)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(pcm, labels, params, state)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return n_sample / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = 32
+    steps, warmup = max(1, min(args.steps, 2)), 0
+    val, dt = cpu_arm(n_sample, steps, warmup)
+    cores = os.cpu_count()
+    sample = f"all {n_sample} clips of one step (full 10 s, T=999), oracle port incl. MFCC+BPTT+clip+Adam, numpy BLAS threads = all cores"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "utt/s", "n_gpus": args.gpus, "steps": steps,
+           "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "C2: 10 s clips, 26-MFCC, 3xBiLSTM-512, Dense-28, CTC, Adam (CPU sample)"},
+           "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from asr_study_b200._lib import lib
+    from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
+    from asr_study_b200.preprocessing import audio
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    nb = args.batch
+    gb = nb * world
+    pcm_np, labels = synth_batch(nb, 1234 + 1000 * rank)
+    pcm_host = torch.from_numpy(pcm_np.reshape(-1)).pin_memory()
+    off_host = torch.arange(nb + 1, dtype=torch.int64) * pcm_np.shape[1]
+    pcm_dev = pcm_host.to(dev)
+    off_dev = off_host.to(dev)
+    flat, loff, mx = pack_labels(labels, dev)
+    feat = audio.MFCC(num_cep=13, d=True, dd=False)
+    eng = AcousticEngine(ModelSpec(F, H, L, C, weight_decay=1e-4), device=dev, seed=4321)
+    loss_host = torch.empty(nb, dtype=torch.float32).pin_memory()
+
+    def allreduce(g):
+        if world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+
+    def step(pcm):
+        x, lens = feat.batch(pcm, off_dev, t_max=T_FRAMES, time_major=True)
+        return eng.train_step(x, lens, flat, loff, mx, global_batch=gb, allreduce=allreduce, lr=1e-3, clipnorm=400.0)
+
+    def step_e2e():
+        pcm = pcm_host.to(dev, non_blocking=True)                 # H2D of this step's audio, inside the timed region
+        loss = step(pcm)
+        loss_host.copy_(loss, non_blocking=True)                   # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+        return loss_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(pcm_dev)
+    torch.cuda.synchronize()
+    if eng.lstm_status() != 0:
+        raise RuntimeError("persistent LSTM kernel watchdog fired during warm-up")
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.asr_launch_count()
+    ms = timed(lambda: step(pcm_dev), args.steps)
+    launches = (lib.asr_launch_count() - l0) // max(args.steps, 1)
+    clocks = sampler.stop()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    value = gb * args.steps / (ms / 1e3)
+    e2e = gb * args.steps / (ms_e2e / 1e3)
+
+    # per-kernel-class device time (instrumented pass, outside the timed region)
+    kern = kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch) if rank == 0 else {}
+    pk = peaks()
+    out = None
+    if rank == 0:
+        step_tf = value * GFLOP_TRAIN_PER_UTT / 1e3 / world                       # TFLOP/s per GPU
+        roof = {"bound": "tensor", "kernel": "whole step (LSTM-GEMM roofline, BASELINE.md section 4)",
+                "achieved": step_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": step_tf / pk["tf_sust"],
+                "peak_source": pk["src"] + " bf16_tflops_sustained", "traffic": None,
+                "mma_precision": "fp16 fwd / bf16 bwd operands, fp32 accumulate"}
+        if kern.get("lstm_fwd_ms"):
+            gf = 2 * 2.0 * T_FRAMES * nb * H * 4 * H / 1e9                       # one launch: both directions
+            roof["dominant_kernel"] = {"name": "lstm_fwd (per layer launch)", "gflop_per_launch": gf,
+                                       "ms_per_launch": kern["lstm_fwd_ms"] / L,
+                                       "achieved_tflops": gf / (kern["lstm_fwd_ms"] / L),
+                                       "frac": gf / (kern["lstm_fwd_ms"] / L) / pk["tf_burst"]}
+        out = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "fp16/bf16 tensor-core operands, fp32 accumulate+state",
+               "data": "synthetic",
+               "config": {"workload": "C2: synthetic 16 kHz 10 s clips, 26-MFCC, 3xBiLSTM-512, Dense-28, CTC, "
+                                      "Adam(1e-3, clipnorm 400), l2 1e-4, dropout 0", "per_gpu_batch": nb,
+                          "global_batch": gb, "frames": T_FRAMES, "parallelism": f"dp{world}",
+                          "l2_flush": "per-step working set ~4 GB >> 126 MB L2 (inputs larger than L2)"},
+               "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": int(pcm_host.numel() * 4),
+                       "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_ms": kern,
+               "final_loss_mean": float(loss_host.mean())}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if args.cpu_baseline:
+            n_sample = 16
+            v, dt = cpu_arm(n_sample, 1, 0)
+            out["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{n_sample} of the 32 clips, 1 step (full T=999), oracle port "
+                                             f"(numpy, BLAS threads = all cores), {dt:.1f} s"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch):
+    """CUDA-event time per kernel class over one step (separate pass; explains `value`)."""
+    res = {}
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def span(name, fn):
+        a, b = ev(), ev()
+        torch.cuda.synchronize()
+        a.record()
+        r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        res[name] = res.get(name, 0.0) + a.elapsed_time(b)
+        return r
+
+    x, lens = span("mfcc_ms", lambda: feat.batch(pcm_dev, off_dev, t_max=T_FRAMES, time_major=True))
+    import asr_study_b200.engine as E
+    keys = {"asr_lstm_forward": "lstm_fwd_ms", "asr_lstm_backward": "lstm_bwd_ms", "asr_gemm_tn": "gemm_ms",
+            "asr_ctc_loss_grad": "ctc_ms", "asr_adam_step": "adam_ms", "asr_grad_sqnorm": "adam_ms"}
+
+    class Tap:
+        def __init__(self, real):
+            self.real = real
+
+        def __getattr__(self, n):
+            f = getattr(self.real, n)
+            if not n.startswith("asr_") or n.endswith("_bytes") or n == "asr_launch_count":
+                return f
+            return lambda *a: span(keys.get(n, "other_ms"), lambda: f(*a))
+
+    real = E.lib
+    E.lib = Tap(real)
+    try:
+        eng.train_step(x, lens, flat, loff, mx, global_batch=gb, lr=1e-3, clipnorm=400.0)
+    finally:
+        E.lib = real
+    return {k: round(v, 4) for k, v in res.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

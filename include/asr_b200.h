@@ -1,0 +1,217 @@
+/*
+ * asr_b200.h — C ABI of libasr_b200.so: the B200-native acoustic hot path of
+ * igormq/asr-study (MFCC/log-mel -> stacked BiLSTM -> CTC loss/grad + decode).
+ *
+ * The reference has no FFI: its extension surface is Python duck typing over
+ * Keras/TF ops.  Each entry point below is what a binding for that path would
+ * call; the reference site it replaces is cited as file:line (relative to the
+ * reference repo).  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative asr_status on failure;
+ *     asr_last_error() returns a thread-local message for the last failure.
+ *   - all data pointers are CALLER-OWNED DEVICE pointers unless the name ends
+ *     in _host; `stream` is a cudaStream_t passed as void*.
+ *   - no hidden allocation on the hot path: scratch is passed in; sizes come
+ *     from the *_workspace_bytes queries.  Plans own small constant tables.
+ *   - re-entrant; host threads may call concurrently on different streams.
+ *   - internal activation layout is TIME-MAJOR [T, N, *] (what TF's CTC ops
+ *     consume after the reference's own transpose, core/ctc_utils.py:39,69).
+ */
+#ifndef ASR_B200_H
+#define ASR_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ASR_OK = 0,
+  ASR_ERR_INVALID = -1,      /* bad argument / unsupported configuration   */
+  ASR_ERR_CUDA = -2,         /* a CUDA runtime call failed                  */
+  ASR_ERR_UNSUPPORTED = -3,  /* valid in the reference, not built here yet  */
+  ASR_ERR_TIMEOUT = -4       /* a persistent kernel's watchdog fired        */
+} asr_status;
+
+const char* asr_last_error(void);
+int32_t asr_version(void);
+/* number of kernels launched by this library in this process (for bench.py's
+ * gpu_launches claim) */
+int64_t asr_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * K1  fused MFCC / log-mel front end
+ * replaces preprocessing/audio.py:41-75 (Feature.__call__, _standarize),
+ *          :223-253 (FBank._call), :339-367 (MFCC._call), :419-442 (LogFbank)
+ *          preprocessing/audio_utils.py:17-50,98-120,143-173
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  float fs;             /* 16000                          audio.py:28  */
+  float win_len;        /* 0.025 s                        audio.py:180 */
+  float win_step;       /* 0.010 s                                     */
+  int32_t num_filt;     /* 40                                          */
+  int32_t nfft;         /* 512 (only value built)                      */
+  float low_freq;       /* 20                                          */
+  float high_freq;      /* 7800                                        */
+  float pre_emph;       /* 0.97                                        */
+  int32_t kind;         /* 0 = mfcc, 1 = logfbank, 2 = fbank (linear)  */
+  int32_t num_cep;      /* 13                              audio.py:324 */
+  int32_t cep_lifter;   /* 22                                          */
+  int32_t append_energy;/* mfcc: c0 <- log(energy+eps); logfbank: extra col */
+  int32_t d, dd;        /* deltas / delta-deltas                       */
+  int32_t mean_norm, var_norm; /* per-utterance CMVN       audio.py:70-75 */
+  float eps;            /* 1e-8                                        */
+  int32_t stride;       /* feats[::stride]                 audio.py:82  */
+  int32_t num_context;  /* must be 0 (ASR_ERR_UNSUPPORTED otherwise)   */
+} asr_mfcc_config;
+
+typedef struct asr_mfcc_plan asr_mfcc_plan;
+
+int32_t asr_mfcc_plan_create(const asr_mfcc_config* cfg, asr_mfcc_plan** out);
+void    asr_mfcc_plan_destroy(asr_mfcc_plan* plan);
+int32_t asr_mfcc_num_feats(const asr_mfcc_plan* plan);
+/* frames for a clip of `num_samples` after stride (audio_utils.py:30-33) */
+int32_t asr_mfcc_num_frames(const asr_mfcc_plan* plan, int64_t num_samples);
+/* bytes of zero-initialised device scratch for a batch of n utterances */
+size_t  asr_mfcc_workspace_bytes(const asr_mfcc_plan* plan, int32_t n);
+/*
+ * pcm      f32 [sum samples], utterance i = pcm[offsets[i] .. offsets[i+1])
+ * offsets  i64 [n+1] (device)
+ * out      f32 [n, t_max, F] (time_major=0, the DatasetIterator batch contract,
+ *          datasets/dataset_generator.py:223-235) or [t_max, n, F] (time_major=1);
+ *          frames >= out_len[i] are zero-filled ('post' padding)
+ * out_len  i32 [n]
+ * ws       workspace, zeroed once by the caller (the kernel leaves it zeroed)
+ */
+int32_t asr_mfcc_forward(const asr_mfcc_plan* plan, const float* pcm,
+                         const int64_t* offsets, int32_t n, int32_t t_max,
+                         float* out, int32_t* out_len, int32_t time_major,
+                         void* ws, void* stream);
+/* host convenience for Feature.__call__ on ONE ndarray (audio.py:60-65):
+ * copies in, runs asr_mfcc_forward, copies out.  out_host f32 [T, F]. */
+int32_t asr_mfcc_forward_host(const asr_mfcc_plan* plan, const float* pcm_host,
+                              int64_t num_samples, float* out_host);
+
+/* ------------------------------------------------------------------------- *
+ * K2/K5  TN GEMM on tcgen05:  C[M,N] (+)= A[M,K] * B[N,K]^T
+ * replaces K.dot(x*B_W, W) hoisted out of the step (core/layers.py:439), the
+ * TimeDistributed(Dense) (core/models.py:71,278) and the autodiff dW/dU/dX.
+ * A, B: 16-bit (dtype_in: 0 = fp16, 1 = bf16), K-major, lda/ldb in elements
+ * (multiples of 8, 16-byte aligned rows).  C: dtype_out 0 = fp32, 1 = fp16,
+ * 2 = bf16, row-major ldc.  bias (f32 [N]) optional.  accumulate != 0 adds
+ * into fp32 C.
+ * ------------------------------------------------------------------------- */
+int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N,
+                    int32_t K, const void* A, int64_t lda, const void* B,
+                    int64_t ldb, void* C, int64_t ldc, const float* bias,
+                    float alpha, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K3/K4  persistent BiLSTM recurrence (both directions in one launch)
+ * replaces LSTM.step under K.rnn / Bidirectional (core/layers.py:432-469;
+ * core/models.py:68-70, 261-271) and its autodiff.  Keras-1 semantics: gate
+ * order i,f,c,o; hard_sigmoid gates; tanh cell; h0=c0=0; no masking; the
+ * reverse direction consumes t = T-1..0.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t T, N, H;          /* H % 32 == 0, N <= 64                           */
+  int32_t training;         /* 1: save gates/c (and transposed copies)        */
+  const float* zx;          /* f32 [T, N, 2, 4H]  x_t*W  (no bias)            */
+  const float* bias;        /* f32 [2, 4H]                                    */
+  const float* U;           /* f32 [2, H, 4H]  master recurrent weights       */
+  const void*  U16;         /* fp16 [2, 4H, H]  U^T (tensor-core operand)     */
+  void*  h16;               /* fp16 [T, N, 2H]  layer output fwd|bwd          */
+  void*  hT16;              /* bf16 [2H, T*N]   transposed copy (training)    */
+  float* h32;               /* f32 [T, N, 2H]   optional fp32 output          */
+  float* gates;             /* f32 [T, N, 2, 4H] activated i,f,g,o (training) */
+  float* cell;              /* f32 [T, N, 2, H]  c_t             (training)   */
+  int32_t* flags;           /* device scratch, asr_lstm_flags_bytes(), zeroed */
+} asr_lstm_fwd_args;
+
+typedef struct {
+  int32_t T, N, H;
+  const float* dh;          /* f32 [T, N, 2H]  dL/d(layer output)             */
+  const float* gates;       /* saved by forward                               */
+  const float* cell;
+  const float* U;           /* f32 [2, H, 4H]                                 */
+  const void*  U16;         /* bf16 [2, H, 4H] (tensor-core operand)          */
+  void*  dz16;              /* bf16 [T, N, 2, 4H]                             */
+  void*  dzT16;             /* bf16 [2*4H, T*N]                               */
+  float* dz32;              /* f32 [T, N, 2, 4H] optional                     */
+  float* dbias;             /* f32 [2, 4H]  (overwritten)                     */
+  int32_t* flags;
+} asr_lstm_bwd_args;
+
+size_t  asr_lstm_flags_bytes(void);
+int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream);
+int32_t asr_lstm_backward(const asr_lstm_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K6  CTC loss + gradient      replaces tf.nn.ctc_loss, core/ctc_utils.py:68-70
+ * logits f32 [T, N, C] time-major; softmax applied inside; blank = C-1 in the
+ * reference.  labels: flat i32 + offsets i32 [N+1].  loss f32 [N];
+ * grad f32 [T, N, C] = grad_scale * dloss_n/dlogits (0 for t >= in_len[n]).
+ * ------------------------------------------------------------------------- */
+size_t  asr_ctc_workspace_bytes(int32_t T, int32_t N, int32_t max_label_len);
+int32_t asr_ctc_loss_grad(const float* logits, int32_t T, int32_t N, int32_t C,
+                          const int32_t* in_len, const int32_t* labels,
+                          const int32_t* label_off, int32_t max_label_len,
+                          int32_t blank, float grad_scale, float* loss,
+                          float* grad, void* ws, void* stream);
+
+/* K7  best-path decode         replaces tf.nn.ctc_greedy_decoder, ctc_utils.py:42
+ * out_labels i32 [N, T] (-1 padded, like to_dense, core/layers_utils.py:54-57),
+ * out_len i32 [N]. */
+int32_t asr_ctc_greedy(const float* logits, int32_t T, int32_t N, int32_t C,
+                       const int32_t* in_len, int32_t blank, int32_t merge_repeated,
+                       int32_t* out_labels, int32_t* out_len, void* stream);
+
+/* K8  prefix beam search       replaces tf.nn.ctc_beam_search_decoder
+ * (top_paths = 1), core/ctc_utils.py:44-50; utils/core_utils.py:70-71 */
+size_t  asr_ctc_beam_workspace_bytes(int32_t T, int32_t N, int32_t C, int32_t beam_width);
+int32_t asr_ctc_beam(const float* logits, int32_t T, int32_t N, int32_t C,
+                     const int32_t* in_len, int32_t blank, int32_t beam_width,
+                     int32_t merge_repeated, int32_t* out_labels,
+                     int32_t* out_len, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K9  global-norm clip + Adam / SGD-momentum   replaces Keras-1 optimizers via
+ * train.py:133-137.  One flat fp32 bucket.  decay_mask (u8 [n] or NULL) marks
+ * elements that carry the l2(weight_decay) regulariser (core/models.py:263-264,
+ * 279): g <- grad_scale*g + 2*wd*p for those.  asr_grad_sqnorm writes
+ * sum(g^2) (f64) to *sqnorm; asr_adam_step reads it for the clip.
+ * ------------------------------------------------------------------------- */
+int32_t asr_grad_sqnorm(const float* grad, const float* param,
+                        const uint8_t* decay_mask, int64_t n, float grad_scale,
+                        float weight_decay, double* sqnorm, void* stream);
+int32_t asr_adam_step(float* param, const float* grad, float* m, float* v,
+                      const uint8_t* decay_mask, int64_t n, float grad_scale,
+                      float weight_decay, const double* sqnorm, float clipnorm,
+                      float lr, float beta1, float beta2, float eps,
+                      int32_t step, void* stream);
+int32_t asr_sgd_step(float* param, const float* grad, float* mom,
+                     const uint8_t* decay_mask, int64_t n, float grad_scale,
+                     float weight_decay, const double* sqnorm, float clipnorm,
+                     float lr, float momentum, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * layout / precision helpers used between the kernels above
+ * ------------------------------------------------------------------------- */
+/* dst16[r, c] = cast(src[r, c]) for r<rows, c<cols; zero-fills c in [cols, ld_dst).
+ * dtype 0 = fp16, 1 = bf16 */
+int32_t asr_cast_rows(const float* src, int64_t ld_src, void* dst16, int64_t ld_dst,
+                      int64_t rows, int32_t cols, int32_t dtype, void* stream);
+/* dst16[c, r] = cast(src[r, c])  (transpose), ld_dst >= rows */
+int32_t asr_cast_transpose(const float* src, int64_t ld_src, void* dst16, int64_t ld_dst,
+                           int64_t rows, int32_t cols, int32_t dtype, void* stream);
+/* out[c] = sum_r src[r, c]  (fp32; bias gradients) */
+int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_t cols,
+                   float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASR_B200_H */

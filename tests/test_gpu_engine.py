@@ -1,0 +1,84 @@
+"""End-to-end parity of the hot path through the engine: features -> logits -> CTC -> BPTT ->
+clip+Adam, CUDA vs oracle on the same seeded inputs (C1-like small config and a mid-size one)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc as oc
+from oracle import model as om
+from tests.util_gpu import dev, norm_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(N, T, F, H, L, C, seed, wd=1e-4):
+    from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
+    rng = np.random.RandomState(seed)
+    params = om.init_params(F, H, L, C, seed=seed)
+    for k in params:                                   # move away from the all-zero-bias symmetric point
+        params[k] = (params[k] + 0.05 * rng.randn(*params[k].shape)).astype(np.float32)
+    x = rng.randn(N, T, F).astype(np.float32)
+    lens = np.array([T] + [int(rng.randint(T // 2, T + 1)) for _ in range(N - 1)], np.int32)
+    labels = [rng.randint(0, C - 1, size=rng.randint(2, max(3, T // 4))).astype(np.int32) for _ in range(N)]
+    eng = AcousticEngine(ModelSpec(F, H, L, C, weight_decay=wd), init_params=params)
+    return eng, params, x, lens, labels, pack_labels
+
+
+@pytest.mark.parametrize("N,T,F,H,L", [(8, 30, 26, 64, 2), (8, 25, 26, 104, 1), (16, 60, 26, 256, 3)])
+def test_forward_loss_decode_parity(N, T, F, H, L):
+    C = 28
+    eng, params, x, lens, labels, pack = _setup(N, T, F, H, L, C, seed=N + T)
+    logits = eng.forward(dev(np.ascontiguousarray(x.transpose(1, 0, 2))), training=False)
+    ref_logits, _ = om.forward(params, x, dtype=np.float64)
+    got = logits.cpu().numpy().transpose(1, 0, 2)
+    assert norm_err(got, ref_logits) < 1e-3                                  # activations: 1e-3 (north_star)
+    flat, off, mx = pack(labels, "cuda")
+    loss, _ = eng.ctc(logits, dev(lens), flat, off, mx, want_grad=False)
+    rl, _ = oc.ctc_loss_grad(ref_logits, lens, labels)
+    np.testing.assert_allclose(loss.cpu().numpy(), rl, rtol=1e-3)            # CTC loss: 1e-3 rel
+    out, out_len = eng.greedy(logits, dev(lens))
+    ref_dec = oc.greedy_decode(got, lens)                                    # same logits -> bit-exact labels
+    out, out_len = out.cpu().numpy(), out_len.cpu().numpy()
+    for n in range(N):
+        assert out[n, :out_len[n]].tolist() == ref_dec[n]
+
+
+@pytest.mark.parametrize("N,T,F,H,L", [(8, 20, 26, 64, 2), (8, 40, 26, 128, 3)])
+def test_train_step_gradients_and_adam_parity(N, T, F, H, L):
+    C = 28
+    eng, params, x, lens, labels, pack = _setup(N, T, F, H, L, C, seed=7 * N + T)
+    flat, off, mx = pack(labels, "cuda")
+    feats = dev(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    loss = eng.train_step(feats, dev(lens), flat, off, mx, lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    assert eng.lstm_status() == 0
+    total, ctc, grads, _ = om.loss_and_grads(params, x, lens, labels, weight_decay=0.0, dtype=np.float64)
+    np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
+    got = eng.params.export("grad")
+    for k, g in grads.items():
+        # 16-bit tensor-core operands (bf16 in the backward GEMMs): 3e-2 norm-wise per tensor
+        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+    # optimiser: replay the oracle's clip+Adam on the DEVICE gradients -> isolates K9
+    p0 = {k: v.copy() for k, v in params.items()}
+    st = {}
+    g_with_l2 = {k: got[k] + (2e-4 * params[k] if (k.endswith(("Wf", "Wb", "Uf", "Ub")) or k == "dense.W") else 0)
+                 for k in got}
+    n = om.clip_adam_step(p0, g_with_l2, st, lr=1e-3, clipnorm=400.0)
+    assert abs(eng.grad_norm() - n) <= 1e-4 * n
+    newp = eng.params.export("flat")
+    for k in p0:
+        np.testing.assert_allclose(newp[k], p0[k], atol=2e-6)
+
+
+def test_clipnorm_engages():
+    C = 28
+    eng, params, x, lens, labels, pack = _setup(8, 20, 26, 64, 1, C, seed=3, wd=0.0)
+    flat, off, mx = pack(labels, "cuda")
+    feats = dev(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    eng.train_step(feats, dev(lens), flat, off, mx, lr=1e-3, clipnorm=1e-3)
+    got = eng.params.export("grad")
+    p0 = {k: v.copy() for k, v in params.items()}
+    om.clip_adam_step(p0, got, {}, lr=1e-3, clipnorm=1e-3)
+    newp = eng.params.export("flat")
+    for k in p0:
+        np.testing.assert_allclose(newp[k], p0[k], atol=2e-6)

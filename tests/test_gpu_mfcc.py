@@ -1,0 +1,107 @@
+"""K1 parity: fused MFCC/log-mel CUDA kernel (through the C ABI) vs the reference-pinned
+golden vectors and the oracle.  Tolerance: 1e-3 on CMVN-normalised features (north_star);
+measured error is ~1e-5 (fp32 kernel vs fp64 reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mfcc as om
+from tests.util_gpu import dev
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "mfcc_reference.npz"))
+TOL = 1e-3
+
+
+def _clip(seed, secs):
+    return np.random.RandomState(int(seed)).randn(int(np.floor(secs * 16000))).astype(np.float32)
+
+
+def _feat(kind):
+    from asr_study_b200.preprocessing import audio
+    return {"mfcc26": audio.MFCC(num_cep=13, d=True, dd=False), "mfcc39": audio.MFCC(),
+            "logfbank40": audio.LogFbank(),
+            "mfcc13_raw": audio.MFCC(d=False, dd=False, mean_norm=False, var_norm=False)}[kind]
+
+
+@pytest.mark.parametrize("kind", ["mfcc26", "mfcc39", "logfbank40", "mfcc13_raw"])
+def test_single_clip_matches_reference_golden(kind):
+    f = _feat(kind)
+    for seed, secs in zip(G["clip_seeds"], G["clip_seconds"]):
+        got = f(_clip(seed, secs))
+        ref = G[f"{kind}_{int(seed)}"]
+        assert got.shape == ref.shape and got.dtype == np.float32
+        if ref.shape[0] == 1 and kind != "mfcc13_raw":
+            assert np.all(got == 0)          # one frame: CMVN gives exactly 0
+            continue
+        scale = max(1.0, np.abs(ref).max()) if kind == "mfcc13_raw" else 1.0
+        assert np.abs(got - ref).max() <= TOL * scale, (kind, seed, np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("time_major", [True, False])
+def test_ragged_batch_padding_and_lengths(time_major):
+    from asr_study_b200.preprocessing import audio
+    f = audio.MFCC(num_cep=13, d=True, dd=False)
+    secs = [1.0, 0.31, 2.05, 0.02, 1.5]
+    clips = [_clip(100 + i, s) for i, s in enumerate(secs)]
+    off = np.zeros(len(clips) + 1, np.int64)
+    off[1:] = np.cumsum([len(c) for c in clips])
+    feats, lens = f.batch(dev(np.concatenate(clips)), dev(off), time_major=time_major)
+    feats, lens = feats.cpu().numpy(), lens.cpu().numpy()
+    o = om.MFCC(num_cep=13, d=True, dd=False)
+    ref = [o(c) for c in clips]
+    assert lens.tolist() == [r.shape[0] for r in ref]
+    x, _ = om.pad_batch(ref)
+    got = feats.transpose(1, 0, 2) if time_major else feats
+    assert got.shape == x.shape
+    assert np.abs(got - x).max() <= TOL
+    for i, r in enumerate(ref):
+        assert np.all(got[i, r.shape[0]:] == 0)          # 'post' zero padding
+
+
+def test_stride_and_larger_tmax():
+    from asr_study_b200.preprocessing import audio
+    f = audio.LogFbank(stride=2, append_energy=True, d=True, dd=True)
+    o = om.LogFbank(stride=2, append_energy=True, d=True, dd=True)
+    c = _clip(7, 1.234)
+    ref = o(c)
+    got = f(c)
+    assert got.shape == ref.shape == (f.num_frames(len(c)), 123)
+    assert np.abs(got - ref).max() <= TOL
+    off = dev(np.array([0, len(c)], np.int64))
+    feats, lens = f.batch(dev(c), off, t_max=ref.shape[0] + 37, time_major=False)
+    assert int(lens[0]) == ref.shape[0]
+    assert np.abs(feats[0, :ref.shape[0]].cpu().numpy() - ref).max() <= TOL
+    assert torch.all(feats[0, ref.shape[0]:] == 0)
+
+
+def test_full_size_10s_clip_properties():
+    """BASELINE size (10 s -> 999 x 26): shape, CMVN invariants, idempotent re-run (workspace left clean)."""
+    from asr_study_b200.preprocessing import audio
+    f = audio.MFCC(num_cep=13, d=True, dd=False)
+    n = 8
+    clips = [_clip(1234 + i, 10.0) for i in range(n)]
+    off = dev(np.arange(n + 1, dtype=np.int64) * 160000)
+    pcm = dev(np.concatenate(clips))
+    a, la = f.batch(pcm, off)
+    b, lb = f.batch(pcm, off)
+    assert a.shape == (999, n, 26) and la.tolist() == [999] * n
+    assert torch.equal(a, b)
+    x = a.double()
+    assert x.mean(dim=0).abs().max().item() < 1e-4
+    assert (x.std(dim=0, unbiased=False) - 1).abs().max().item() < 1e-4
+    ref = om.MFCC(num_cep=13, d=True, dd=False)(clips[3])
+    assert np.abs(a[:, 3].cpu().numpy() - ref).max() <= TOL
+
+
+def test_errors_are_loud():
+    from asr_study_b200.preprocessing import audio
+    from asr_study_b200 import AsrError
+    with pytest.raises(ValueError):
+        audio.MFCC(high_freq=9000)                      # audio.py:186-187
+    with pytest.raises(TypeError):
+        audio.MFCC()("some.wav")
+    with pytest.raises(AsrError):
+        audio.MFCC(num_context=2)(np.zeros(1000, np.float32))
