@@ -45,15 +45,21 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
   const int S = 2 * L + 1;
   const float NEG = -CUDART_INF_F;
 
-  float* w_alpha = ws + (size_t)n * ((size_t)2 * T * s_max + T);
+  // per-utterance workspace: alpha[T][s_max], beta[T][s_max], lse[T] (f32) then offA[T], offB[T] (f64).
+  // alpha/beta rows are stored RELATIVE to a per-frame offset (row max = 0) that is accumulated in
+  // fp64, so fp32 resolution applies to O(1) magnitudes instead of O(T) log-probabilities.
+  const size_t fl_per = ((size_t)2 * T * s_max + T + 1) & ~(size_t)1;
+  float* w_alpha = ws + (size_t)n * (fl_per + 4 * (size_t)T);
   float* w_beta = w_alpha + (size_t)T * s_max;
   float* w_lse = w_beta + (size_t)T * s_max;
+  double* w_offA = reinterpret_cast<double*>(w_alpha + fl_per);
+  double* w_offB = w_offA + T;
 
   int* ext = reinterpret_cast<int*>(sm);            // [32*NJ]
   float* rowA = sm + 32 * NJ;                        // [32*NJ + 2] alpha exchange (2 pad in front)
   float* rowB = rowA + 32 * NJ + 2;                  // [32*NJ + 2] beta exchange (2 pad at end)
   float* acc = rowB + 32 * NJ + 2;                   // [CTC_WARPS][C]
-  __shared__ float s_logp;
+  __shared__ double s_logp;
 
   for (int s = tid; s < 32 * NJ; s += CTC_THREADS)
     ext[s] = (s < S && (s & 1)) ? labels[l0 + (s >> 1)] : blank;
@@ -97,8 +103,23 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
       for (int j = 0; j < NJ; ++j) {
         const int s = j * 32 + lane;
         a[j] = (s < 2 && s < S) ? row[lab[j]] - z : NEG;
-        if (s < S) w_alpha[s] = a[j];
       }
+    }
+    double offA = 0.0;
+    {
+      float m = NEG;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) m = fmaxf(m, a[j]);
+      m = asr::warp_max(m);
+      if (m > NEG) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) a[j] -= m;
+        offA += (double)m;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (j * 32 + lane < S) w_alpha[j * 32 + lane] = a[j];
+      if (lane == 0) w_offA[0] = offA;
     }
     if (len > 1) {
       const float* row = logits + ((size_t)1 * N + n) * C;
@@ -123,7 +144,21 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
         const float p2 = skip[j] ? prev[s - 2] : NEG;
         const float v = lse3(a[j], p1, p2) + (x[j] - z);
         a[j] = (s < S) ? v : NEG;
-        if (s < S) w_alpha[(size_t)t * s_max + s] = a[j];
+      }
+      {
+        float m = NEG;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) m = fmaxf(m, a[j]);
+        m = asr::warp_max(m);
+        if (m > NEG) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) a[j] -= m;
+          offA += (double)m;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (j * 32 + lane < S) w_alpha[(size_t)t * s_max + j * 32 + lane] = a[j];
+        if (lane == 0) w_offA[t] = offA;
       }
       __syncwarp();
       if (t + 1 < len) {
@@ -135,7 +170,10 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
 #pragma unroll
     for (int j = 0; j < NJ; ++j) prev[j * 32 + lane] = a[j];
     __syncwarp();
-    if (lane == 0) s_logp = (S > 1) ? lse2(prev[S - 1], prev[S - 2]) : prev[S - 1];
+    if (lane == 0) {
+      const float tail = (S > 1) ? lse2(prev[S - 1], prev[S - 2]) : prev[S - 1];
+      s_logp = (tail > NEG) ? offA + (double)tail : -(double)CUDART_INF;
+    }
   } else if (warp == 1) {
     bool skip[NJ];
     int lab[NJ];
@@ -156,8 +194,23 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
       for (int j = 0; j < NJ; ++j) {
         const int s = j * 32 + lane;
         b[j] = (s < S && s >= S - 2) ? row[lab[j]] - z : NEG;
-        if (s < S) w_beta[(size_t)(len - 1) * s_max + s] = b[j];
       }
+    }
+    double offB = 0.0;
+    {
+      float m = NEG;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) m = fmaxf(m, b[j]);
+      m = asr::warp_max(m);
+      if (m > NEG) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) b[j] -= m;
+        offB += (double)m;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (j * 32 + lane < S) w_beta[(size_t)(len - 1) * s_max + j * 32 + lane] = b[j];
+      if (lane == 0) w_offB[len - 1] = offB;
     }
     if (len > 1) {
       const float* row = logits + ((size_t)(len - 2) * N + n) * C;
@@ -182,7 +235,21 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
         const float p2 = skip[j] ? nxt[s + 2] : NEG;
         const float v = lse3(b[j], p1, p2) + (x[j] - z);
         b[j] = (s < S) ? v : NEG;
-        if (s < S) w_beta[(size_t)t * s_max + s] = b[j];
+      }
+      {
+        float m = NEG;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) m = fmaxf(m, b[j]);
+        m = asr::warp_max(m);
+        if (m > NEG) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) b[j] -= m;
+          offB += (double)m;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (j * 32 + lane < S) w_beta[(size_t)t * s_max + j * 32 + lane] = b[j];
+        if (lane == 0) w_offB[t] = offB;
       }
       __syncwarp();
       if (t > 0) {
@@ -193,9 +260,9 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
   }
   __syncthreads();
 
-  const float logp = s_logp;
-  if (tid == 0) loss[n] = -logp;
-  const bool feasible = logp > NEG;
+  const double logp = s_logp;
+  if (tid == 0) loss[n] = (float)(-logp);
+  const bool feasible = logp > -(double)CUDART_INF;
 
   // ---- phase 2: gradient ----------------------------------------------------------
   float* my = acc + warp * C;
@@ -207,6 +274,7 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
     }
     const float* row = logits + ((size_t)t * N + n) * C;
     const float z = w_lse[t];
+    const float kf = (float)(w_offA[t] + w_offB[t] - logp);   // frame constant, O(1) after the fp64 cancellation
     for (int k = lane; k < C; k += 32) my[k] = 0.0f;
     float v[NJ], m = NEG;
 #pragma unroll
@@ -235,7 +303,7 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
     for (int k = lane; k < C; k += 32) {
       const float lp = row[k] - z;
       float occ = 0.0f;
-      if (my[k] > 0.0f) occ = my[k] * expf(m - lp - logp);
+      if (my[k] > 0.0f) occ = my[k] * expf(m + kf - lp);
       g[k] = grad_scale * (expf(lp) - occ);
     }
     __syncwarp();
@@ -296,7 +364,8 @@ ctc_greedy_kernel(const float* __restrict__ logits, int T, int N, int C,
 extern "C" size_t asr_ctc_workspace_bytes(int32_t T, int32_t N, int32_t max_label_len) {
   if (T <= 0 || N <= 0 || max_label_len < 0) return 0;
   const size_t s_max = 2 * (size_t)max_label_len + 1;
-  return (size_t)N * (2 * (size_t)T * s_max + T) * sizeof(float);
+  const size_t fl_per = ((size_t)2 * T * s_max + T + 1) & ~(size_t)1;
+  return (size_t)N * (fl_per + 4 * (size_t)T) * sizeof(float);
 }
 
 extern "C" int32_t asr_ctc_loss_grad(const float* logits, int32_t T, int32_t N, int32_t C, const int32_t* in_len,

@@ -11,11 +11,14 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, T* __restrict__ dst, int64_t ld_dst, int64_t rows,
                  int cols) {
-  const int64_t total = rows * ld_dst;
+  // writes cols columns per row and zero-fills up to the next multiple of 8 (the 16-byte K padding
+  // the GEMM operands need); never touches anything beyond that, so dst may be a column sub-block.
+  const int cp = min((int64_t)((cols + 7) / 8 * 8), ld_dst);
+  const int64_t total = rows * cp;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / ld_dst;
-    const int c = (int)(i - r * ld_dst);
-    dst[i] = cvt<T>(c < cols ? src[r * ld_src + c] : 0.0f);
+    const int64_t r = i / cp;
+    const int c = (int)(i - r * cp);
+    dst[r * ld_dst + c] = cvt<T>(c < cols ? src[r * ld_src + c] : 0.0f);
   }
 }
 
@@ -72,7 +75,7 @@ inline int grid_1d(int64_t total) {
 extern "C" int32_t asr_cast_rows(const float* src, int64_t ld_src, void* dst16, int64_t ld_dst, int64_t rows,
                                  int32_t cols, int32_t dtype, void* stream) {
   ASR_CHECK_ARG(src && dst16 && rows > 0 && cols > 0 && ld_dst >= cols && ld_src >= cols, "asr_cast_rows: bad argument");
-  const int grid = grid_1d(rows * ld_dst);
+  const int grid = grid_1d(rows * ((cols + 7) / 8 * 8));
   if (dtype == 0)
     cast_rows_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst16, ld_dst, rows, cols);
   else

@@ -188,6 +188,12 @@ class AcousticEngine:
             wt = self._buf(f"WcatT16.{l}", (8 * H, Dp), torch.float16, zero=True)     # [8H, D]  fwd B operand
             for i, d in enumerate("fb"):
                 lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wt[i * 4 * H:]), Dp, D, 4 * H, F16, st)
+            ut = self._buf(f"UT16.{l}", (2, 4 * H, H), torch.float16)                 # [2, 4H, H] U^T, fwd recurrence
+            for i, d in enumerate("fb"):
+                lib.asr_cast_transpose(ptr(P.p(f"l{l}.U{d}")), 4 * H, ptr(ut[i]), H, H, 4 * H, F16, st)
+            if training:
+                ub = self._buf(f"Ub16.{l}", (2, H, 4 * H), torch.bfloat16)             # [2, H, 4H] U, BPTT recurrence
+                lib.asr_cast_rows(ptr(P.p(f"l{l}.Uf")), 4 * H, ptr(ub), 4 * H, 2 * H, 4 * H, BF16, st)
             if training and l > 0:
                 wc = self._buf(f"Wcat16.{l}", (D, 8 * H), torch.bfloat16)              # [D, 8H]  dX B operand
                 for i, d in enumerate("fb"):
@@ -225,7 +231,8 @@ class AcousticEngine:
         for l in range(L):
             self._gemm(F16, OUT_F32, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, w["zx"], 8 * H)
             a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(w["zx"]).value,
-                            bias=ptr(P.p(f"l{l}.bf")).value, U=ptr(P.p(f"l{l}.Uf")).value, U16=None,
+                            bias=ptr(P.p(f"l{l}.bf")).value, U=ptr(P.p(f"l{l}.Uf")).value,
+                            U16=ptr(self._ws[f"UT16.{l}"]).value,
                             h16=ptr(w[f"h16.{l}"]).value,
                             hT16=ptr(w[f"hT16.{l}"]).value if training else None, h32=None,
                             gates=ptr(w[f"gates.{l}"]).value if training else None,
@@ -287,7 +294,8 @@ class AcousticEngine:
         self._gemm(BF16, OUT_F32, R, 2 * H, cp, w["dl16"], cp, self._ws["Wd16"], cp, dh, 2 * H)
         for l in range(L - 1, -1, -1):
             a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(w[f"gates.{l}"]).value,
-                            cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value, U16=None,
+                            cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value,
+                            U16=ptr(self._ws[f"Ub16.{l}"]).value,
                             dz16=ptr(w["dz16"]).value, dzT16=ptr(w["dzT16"]).value, dz32=None,
                             dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value)
             lib.asr_lstm_backward(C.byref(a), st)

@@ -200,7 +200,7 @@ int32_t asr_sgd_step(float* param, const float* grad, float* mom,
 /* ------------------------------------------------------------------------- *
  * layout / precision helpers used between the kernels above
  * ------------------------------------------------------------------------- */
-/* dst16[r, c] = cast(src[r, c]) for r<rows, c<cols; zero-fills c in [cols, ld_dst).
+/* dst16[r, c] = cast(src[r, c]) for r<rows, c<cols; zero-fills c in [cols, min(ld_dst, roundup8(cols))).
  * dtype 0 = fp16, 1 = bf16 */
 int32_t asr_cast_rows(const float* src, int64_t ld_src, void* dst16, int64_t ld_dst,
                       int64_t rows, int32_t cols, int32_t dtype, void* stream);

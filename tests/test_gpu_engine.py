@@ -43,7 +43,7 @@ def test_forward_loss_decode_parity(N, T, F, H, L):
         assert out[n, :out_len[n]].tolist() == ref_dec[n]
 
 
-@pytest.mark.parametrize("N,T,F,H,L", [(8, 20, 26, 64, 2), (8, 40, 26, 128, 3)])
+@pytest.mark.parametrize("N,T,F,H,L", [(8, 20, 26, 64, 2), (8, 40, 26, 128, 3), (16, 30, 26, 128, 2)])
 def test_train_step_gradients_and_adam_parity(N, T, F, H, L):
     C = 28
     eng, params, x, lens, labels, pack = _setup(N, T, F, H, L, C, seed=7 * N + T)

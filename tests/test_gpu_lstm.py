@@ -29,8 +29,9 @@ def _params(rng, D, H, scale=1.0):
 def _device_fwd(p, x_ntd, training=True, engine=None):
     """x [N,T,D] -> runs zx GEMM in torch fp32 (operand prep is not under test here) + asr_lstm_forward."""
     from asr_study_b200._lib import LstmFwdArgs, lib, ptr, cur_stream
-    if engine:
-        os.environ["ASR_B200_LSTM"] = engine
+    os.environ.pop("ASR_B200_LSTM", None)
+    if engine == "fp32":
+        os.environ["ASR_B200_LSTM"] = "fp32"
     N, T, D = x_ntd.shape
     H = p["Uf"].shape[0]
     x = dev(x_ntd.transpose(1, 0, 2)).reshape(T * N, D)
@@ -60,8 +61,9 @@ def _device_fwd(p, x_ntd, training=True, engine=None):
 
 def _device_bwd(p, fwd, aux, dout_ntd, engine=None):
     from asr_study_b200._lib import LstmBwdArgs, lib, ptr, cur_stream
-    if engine:
-        os.environ["ASR_B200_LSTM"] = engine
+    os.environ.pop("ASR_B200_LSTM", None)
+    if engine == "fp32":
+        os.environ["ASR_B200_LSTM"] = "fp32"
     N, T, H2 = dout_ntd.shape
     H = H2 // 2
     R = T * N
@@ -150,3 +152,49 @@ def test_full_length_sequence_T999_stability():
     fwd, _ = _device_fwd(p, x, training=False, engine="fp32")
     h = fwd["h32"].cpu().numpy().reshape(T, N, 2 * H).transpose(1, 0, 2)
     assert norm_err(h, ref) < 1e-4
+
+
+TC_SHAPES = [(16, 12, 26, 64), (16, 25, 20, 256), (32, 40, 26, 512), (48, 7, 26, 128)]
+
+
+@pytest.mark.parametrize("N,T,D,H", TC_SHAPES)
+def test_tensor_core_engine_forward_backward_vs_oracle(N, T, D, H):
+    """tcgen05 persistent recurrence: fp16 forward operands (1e-3 activation bar), bf16 backward operands."""
+    rng = np.random.RandomState(N * 100 + T)
+    p = _params(rng, D, H, scale=1.5)
+    x = rng.randn(N, T, D).astype(np.float32)
+    dout = rng.randn(N, T, 2 * H).astype(np.float32)
+    ref, caches, ref_dz, ref_db = _oracle(p, x, dout)
+    fwd, aux = _device_fwd(p, x, engine="tc")
+    h16 = fwd["h16"].float().cpu().numpy().reshape(T, N, 2 * H).transpose(1, 0, 2)
+    assert norm_err(h16, ref) < 1e-3, norm_err(h16, ref)
+    h32 = fwd["h32"].cpu().numpy().reshape(T, N, 2 * H).transpose(1, 0, 2)
+    assert norm_err(h32, ref) < 1e-3
+    g = fwd["gates"].cpu().numpy().reshape(T, N, 2, 4 * H)
+    c = fwd["cell"].cpu().numpy().reshape(T, N, 2, H)
+    for d in range(2):
+        assert norm_err(g[:, :, d].transpose(1, 0, 2), caches[d]["gates"]) < 1e-3
+        assert norm_err(c[:, :, d].transpose(1, 0, 2), caches[d]["cs"]) < 1e-3
+    hT = fwd["hT16"].float().cpu().numpy().reshape(2 * H, T, N).transpose(2, 1, 0)
+    assert norm_err(hT, ref) < 8e-3
+    # fp32 engine on the same inputs: the two device engines must agree to the same bar
+    fwd32, _ = _device_fwd(p, x, engine="fp32")
+    assert norm_err(fwd["h32"].cpu().numpy(), fwd32["h32"].cpu().numpy()) < 1e-3
+    bwd = _device_bwd(p, fwd, aux, dout, engine="tc")
+    dz = bwd["dz32"].cpu().numpy().reshape(T, N, 8 * H).transpose(1, 0, 2)
+    assert norm_err(dz, ref_dz) < 2e-2, norm_err(dz, ref_dz)
+    assert norm_err(bwd["dbias"].cpu().numpy(), ref_db) < 2e-2
+    dzT = bwd["dzT16"].float().cpu().numpy().reshape(8 * H, T, N).transpose(2, 1, 0)
+    assert norm_err(dzT, ref_dz) < 3e-2
+
+
+def test_tensor_core_engine_T999_drift():
+    """T = 999 (BASELINE length), H = 512: drift of the fp16-operand recurrence vs the fp64 oracle."""
+    rng = np.random.RandomState(5)
+    N, T, D, H = 16, 999, 26, 512
+    p = _params(rng, D, H)
+    x = rng.randn(N, T, D).astype(np.float32)
+    ref, *_ = _oracle(p, x, np.zeros((N, T, 2 * H), np.float32))
+    fwd, _ = _device_fwd(p, x, training=False, engine="tc")
+    h = fwd["h32"].cpu().numpy().reshape(T, N, 2 * H).transpose(1, 0, 2)
+    assert norm_err(h, ref) < 1e-3, norm_err(h, ref)
