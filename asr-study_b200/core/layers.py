@@ -1,0 +1,42 @@
+"""Recurrent-layer descriptors with the reference's constructor surface
+(core/layers.py:356-516).  A layer here is a *configuration record*: the arithmetic of
+LSTM.step (core/layers.py:432-469) lives in the persistent CUDA kernels; the model factories
+collect these records into the engine's ModelSpec.
+
+Built: the default step (no LN / MI / zoneout / dropout).  The variant switches are accepted
+and rejected loudly when set (SURVEY 8f rank 1 — next rows), never silently ignored.
+"""
+
+
+class LSTM(object):
+    def __init__(self, output_dim, zoneout_h=0., zoneout_c=0., layer_norm=None, mi=None, return_sequences=True,
+                 consume_less="gpu", activation="tanh", inner_activation="hard_sigmoid", W_regularizer=None,
+                 U_regularizer=None, dropout_W=0., dropout_U=0., go_backwards=False, **kwargs):
+        if zoneout_h or zoneout_c:
+            raise NotImplementedError("zoneout is not built yet (core/layers.py:457-467)")
+        if layer_norm is not None:
+            raise NotImplementedError("layer normalisation is not built yet (core/layers.py:407-430)")
+        if mi is not None:
+            raise NotImplementedError("multiplicative integration is not built yet (core/layers.py:441-443)")
+        if activation != "tanh" or inner_activation != "hard_sigmoid":
+            raise NotImplementedError("only tanh / hard_sigmoid (the Keras-1 defaults) are built")
+        if dropout_W or dropout_U:
+            raise NotImplementedError("variational dropout is not built yet (core/layers.py:438-439); pass dropout=0")
+        if not return_sequences:
+            raise NotImplementedError("return_sequences=False is not used by any reference topology")
+        self.output_dim = int(output_dim)
+        self.W_regularizer, self.U_regularizer = W_regularizer, U_regularizer
+        self.consume_less = "gpu"
+
+    def get_config(self):
+        return {"output_dim": self.output_dim, "layer_norm": None, "mi": None, "zoneout_h": 0., "zoneout_c": 0.}
+
+
+def recurrent(output_dim, model="keras_lstm", activation="tanh", regularizer=None, dropout=0., **kwargs):
+    """core/layers.py:482-516 — only the LSTM families are built."""
+    if model in ("keras_lstm", "lstm"):
+        return LSTM(output_dim, activation=activation, W_regularizer=regularizer, U_regularizer=regularizer,
+                    dropout_W=dropout, dropout_U=dropout, **kwargs)
+    if model in ("rnn", "gru", "rhn"):
+        raise NotImplementedError("model %s is outside the BiLSTM hot path" % model)
+    raise ValueError("model %s was not recognized" % model)

@@ -1,0 +1,272 @@
+"""Model factories with the reference's surface (core/models.py:31-281) on the CUDA engine.
+
+``graves2006``, ``eyben`` (BiLSTM part), ``brsmv1`` and ``ctc_model`` keep their names, keyword
+arguments and defaults; they return a ``CTCModel`` that answers the Keras calls train.py /
+eval.py / predict.py make on it (compile, fit_generator, evaluate_generator, predict,
+train_on_batch, optimizer.lr, metrics_names, get_layer, save) — see SURVEY.md 8(b).
+``maas`` / ``deep_speech`` are SimpleRNN + clipped-ReLU stacks that cannot even be constructed in
+the reference (un-imported names, core/models.py:122,129): out of scope, they raise.
+"""
+from __future__ import annotations
+
+import math
+import pickle
+import time
+
+import numpy as np
+import torch
+
+from ..engine import AcousticEngine, ModelSpec, pack_labels
+from . import ctc_utils, metrics
+from .layers import LSTM
+
+_PAD = 16          # batch rows are padded to a multiple of 16 (tensor-core tile / 16-byte operand rows)
+
+
+class Adam(object):
+    """keras.optimizers.Adam as configured at train.py:137."""
+
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-8, clipnorm=0.):
+        self.lr, self.beta_1, self.beta_2, self.epsilon, self.clipnorm = lr, beta_1, beta_2, epsilon, clipnorm
+        self.kind = "adam"
+
+
+class SGD(object):
+    """keras.optimizers.SGD as configured at train.py:134-135."""
+
+    def __init__(self, lr=0.01, momentum=0., clipnorm=0.):
+        self.lr, self.momentum, self.clipnorm = lr, momentum, clipnorm
+        self.kind = "sgd"
+
+
+def _label_rows(labels):
+    if labels is None:
+        return None
+    if hasattr(labels, "tocsr"):
+        m = labels.tocsr()
+        return [m.data[m.indptr[i]:m.indptr[i + 1]].astype(np.int32) for i in range(m.shape[0])]
+    return [np.asarray(r, dtype=np.int32) for r in labels]
+
+
+class CTCModel(object):
+    """[inputs, labels, inputs_length] -> [ctc loss per utterance, greedy decode] (core/models.py:31-52)."""
+
+    metrics_names = ["loss", "ctc_loss", "decoder_loss", "decoder_ler"]
+
+    def __init__(self, spec: ModelSpec, device=None, seed=4321, is_greedy=True, beam_width=100,
+                 merge_repeated=True, input_std_noise=0.0):
+        if device is None:
+            import os
+            device = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
+        self.spec = spec
+        self.engine = AcousticEngine(spec, device=device, seed=seed)
+        self.device = self.engine.device
+        self.optimizer = Adam()
+        self.decoder = dict(is_greedy=is_greedy, beam_width=beam_width, merge_repeated=merge_repeated)
+        self.input_std_noise = float(input_std_noise or 0.0)
+        self.allreduce = None
+        self.world_size = 1
+        self.history = {}
+        self._noise_rng = torch.Generator(device=self.device)
+        self._noise_rng.manual_seed(1234)
+
+    # ---- Keras-facing plumbing --------------------------------------------------
+    def compile(self, loss=None, optimizer=None, metrics=None, loss_weights=None, **kw):
+        if optimizer is not None:
+            self.optimizer = optimizer
+        return self
+
+    def get_layer(self, name=None, index=None):
+        if name in ("inputs", "labels", "inputs_length", "decoder", "ctc", "beam_search"):
+            return name
+        raise ValueError("No such layer: %s" % name)
+
+    def set_data_parallel(self, allreduce, world_size):
+        """allreduce(flat_grad_tensor) must SUM in place across ranks (one NCCL all-reduce per step)."""
+        self.allreduce, self.world_size = allreduce, int(world_size)
+
+    # ---- batches ------------------------------------------------------------------
+    def _device_batch(self, x, x_len, labels, training):
+        x = np.asarray(x, dtype=np.float32)
+        N, T, F = x.shape
+        Np = (N + _PAD - 1) // _PAD * _PAD
+        xt = torch.zeros(T, Np, F, dtype=torch.float32, device=self.device)
+        xt[:, :N] = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 0, 2))).to(self.device)
+        if training and self.input_std_noise > 0:           # GaussianNoise(std), core/models.py:67,251
+            xt[:, :N] += self.input_std_noise * torch.randn(T, N, F, device=self.device, generator=self._noise_rng)
+        lens = np.zeros(Np, np.int32)
+        lens[:N] = np.asarray(x_len).reshape(-1)[:N]
+        rows = _label_rows(labels)
+        packed = None
+        if rows is not None:
+            rows = rows + [np.zeros(0, np.int32)] * (Np - N)
+            packed = pack_labels(rows, self.device)
+        return xt, torch.as_tensor(lens, device=self.device), packed, N
+
+    def _decode(self, logits, lens):
+        if self.decoder["is_greedy"]:
+            out, out_len = self.engine.greedy(logits, lens, True)
+        else:
+            out, out_len = self.engine.beam(logits, lens, self.decoder["beam_width"], self.decoder["merge_repeated"])
+        return out
+
+    # ---- train / eval / predict ------------------------------------------------------
+    def train_on_batch(self, x, y=None):
+        feats, labels, x_len = x[0], x[1], x[2]
+        xt, lens, (flat, off, mx), N = self._device_batch(feats, x_len, labels, True)
+        gb = N * self.world_size
+        o = self.optimizer
+        kw = dict(lr=o.lr, clipnorm=o.clipnorm, opt=o.kind)
+        if o.kind == "adam":
+            kw.update(beta1=o.beta_1, beta2=o.beta_2, eps=o.epsilon)
+        else:
+            kw.update(momentum=o.momentum)
+        loss = self.engine.train_step(xt, lens, flat, off, mx, global_batch=gb, allreduce=self.allreduce, **kw)
+        dec = self._decode(self.engine._w["logits"], lens)[:N]
+        ctc = float(loss[:N].mean().item())
+        reg = self._reg()
+        return [ctc + reg, ctc, 0.0, metrics.ler(_label_rows(labels), dec)]
+
+    def test_on_batch(self, x, y=None):
+        feats, labels, x_len = x[0], x[1], x[2]
+        xt, lens, (flat, off, mx), N = self._device_batch(feats, x_len, labels, False)
+        logits = self.engine.forward(xt, training=False)
+        loss, _ = self.engine.ctc(logits, lens, flat, off, mx, want_grad=False)
+        dec = self._decode(logits, lens)[:N]
+        ctc = float(loss[:N].mean().item())
+        return [ctc + self._reg(), ctc, 0.0, metrics.ler(_label_rows(labels), dec)]
+
+    def predict(self, x, batch_size=None, verbose=0):
+        """x = [inputs, inputs_length] (predict mode, utils/core_utils.py:76-93) -> -1-padded label matrix."""
+        feats, x_len = x[0], x[1]
+        xt, lens, _, N = self._device_batch(feats, x_len, None, False)
+        logits = self.engine.forward(xt, training=False)
+        return self._decode(logits, lens)[:N].cpu().numpy()
+
+    predict_on_batch = predict
+
+    def logits(self, feats, x_len):
+        """batch-major logits [N,T,C] (what the reference's TimeDistributed(Dense) emits)."""
+        xt, lens, _, N = self._device_batch(feats, x_len, None, False)
+        return self.engine.forward(xt, training=False)[:, :N].transpose(0, 1).contiguous()
+
+    def _reg(self):
+        wd = self.spec.weight_decay
+        if not wd:
+            return 0.0
+        P = self.engine.params
+        return float(wd * (P.flat * P.flat * P.decay.float()).sum().item())
+
+    def fit_generator(self, generator, samples_per_epoch, nb_epoch, validation_data=None, nb_val_samples=None,
+                      max_q_size=10, nb_worker=1, callbacks=None, verbose=1, initial_epoch=0, **kw):
+        callbacks = callbacks or []
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+        for epoch in range(initial_epoch, nb_epoch):
+            seen, agg, t0 = 0, np.zeros(4), time.time()
+            while seen < samples_per_epoch:
+                x, y = next(generator)
+                n = np.asarray(x[0]).shape[0]
+                agg += np.asarray(self.train_on_batch(x, y)) * n
+                seen += n
+            logs = dict(zip(["loss", "ctc_loss", "decoder_loss", "decoder_ler"], agg / max(seen, 1)))
+            if validation_data is not None and nb_val_samples:
+                v = self.evaluate_generator(validation_data, nb_val_samples)
+                logs.update({"val_" + k: val for k, val in zip(self.metrics_names, v)})
+            for k, v in logs.items():
+                self.history.setdefault(k, []).append(float(v))
+            if verbose:
+                show = {k: round(float(logs[k]), 4) for k in ("loss", "decoder_ler", "val_loss", "val_decoder_ler")
+                        if k in logs}
+                print("Epoch %d/%d - %.1fs - %s - %.1f utt/s" % (epoch + 1, nb_epoch, time.time() - t0, show,
+                                                                  seen / max(time.time() - t0, 1e-9)))
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+        return self.history
+
+    def evaluate_generator(self, generator, val_samples, max_q_size=10, nb_worker=1, **kw):
+        seen, agg = 0, np.zeros(4)
+        while seen < val_samples:
+            x, y = next(generator)
+            n = np.asarray(x[0]).shape[0]
+            agg += np.asarray(self.test_on_batch(x, y)) * n
+            seen += n
+        return list(agg / max(seen, 1))
+
+    # ---- checkpoint (weights + optimiser state + meta; the .h5 wire format needs h5py: next row) ----
+    def save(self, path, meta=None):
+        P = self.engine.params
+        blob = dict(spec=self.spec.__dict__, params=P.export("flat"), m=P.export("m"), v=P.export("v"),
+                    step=self.engine.step_count, optimizer=self.optimizer.__dict__, decoder=self.decoder,
+                    meta=meta or {})
+        with open(path, "wb") as f:
+            pickle.dump(blob, f)
+
+    @classmethod
+    def load(cls, path, device=None, **kw):
+        with open(path, "rb") as f:
+            blob = pickle.load(f)
+        m = cls(ModelSpec(**blob["spec"]), device=device, **kw)
+        P = m.engine.params
+        P.load(blob["params"])
+        for name in ("m", "v"):
+            for k, val in blob[name].items():
+                P._view(getattr(P, name), k).copy_(torch.as_tensor(val))
+        m.engine.step_count = blob["step"]
+        o = blob["optimizer"]
+        m.optimizer = Adam(o["lr"], o["beta_1"], o["beta_2"], o["epsilon"], o["clipnorm"]) if o["kind"] == "adam" \
+            else SGD(o["lr"], o["momentum"], o["clipnorm"])
+        m.decoder = blob["decoder"]
+        return m, blob.get("meta", {})
+
+
+# -------------------------------------------------------------------------------------------
+# factories
+# -------------------------------------------------------------------------------------------
+def ctc_model(inputs, output, **kwargs):
+    """core/models.py:31-52.  ``inputs`` = num_features, ``output`` = list of LSTM layer records followed by
+    the number of classes: ``ctc_model(26, [LSTM(100), 28])`` is graves2006."""
+    *layers, num_classes = output
+    hs = {l.output_dim for l in layers}
+    if not layers or len(hs) != 1 or not all(isinstance(l, LSTM) for l in layers):
+        raise NotImplementedError("the engine stacks identical-width BiLSTM layers")
+    wd = kwargs.pop("weight_decay", 0.0)
+    spec = ModelSpec(int(inputs), hs.pop(), len(layers), int(num_classes), float(wd), kwargs.pop("name", "ctc_model"))
+    return CTCModel(spec, **kwargs)
+
+
+def graves2006(num_features=26, num_hiddens=100, num_classes=28, std=.6, **kw):
+    """core/models.py:55-73: GaussianNoise(std) -> Bidirectional(LSTM(H)) -> TimeDistributed(Dense(C))."""
+    if num_hiddens % 64:
+        # the kernels take any H through the fp32 engine; H=100 is the reference default
+        pass
+    return ctc_model(num_features, [LSTM(num_hiddens), num_classes], name="graves2006", input_std_noise=std, **kw)
+
+
+def eyben(num_features=39, num_hiddens=[78, 120, 27], num_classes=28, **kw):
+    """core/models.py:76-103 needs an input Dense and two different LSTM widths: not built."""
+    raise NotImplementedError("eyben: heterogeneous widths + input projection are not on the built path yet")
+
+
+def maas(*a, **k):
+    raise NotImplementedError("maas is a SimpleRNN model outside the BiLSTM hot path (and broken in the reference)")
+
+
+def deep_speech(*a, **k):
+    raise NotImplementedError("deep_speech is a SimpleRNN model outside the BiLSTM hot path (and broken in the reference)")
+
+
+def brsmv1(num_features=39, num_classes=28, num_hiddens=256, num_layers=5, dropout=0.2, zoneout=0.,
+           input_dropout=False, input_std_noise=.0, weight_decay=1e-4, residual=None, layer_norm=None, mi=None,
+           activation='tanh', **kw):
+    """core/models.py:217-281.  Built: the N x BiLSTM + Dense trunk with l2(weight_decay).  The regulariser
+    switches (variational dropout, zoneout, LN, MI, residual) are next rows: any non-off value
+    raises instead of being ignored — pass dropout=0 explicitly."""
+    if residual is not None or input_dropout:
+        raise NotImplementedError("residual / input_dropout are not built yet")
+    layers = [LSTM(num_hiddens, zoneout_c=zoneout, zoneout_h=zoneout, mi=mi, layer_norm=layer_norm,
+                   activation=activation, dropout_W=dropout, dropout_U=dropout) for _ in range(num_layers)]
+    return ctc_model(num_features, layers + [num_classes], name="brsmv1", weight_decay=weight_decay,
+                     input_std_noise=input_std_noise, **kw)

@@ -17,6 +17,11 @@ size_t scratch_bytes(int H);
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
 int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st);
 }
+namespace lstmtc2 {
+bool supports_fwd(const asr_lstm_fwd_args* a);
+size_t scratch_bytes(int H);
+int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
+}
 namespace lstmtc {
 bool supports_fwd(const asr_lstm_fwd_args* a);
 bool supports_bwd(const asr_lstm_bwd_args* a);
@@ -50,8 +55,10 @@ extern "C" int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, i
 
 extern "C" size_t asr_lstm_flags_bytes(void) {
   // sized for the largest supported hidden size of either engine
-  const size_t a = lstm32::scratch_bytes(1024), b = lstmtc::scratch_bytes(1024);
-  return a > b ? a : b;
+  size_t m = lstm32::scratch_bytes(1024);
+  if (lstmtc::scratch_bytes(1024) > m) m = lstmtc::scratch_bytes(1024);
+  if (lstmtc2::scratch_bytes(1024) > m) m = lstmtc2::scratch_bytes(1024);
+  return m;
 }
 
 static int32_t check_common(int T, int N, int H) {
@@ -64,7 +71,10 @@ extern "C" int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream) {
   if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
   ASR_CHECK_ARG(!a->training || (a->gates && a->cell), "asr_lstm_forward: training needs gates/cell buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  if (!env_is("ASR_B200_LSTM", "fp32") && lstmtc::supports_fwd(a)) return lstmtc::forward(a, st);
+  if (!env_is("ASR_B200_LSTM", "fp32")) {
+    if (!env_is("ASR_B200_LSTM", "tc1") && lstmtc2::supports_fwd(a)) return lstmtc2::forward(a, st);
+    if (lstmtc::supports_fwd(a)) return lstmtc::forward(a, st);
+  }
   ASR_CHECK_ARG(a->U, "asr_lstm_forward: fp32 engine needs U");
   return lstm32::forward(a, st);
 }

@@ -20,6 +20,16 @@
 
 namespace lstmtc {
 
+#ifdef ASR_LSTM_PROFILE
+#define PROF_DECL long long pt0 = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF(i) do { const long long now = clock64(); pacc[i] += now - pt0; pt0 = now; } while (0)
+#define PROF_DUMP(base) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int i = 0; i < 8; ++i) reinterpret_cast<long long*>(flags + 1024)[(base) + i] = pacc[i]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_DUMP(base)
+#endif
+
 constexpr int UPC = 32;                 // hidden units per CTA
 constexpr int FLAG_BASE = 128;          // ints; [0,128) belongs to the fp32 engine's header (status at 64)
 constexpr int STATUS_IDX = 64;
@@ -117,7 +127,9 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags) {
   const size_t R = (size_t)T * N;
 
   __shared__ int s_dead;
+  PROF_DECL;
   for (int s = 0; s < T; ++s) {
+    PROF(7);
     if ((s & 15) == 15) {                              // bail out together if any CTA's watchdog fired
       if (tid == 0) s_dead = ld_acquire(status);
       __syncthreads();
@@ -137,6 +149,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags) {
     float z[NPT][4];
     if (s > 0) {
       wait_step(flag, nctas * s, status);
+      PROF(0);
       // h_{t-1} rows of this group -> UMMA B layout (K-major, SW128)
       {
         const int chunks_per_row = H / 8;
@@ -150,6 +163,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags) {
       }
       tc::fence_proxy_async_smem();
       __syncthreads();
+      PROF(1);
       if (tid == 0) {
         tc::tcgen05_fence_after();
         for (int kc = 0; kc < KC; ++kc) {
@@ -160,8 +174,10 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags) {
         }
         tc::umma_commit(mma_bar);
       }
+      PROF(2);
       if (!tc::mbar_wait(mma_bar, (uint32_t)((s - 1) & 1), WATCHDOG_CYCLES)) atomicExch(status, 1);
       tc::tcgen05_fence_after();
+      PROF(3);
       {
         uint32_t r[NG];
         if constexpr (NG == 16) tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), r);
@@ -194,11 +210,13 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags) {
       const size_t row = (size_t)t * N + n0 + warp * NPT + i;
       h16[row * 2 * H + dir * H + u] = __float2half_rn(hv[i]);      // exchange-critical store first
     }
+    PROF(4);
     __syncthreads();
     if (tid == 0) {
       __threadfence();
       red_release(flag, 1);
     }
+    PROF(5);
     // non-critical outputs after the release: they overlap the peers' next step
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
@@ -211,7 +229,9 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags) {
         if (a.hT16) reinterpret_cast<__nv_bfloat16*>(a.hT16)[(size_t)(dir * H + u) * R + row] = __float2bfloat16_rn(hv[i]);
       }
     }
+    PROF(6);
   }
+  PROF_DUMP(0);
   tc::tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 32);
@@ -279,7 +299,9 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags) {
   const size_t R = (size_t)T * N;
 
   __shared__ int s_dead;
+  PROF_DECL;
   for (int s = 0; s < T; ++s) {
+    PROF(7);
     if ((s & 15) == 15) {
       if (tid == 0) s_dead = ld_acquire(status);
       __syncthreads();
@@ -306,6 +328,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags) {
     for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
     if (s > 0) {
       wait_step(flag, nctas * s, status);
+      PROF(0);
       const int chunks_per_row = K4 / 8;               // 16-byte chunks per dz row (this direction)
       const __nv_bfloat16* src = dz16 + (((size_t)t_bprev * N + n0) * 2 + dir) * K4;
       const int per_q = NG * chunks_per_row / 4;
@@ -329,8 +352,10 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags) {
           if (q == 3) tc::umma_commit(mma_bar);
         }
       }
+      PROF(1);
       if (!tc::mbar_wait(mma_bar, (uint32_t)((s - 1) & 1), WATCHDOG_CYCLES)) atomicExch(status, 1);
       tc::tcgen05_fence_after();
+      PROF(3);
       if (warp < 4) {
         uint32_t r[NG];
         if constexpr (NG == 16) tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), r);
@@ -370,11 +395,13 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags) {
         }
       }
     }
+    PROF(4);
     __syncthreads();
     if (tid == 0) {
       __threadfence();
       red_release(flag, 1);
     }
+    PROF(5);
     if (ew) {
 #pragma unroll
       for (int i = 0; i < NPT; ++i) {
@@ -387,7 +414,9 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags) {
         }
       }
     }
+    PROF(6);
   }
+  PROF_DUMP(8);
   if (ew) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);
@@ -406,7 +435,7 @@ static bool shape_ok(int T, int N, int H) {
 }
 bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && a->h16 && shape_ok(a->T, a->N, a->H); }
 bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && shape_ok(a->T, a->N, a->H); }
-size_t scratch_bytes(int) { return 4096; }
+size_t scratch_bytes(int) { return 8192; }
 
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st) {
   const int H = a->H, KC = H / 64;

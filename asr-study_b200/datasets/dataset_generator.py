@@ -1,0 +1,123 @@
+"""Batch iterators with the reference's contract (datasets/dataset_generator.py:129-251):
+
+    next(it) -> ([x f32 [N,Tmax,F] zero-padded 'post', labels scipy COO int32 [N,Lmax], x_len [N]],
+                 [zeros [N], labels])                      (train / eval)
+             -> [x, x_len]                                  (predict)
+
+``input_parser`` is a preprocessing.audio Feature.  When it has the batched device entry
+(``.batch``), the whole batch's features come from ONE fused-kernel launch on the GPU instead of the
+reference's per-utterance python loop (dataset_generator.py:225); the padding, lengths and the
+"index_array.sort()" quirk are kept.  HDF5 / JSON readers are out of scope (no h5py here).
+"""
+import threading
+
+import numpy as np
+import scipy.sparse
+
+
+class DatasetIterator(object):
+    def __init__(self, inputs, labels=None, batch_size=32, shuffle=False, seed=None, input_parser=None,
+                 label_parser=None, mode="train"):
+        if labels is not None and len(inputs) != len(labels):
+            raise ValueError("inputs and labels should have the same length. Found: len(inputs) = %s, "
+                             "len(labels) = %s" % (len(inputs), len(labels)))
+        self.inputs, self.labels = list(inputs), (list(labels) if labels is not None else None)
+        self.batch_size, self.shuffle = batch_size, shuffle
+        self.input_parser, self.label_parser, self.mode = input_parser, label_parser, mode
+        self.lock = threading.Lock()
+        self._rng = np.random.RandomState(None if seed is None else int(seed))
+        self._order, self._pos = None, 0
+
+    @property
+    def len(self):
+        return len(self.inputs)
+
+    def __iter__(self):
+        return self
+
+    def _next_indices(self):
+        n = len(self.inputs)
+        if self._order is None or self._pos >= n:
+            self._order = self._rng.permutation(n) if self.shuffle else np.arange(n)
+            self._pos = 0
+        idx = self._order[self._pos:self._pos + self.batch_size]
+        self._pos += self.batch_size
+        return np.sort(idx)                                   # dataset_generator.py:200
+
+    def __next__(self):
+        with self.lock:
+            idx = self._next_indices()
+        batch_inputs, batch_len = self._make_in([self.inputs[i] for i in idx])
+        batch_labels = self._make_out([self.labels[i] for i in idx]) if self.labels is not None else None
+        if batch_labels is None or self.mode == "predict":
+            return [batch_inputs, batch_len]
+        return ([batch_inputs, batch_labels, batch_len], [np.zeros((batch_inputs.shape[0],)), batch_labels])
+
+    next = __next__
+
+    def _make_in(self, inputs):
+        p = self.input_parser
+        if p is not None and hasattr(p, "batch") and str(p) != "raw":
+            import torch
+            clips = [np.ascontiguousarray(np.asarray(c, dtype=np.float32).reshape(-1)) for c in inputs]
+            off = np.zeros(len(clips) + 1, np.int64)
+            off[1:] = np.cumsum([len(c) for c in clips])
+            dev = torch.device("cuda", torch.cuda.current_device())
+            feats, lens = p.batch(torch.from_numpy(np.concatenate(clips)).to(dev), torch.from_numpy(off).to(dev),
+                                  time_major=False)
+            return feats.cpu().numpy(), lens.cpu().numpy().astype(np.int64)
+        if p is not None:
+            inputs = [p(i) for i in inputs]
+        lens = np.asarray([np.asarray(i).shape[0] for i in inputs])
+        F = np.asarray(inputs[0]).shape[1]
+        x = np.zeros((len(inputs), int(lens.max()), F), dtype=np.float32)          # pad_sequences(.., 'post')
+        for k, f in enumerate(inputs):
+            x[k, :lens[k]] = f
+        return x, lens
+
+    def _make_out(self, labels):
+        if self.label_parser is not None:
+            labels = [self.label_parser(l) for l in labels]
+        rows, cols, data = [], [], []
+        for r, lab in enumerate(labels):
+            cols.extend(range(len(lab)))
+            rows.extend(len(lab) * [r])
+            data.extend(lab)
+        return scipy.sparse.coo_matrix((data, (rows, cols)), shape=(len(labels), max(len(l) for l in labels)),
+                                       dtype="int32")
+
+
+class DatasetGenerator(object):
+    """datasets/dataset_generator.py:24-126 for in-memory data (dict-of-lists, e.g. Dummy.to_dict_list())."""
+
+    def __init__(self, input_parser=None, label_parser=None, batch_size=32, shuffle=True, seed=None, mode="train"):
+        self.input_parser, self.label_parser = input_parser, label_parser
+        self.batch_size, self.shuffle, self.seed, self.mode = batch_size, shuffle, seed, mode
+
+    def flow(self, inputs, labels):
+        return DatasetIterator(inputs, labels, batch_size=self.batch_size, shuffle=self.shuffle, seed=self.seed,
+                               input_parser=self.input_parser, label_parser=self.label_parser, mode=self.mode)
+
+    def flow_from_dl(self, dl, datasets=None):
+        def pick(name):
+            if name is None or "dataset" not in dl:
+                return self.flow(dl["input"], dl["label"])
+            keep = [i for i, d in enumerate(dl["dataset"]) if d == name]
+            return self.flow([dl["input"][i] for i in keep], [dl["label"][i] for i in keep])
+        if datasets is None:
+            return pick(None)
+        if isinstance(datasets, str):
+            return pick(datasets)
+        return [pick(d) for d in datasets]
+
+    def flow_from_fname(self, fname, datasets=None):
+        if isinstance(fname, str) and fname.startswith("dummy"):
+            from .dummy import Dummy
+            kw = {}
+            if ":" in fname:                                   # dummy:num_speakers=2,num_utterances_per_speaker=4
+                for kv in fname.split(":", 1)[1].split(","):
+                    k, v = kv.split("=")
+                    kw[k] = eval(v, {}, {})
+            return self.flow_from_dl(Dummy(**kw).to_dict_list(), datasets)
+        raise NotImplementedError("HDF5 / JSON dataset files need h5py / corpora that are not available here; "
+                                  "use 'dummy[:k=v,...]' or DatasetGenerator.flow(inputs, labels)")
