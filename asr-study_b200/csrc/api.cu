@@ -19,6 +19,8 @@ int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st);
 }
 namespace lstmtc2 {
 bool supports_fwd(const asr_lstm_fwd_args* a);
+bool supports_bwd(const asr_lstm_bwd_args* a);
+int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st);
 size_t scratch_bytes(int H);
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
 }
@@ -83,7 +85,10 @@ extern "C" int32_t asr_lstm_backward(const asr_lstm_bwd_args* a, void* stream) {
   ASR_CHECK_ARG(a && a->dh && a->gates && a->cell && a->dbias && a->flags, "asr_lstm_backward: null argument");
   if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!env_is("ASR_B200_LSTM", "fp32") && lstmtc::supports_bwd(a)) return lstmtc::backward(a, st);
+  if (!env_is("ASR_B200_LSTM", "fp32")) {
+    if (!env_is("ASR_B200_LSTM", "tc1") && lstmtc2::supports_bwd(a)) return lstmtc2::backward(a, st);
+    if (lstmtc::supports_bwd(a)) return lstmtc::backward(a, st);
+  }
   ASR_CHECK_ARG(a->U, "asr_lstm_backward: fp32 engine needs U");
   return lstm32::backward(a, st);
 }

@@ -19,12 +19,23 @@
 
 namespace lstmtc2 {
 
+#ifdef ASR_LSTM_PROFILE
+#define PROF_DECL long long pt0 = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF(i) do { const long long now = clock64(); pacc[i] += now - pt0; pt0 = now; } while (0)
+#define PROF_DUMP(base) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int i = 0; i < 8; ++i) reinterpret_cast<long long*>(flags + 1024)[(base) + i] = pacc[i]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_DUMP(base)
+#endif
+
 constexpr int UPC = 32;
 constexpr int NG = 16;
 constexpr int THREADS = 128;
 constexpr int STATUS_IDX = 64;
 constexpr int HEADER_BYTES = 8192;
-constexpr uint32_t D_COL = 0, A_COL = 32;
+constexpr int NACC = 4;                                   // independent TMEM accumulators (breaks the MMA dependency chain)
+constexpr uint32_t D_COL = 0, A_COL = 64;
 constexpr long long WATCHDOG_CYCLES = 2000000000LL;
 
 __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) {
@@ -105,7 +116,9 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __half* h16 = reinterpret_cast<__half*>(a.h16);
   const size_t R = (size_t)T * N;
 
+  PROF_DECL;
   for (int s = 0; s < T; ++s) {
+    PROF(7);
     const int t = dir ? (T - 1 - s) : s;
     float zx[NPT][4];
 #pragma unroll
@@ -141,6 +154,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
           }
         }
       } while (!ok);
+      PROF(0);
 #pragma unroll
       for (int q = 0; q < WPT; ++q) {
         const int i = tid + q * THREADS;
@@ -149,30 +163,40 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
       tc::fence_proxy_async_smem();
       __syncthreads();
+      PROF(1);
       if (s_dead) break;
       if (tid == 0) {
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < H / 16; ++kb) {
           const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-          tc::umma_ts(tmem + D_COL, tmem + A_COL + kb * 8, bd, idesc, kb != 0);
+          tc::umma_ts(tmem + D_COL + (kb % NACC) * NG, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
         }
         tc::umma_commit(mma_bar);
       }
+      PROF(2);
       if (!tc::mbar_wait(mma_bar, (uint32_t)((s - 1) & 1), WATCHDOG_CYCLES)) {
         atomicExch(status, 1);
         s_dead = 1;
       }
       tc::tcgen05_fence_after();
+      PROF(3);
       {
-        uint32_t r[NG];
-        tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + D_COL, r);
+        uint32_t r0[NG], r1[NG], r2[NG], r3[NG];
+        const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
+        tc::tmem_ld16(tq, r0);
+        tc::tmem_ld16(tq + NG, r1);
+        tc::tmem_ld16(tq + 2 * NG, r2);
+        tc::tmem_ld16(tq + 3 * NG, r3);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int n = 0; n < NG; ++n) sZ[(warp * NG + n) * 32 + lane] = __uint_as_float(r[n]);
+        for (int n = 0; n < NG; ++n)
+          sZ[(warp * NG + n) * 32 + lane] = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) +
+                                            (__uint_as_float(r2[n]) + __uint_as_float(r3[n]));
       }
       tc::tcgen05_fence_before();
       __syncthreads();
+      PROF(4);
       if (s_dead) break;
 #pragma unroll
       for (int i = 0; i < NPT; ++i)
@@ -204,6 +228,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         st_volatile_v2(xo + (size_t)(warp * NPT + i) * (H / 2) + (u >> 1), wv);
       }
     }
+    PROF(5);
     // side outputs (not on the recurrence's critical path)
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
@@ -214,10 +239,284 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         float* gp = a.gates + (row * 2 + dir) * 4 * H;
         gp[u] = gi[i]; gp[H + u] = gf[i]; gp[2 * H + u] = gg[i]; gp[3 * H + u] = go[i];
         a.cell[(row * 2 + dir) * H + u] = c_state[i];
-        if (a.hT16) reinterpret_cast<__nv_bfloat16*>(a.hT16)[(size_t)(dir * H + u) * R + row] = __float2bfloat16_rn(hv[i]);
+      }
+    }
+    if (a.training && a.hT16) {   // the thread's NPT samples are contiguous in the transposed copy: one 8-byte store
+      static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0], hv[1]), p1 = __floats2bfloat162_rn(hv[2], hv[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.hT16) + (size_t)(dir * H + u) * R +
+                                (size_t)t * N + n0 + warp * NPT) = pk;
+    }
+    PROF(6);
+  }
+  PROF_DUMP(0);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward through time (v2): 4 x 4 CTA grid per (direction, batch group), H = 512
+//   CTA (r, c) owns the 32 hidden units [128r + 32c, +32) for the element-wise BPTT step, and the
+//   [128 units of row block r] x [512 gate columns of column block c] tile of U (bf16) in TMEM.
+//   Column block c = the gate columns (g, u) of the units owned by the four CTAs (., c).
+//   step:  hop 1  gather dz_{prev} of column c (LL ring, written by the 4 CTAs of the column)
+//          MMA    P_c[128 units of row r][n] = U_tile . dz_c^T          (32 TS-mode tcgen05.mma)
+//          hop 2  warp w holds the rows owned by CTA (r, w): send them there (LL ring, fp32)
+//                 and sum the four partials that arrive for my own units -> dh_rec
+//          element-wise BPTT -> dz (published to hop 1 of the next step) + side outputs
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1)
+bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf1, uint2* __restrict__ xbuf2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int H = 512, K4 = 4 * H;
+  constexpr int KC = 8;                                  // 512-wide K block = 8 chunks of 64
+  constexpr int B_CHUNK = NG * 128;
+  constexpr int WORDS1 = NG * 256;                       // hop-1 LL words per (dir, grp, column, parity)
+  constexpr int WPT1 = WORDS1 / THREADS;                 // 32
+  constexpr int WORDS2 = NG * 32;                        // hop-2 LL words per (dir, grp, r, recv, send, parity)
+  constexpr int NPT = NG / 4;
+  const int T = a.T, N = a.N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
+  const int r = cta >> 2, c = cta & 3;
+  const int u0 = cta * UPC, n0 = grp * NG;
+
+  uint8_t* sB = smem;
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sB + KC * B_CHUNK);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  __shared__ int s_dead;
+
+  if (tid == 0) {
+    tc::mbar_init(mma_bar, 1);
+    tc::fence_mbar_init();
+    s_dead = 0;
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // one-time: U tile -> TMEM.  lane m <-> unit 128r + m ; K index k = (r'*4 + g)*32 + j <-> gate column
+  // g*H + 128r' + 32c + j   (two bf16 per 32-bit column)
+  {
+    const __nv_bfloat16* Ub = reinterpret_cast<const __nv_bfloat16*>(a.U16) + (size_t)dir * H * K4 +
+                              (size_t)(128 * r + tid) * K4;
+#pragma unroll 1
+    for (int sp = 0; sp < 8; ++sp) {                     // 2 segments (64 K elements) per tcgen05.st
+      uint32_t rr[32];
+#pragma unroll
+      for (int hs = 0; hs < 2; ++hs) {
+        const int seg = 2 * sp + hs, rp = seg >> 2, g = seg & 3;
+        const uint4* src = reinterpret_cast<const uint4*>(Ub + g * H + 128 * rp + 32 * c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 v = __ldg(src + q);
+          rr[hs * 16 + 4 * q] = v.x; rr[hs * 16 + 4 * q + 1] = v.y; rr[hs * 16 + 4 * q + 2] = v.z; rr[hs * 16 + 4 * q + 3] = v.w;
+        }
+      }
+      tc::tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + A_COL + sp * 32, rr);
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+
+  const uint32_t idesc = tc::umma_idesc_f16(128, NG, 1);
+  const uint32_t sB_addr = tc::smem_u32(sB);
+  const int u = u0 + lane;
+  float dc_carry[NPT], db[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) dc_carry[i] = 0.0f;
+
+  int* status = flags + STATUS_IDX;
+  // hop 1: [(dir,grp)][column 4][parity 2][WORDS1]
+  uint2* x1 = xbuf1 + ((size_t)(dir * G + grp) * 4 + c) * 2 * WORDS1;
+  // hop 2: [(dir,grp)][r 4][recv 4][send 4][parity 2][WORDS2]
+  uint2* x2row = xbuf2 + ((size_t)(dir * G + grp) * 4 + r) * 4 * 4 * 2 * WORDS2;
+  __nv_bfloat16* dz16 = reinterpret_cast<__nv_bfloat16*>(a.dz16);
+  const size_t R = (size_t)T * N;
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? s : (T - 1 - s);
+    const int t_fprev = dir ? (t + 1) : (t - 1);
+    const bool has_fprev = dir ? (t + 1 < T) : (t > 0);
+    float dho[NPT], gi[NPT], gf[NPT], gg[NPT], go[NPT], cc[NPT], cp[NPT];
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
+      dho[i] = __ldg(a.dh + row * 2 * H + dir * H + u);
+      const float* gp = a.gates + (row * 2 + dir) * 4 * H;
+      gi[i] = __ldg(gp + u); gf[i] = __ldg(gp + H + u); gg[i] = __ldg(gp + 2 * H + u); go[i] = __ldg(gp + 3 * H + u);
+      cc[i] = __ldg(a.cell + (row * 2 + dir) * H + u);
+      cp[i] = has_fprev ? __ldg(a.cell + ((((size_t)t_fprev * N + n0 + warp * NPT + i) * 2 + dir) * H + u)) : 0.0f;
+    }
+    float dh_rec[NPT];
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
+    if (s > 0) {
+      const uint32_t tag = (uint32_t)s;
+      const int par = (s - 1) & 1;
+      // ---- hop 1: dz_{prev} of my column block -> smem B ------------------------------------------
+      {
+        const uint2* src = x1 + (size_t)par * WORDS1 + tid;
+        uint2 w[WPT1];
+#pragma unroll
+        for (int q = 0; q < WPT1; ++q) w[q] = ld_volatile_v2(src + q * THREADS);
+        bool ok;
+        long long t0 = 0;
+        do {
+          ok = true;
+#pragma unroll
+          for (int q = 0; q < WPT1; ++q)
+            if (w[q].y != tag) {
+              w[q] = ld_volatile_v2(src + q * THREADS);
+              ok = false;
+            }
+          if (!ok) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > WATCHDOG_CYCLES) {
+              atomicExch(status, 1);
+              s_dead = 1;
+              break;
+            }
+          }
+        } while (!ok);
+#pragma unroll
+        for (int q = 0; q < WPT1; ++q) {
+          const int i = tid + q * THREADS;
+          const int n = i >> 8, k = 2 * (i & 255);
+          *reinterpret_cast<uint32_t*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = w[q].x;
+        }
+      }
+      tc::fence_proxy_async_smem();
+      __syncthreads();
+      if (s_dead) break;
+      if (tid == 0) {
+        tc::tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 32; ++kb) {
+          const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
+          tc::umma_ts(tmem + D_COL + (kb % NACC) * NG, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
+        }
+        tc::umma_commit(mma_bar);
+      }
+      if (!tc::mbar_wait(mma_bar, (uint32_t)((s - 1) & 1), WATCHDOG_CYCLES)) {
+        atomicExch(status, 1);
+        s_dead = 1;
+      }
+      tc::tcgen05_fence_after();
+      // ---- hop 2 (send): my warp's 32 rows are the units of CTA (r, warp) -----------------------------
+      {
+        uint32_t r0[NG], r1[NG], r2[NG], r3[NG];
+        const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
+        tc::tmem_ld16(tq, r0);
+        tc::tmem_ld16(tq + NG, r1);
+        tc::tmem_ld16(tq + 2 * NG, r2);
+        tc::tmem_ld16(tq + 3 * NG, r3);
+        tc::tmem_ld_wait();
+        uint2* dst = x2row + ((size_t)(warp * 4 + c) * 2 + par) * WORDS2 + lane;
+#pragma unroll
+        for (int n = 0; n < NG; ++n) {
+          const float pv = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) + (__uint_as_float(r2[n]) + __uint_as_float(r3[n]));
+          st_volatile_v2(dst + n * 32, make_uint2(__float_as_uint(pv), tag));
+        }
+      }
+      tc::tcgen05_fence_before();
+      // ---- hop 2 (receive): four partials for each of my (unit, sample) ---------------------------------
+      {
+        uint2 w[4 * NPT];
+        const uint2* src = x2row + ((size_t)(c * 4) * 2 + par) * WORDS2 + lane;   // + send*2*WORDS2 + n*32
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd)
+#pragma unroll
+          for (int i = 0; i < NPT; ++i) w[sd * NPT + i] = ld_volatile_v2(src + (size_t)sd * 2 * WORDS2 + (warp * NPT + i) * 32);
+        bool ok;
+        long long t0 = 0;
+        do {
+          ok = true;
+#pragma unroll
+          for (int sd = 0; sd < 4; ++sd)
+#pragma unroll
+            for (int i = 0; i < NPT; ++i)
+              if (w[sd * NPT + i].y != tag) {
+                w[sd * NPT + i] = ld_volatile_v2(src + (size_t)sd * 2 * WORDS2 + (warp * NPT + i) * 32);
+                ok = false;
+              }
+          if (!ok) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > WATCHDOG_CYCLES) {
+              atomicExch(status, 1);
+              s_dead = 1;
+              break;
+            }
+          }
+        } while (!ok);
+#pragma unroll
+        for (int i = 0; i < NPT; ++i)
+          dh_rec[i] = (__uint_as_float(w[i].x) + __uint_as_float(w[NPT + i].x)) +
+                      (__uint_as_float(w[2 * NPT + i].x) + __uint_as_float(w[3 * NPT + i].x));
+      }
+      __syncthreads();                                   // all warps done with TMEM D and sB before the next step
+      if (s_dead) break;
+    }
+    float dz[NPT][4];
+    uint2* xo = x1 + (size_t)(s & 1) * WORDS1;
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const float dh = dho[i] + dh_rec[i];
+      const float tch = tanhf(cc[i]);
+      const float d_o = dh * tch * asr::hard_sigmoid_grad(go[i]);
+      const float dc = dc_carry[i] + dh * go[i] * (1.0f - tch * tch);
+      dz[i][0] = dc * gg[i] * asr::hard_sigmoid_grad(gi[i]);
+      dz[i][1] = dc * cp[i] * asr::hard_sigmoid_grad(gf[i]);
+      dz[i][2] = dc * gi[i] * (1.0f - gg[i] * gg[i]);
+      dz[i][3] = d_o;
+      dc_carry[i] = dc * gf[i];
+      // publish to hop 1 of the next step: K index k = (r*4 + g)*32 + lane, pairs of adjacent units
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float other = __shfl_down_sync(0xffffffffu, dz[i][g], 1);
+        if (!(lane & 1)) {
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(dz[i][g], other);
+          uint2 wv;
+          wv.x = *reinterpret_cast<const uint32_t*>(&pk);
+          wv.y = (uint32_t)(s + 1);
+          st_volatile_v2(xo + (size_t)(warp * NPT + i) * 256 + (((r * 4 + g) * 32 + lane) >> 1), wv);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        db[g] += dz[i][g];
+        dz16[(row * 2 + dir) * K4 + g * H + u] = __float2bfloat16_rn(dz[i][g]);
+        if (a.dz32) a.dz32[(row * 2 + dir) * K4 + g * H + u] = dz[i][g];
+      }
+    }
+    if (a.dzT16) {
+      static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]), p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.dzT16) + (size_t)(dir * K4 + g * H + u) * R +
+                                  (size_t)t * N + n0 + warp * NPT) = pk;
       }
     }
   }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);
   tc::tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
@@ -229,7 +528,12 @@ static bool shape_ok(int T, int N, int H) {
          (H / UPC) * 2 * (N / NG) <= 148;
 }
 bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && a->h16 && shape_ok(a->T, a->N, a->H); }
-size_t scratch_bytes(int) { return HEADER_BYTES + (size_t)2 * 8 * 2 * NG * (512 / 2) * sizeof(uint2); }
+bool supports_bwd(const asr_lstm_bwd_args* a) {
+  return a->U16 && a->dz16 && a->H == 512 && a->T >= 1 && a->N >= NG && a->N % NG == 0 && a->N / NG <= 4;
+}
+constexpr size_t X1_BYTES_PER_DG = (size_t)4 * 2 * NG * 256 * sizeof(uint2);            // hop 1 per (dir, grp)
+constexpr size_t X2_BYTES_PER_DG = (size_t)4 * 4 * 4 * 2 * NG * 32 * sizeof(uint2);     // hop 2 per (dir, grp)
+size_t scratch_bytes(int) { return HEADER_BYTES + (size_t)2 * 8 * (X1_BYTES_PER_DG + X2_BYTES_PER_DG); }
 
 template <int H>
 static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
@@ -244,6 +548,23 @@ static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
   void* kargs[] = {&args, &flags, &xbuf};
   ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
+  asr::count_launch();
+  return ASR_OK;
+}
+
+int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
+  const int G = a->N / NG;
+  const size_t smem = 1024 + (size_t)8 * NG * 128 + 64;
+  const size_t x1 = (size_t)2 * G * X1_BYTES_PER_DG, x2 = (size_t)2 * G * X2_BYTES_PER_DG;
+  ASR_CUDA(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + x1 + x2, st));
+  ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));
+  asr_lstm_bwd_args args = *a;
+  int* flags = a->flags;
+  uint2* xbuf1 = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
+  uint2* xbuf2 = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES + x1);
+  void* kargs[] = {&args, &flags, &xbuf1, &xbuf2};
+  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd_kernel, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
   asr::count_launch();
   return ASR_OK;
 }

@@ -16,11 +16,11 @@ gates = torch.empty(R, 8 * H, device=dev); cell = torch.empty(R, 2 * H, device=d
 flags = torch.zeros(lib.asr_lstm_flags_bytes() // 4, dtype=torch.int32, device=dev)
 a = LstmFwdArgs(T=T, N=N, H=H, training=1, zx=ptr(zx).value, bias=ptr(bias).value, U=ptr(U).value, U16=ptr(UT16).value,
                 h16=ptr(h16).value, hT16=ptr(hT16).value, h32=None, gates=ptr(gates).value, cell=ptr(cell).value, flags=ptr(flags).value)
-names = ["wait_flag", "load_B+sync", "issue", "mma_wait", "epilogue", "sync+fence+red", "side_stores", "loop_top"]
+names = ["poll_LL", "smem+fence+sync", "issue", "mma_wait", "tmem_ld+xchg", "gates+publish", "side_stores", "loop_top"]
 for rep in range(2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); lib.asr_lstm_forward(C.byref(a), cur_stream()); e1.record(); torch.cuda.synchronize()
-    p = flags[1024:1024 + 32].view(torch.int64).cpu().numpy()
+    p = flags[1024:1024 + 64].view(torch.int64).cpu().numpy()
     print("fwd ms", e0.elapsed_time(e1), "status", int(flags[64]))
     print("  fwd cycles/step:", {n: int(v / T) for n, v in zip(names, p[:8])}, "sum", int(p[:8].sum() / T))
 dh = torch.randn(R, 2 * H, device=dev, generator=g) * 0.01
@@ -31,6 +31,6 @@ b = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(gates).value, cell=pt
 for rep in range(2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); lib.asr_lstm_backward(C.byref(b), cur_stream()); e1.record(); torch.cuda.synchronize()
-    p = flags[1024:1024 + 32].view(torch.int64).cpu().numpy()
+    p = flags[1024:1024 + 64].view(torch.int64).cpu().numpy()
     print("bwd ms", e0.elapsed_time(e1), "status", int(flags[64]))
     print("  bwd cycles/step:", {n: int(v / T) for n, v in zip(names, p[8:16])}, "sum", int(p[8:16].sum() / T))
