@@ -1,0 +1,63 @@
+"""K8 parity: device prefix beam search (C ABI) vs the oracle's restatement of TF's CTCBeamSearchDecoder
+(top path).  Label sequences must be identical; the LER bar of config 5 follows from that."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc as oc
+from tests.util_gpu import dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _beam(logits_ntc, lens, W, merge=True):
+    from asr_study_b200.core import ctc_utils
+    y = dev(logits_ntc)
+    out = ctc_utils.decode([y, dev(np.asarray(lens, np.int32))], is_greedy=False, beam_width=W, merge_repeated=merge)
+    out = out.cpu().numpy()
+    return [[int(v) for v in r if v >= 0] for r in out]
+
+
+@pytest.mark.parametrize("T,C,W,scale", [(20, 5, 4, 2.0), (40, 6, 8, 1.0), (60, 28, 16, 3.0), (50, 28, 100, 1.5),
+                                         (120, 28, 100, 4.0), (30, 12, 400, 1.0)])
+def test_beam_matches_oracle(T, C, W, scale):
+    rng = np.random.RandomState(T * 31 + W)
+    N = 4
+    logits = (rng.randn(N, T, C) * scale).astype(np.float32)
+    lens = [T, T - 3, max(1, T // 2), 1]
+    got = _beam(logits, lens, W)
+    ref = oc.beam_decode(logits, lens, beam_width=W)
+    assert got == ref
+    got2 = _beam(logits, lens, W, merge=False)
+    ref2 = oc.beam_decode(logits, lens, beam_width=W, merge_repeated=False)
+    assert got2 == ref2
+
+
+def test_beam_peaky_equals_greedy_and_empty():
+    T, C = 64, 28
+    seq = np.random.RandomState(0).randint(0, C, size=T)
+    logits = np.full((2, T, C), -30.0, np.float32)
+    for t, k in enumerate(seq):
+        logits[:, t, k] = 30.0
+    got = _beam(logits, [T, 0], 50, merge=False)
+    assert got[0] == oc.greedy_decode_single(logits[0], T, C - 1)
+    assert got[1] == []
+
+
+def test_beam_width_1_and_ler_on_model_like_posteriors():
+    """width 100 on smoother, trained-like posteriors (config 5 shape in miniature): LER(beam) vs truth equals
+    the oracle's to the digit because the label sequences match."""
+    rng = np.random.RandomState(5)
+    N, T, C = 6, 150, 28
+    truth = [rng.randint(0, 26, size=rng.randint(5, 20)) for _ in range(N)]
+    logits = rng.randn(N, T, C).astype(np.float32)
+    for n, lab in enumerate(truth):                     # plant the truth with blanks in between
+        pos = np.linspace(3, T - 4, len(lab)).astype(int)
+        logits[n, :, C - 1] += 2.5
+        for p_, k in zip(pos, lab):
+            logits[n, p_, k] += 6.0
+    got = _beam(logits, [T] * N, 100)
+    ref = oc.beam_decode(logits, [T] * N, beam_width=100)
+    assert got == ref
+    assert abs(oc.ler(truth, got) - oc.ler(truth, ref)) < 1e-12
+    assert _beam(logits, [T] * N, 1) == oc.beam_decode(logits, [T] * N, beam_width=1)
