@@ -115,9 +115,11 @@ class DatasetGenerator(object):
             from .dummy import Dummy
             kw = {}
             if ":" in fname:                                   # dummy:num_speakers=2,num_utterances_per_speaker=4
-                for kv in fname.split(":", 1)[1].split(","):
+                import ast
+                import re
+                for kv in re.split(r",(?![^\[]*\])", fname.split(":", 1)[1]):   # commas outside [...]
                     k, v = kv.split("=")
-                    kw[k] = eval(v, {}, {})
+                    kw[k] = ast.literal_eval(v)
             return self.flow_from_dl(Dummy(**kw).to_dict_list(), datasets)
         raise NotImplementedError("HDF5 / JSON dataset files need h5py / corpora that are not available here; "
                                   "use 'dummy[:k=v,...]' or DatasetGenerator.flow(inputs, labels)")

@@ -299,7 +299,7 @@ def kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

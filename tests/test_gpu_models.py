@@ -1,0 +1,103 @@
+"""Plugin-surface tests on the GPU: the reference's call shapes (get_from_module, model factories, compile,
+fit_generator / evaluate_generator / predict, DatasetGenerator batches, train.py / eval.py flags) drive the
+CUDA engine, and config C1 (Dummy -> mfcc -> 1 x BiLSTM-100, batch 2) matches the oracle step for step."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc as oc
+from oracle import mfcc as omf
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_registry_lookup_contract():
+    from asr_study_b200.utils.generic_utils import get_from_module
+    f = get_from_module("preprocessing.audio", "MFCC", params=["num_cep", "13", "dd", "False"])
+    assert str(f) == "mfcc" and f.num_feats == 26
+    assert str(get_from_module("preprocessing.audio", "logfbank", params=[])) == "logfbank"
+    assert get_from_module("preprocessing.audio", "raw", params=[]).__class__.__name__ == "Raw"   # instance as-is
+    assert get_from_module("preprocessing.audio", None) is None
+    lp = get_from_module("preprocessing.text", "simple_char_parser", params=[])
+    assert lp.num_classes == 28 and lp.blank == 27 and lp("ab z") == [0, 1, 26, 25]
+    with pytest.raises(KeyError):
+        get_from_module("core.models", "nope")
+
+
+def test_c1_dummy_mfcc_graves2006_matches_oracle_step():
+    """configs[0]: Dummy -> mfcc -> graves2006 (1 x BiLSTM-100), batch 2; first training step vs oracle."""
+    from asr_study_b200.core import models
+    from asr_study_b200.datasets.dataset_generator import DatasetGenerator
+    from asr_study_b200.datasets.dummy import Dummy
+    from asr_study_b200.preprocessing import audio
+    from asr_study_b200.preprocessing.text import simple_char_parser
+    dl = Dummy(num_speakers=1, num_utterances_per_speaker=2, max_duration=1.2, min_duration=0.6, seed=7).to_dict_list()
+    feat = audio.MFCC(num_cep=13, d=True, dd=False)
+    gen = DatasetGenerator(feat, simple_char_parser, batch_size=2, shuffle=False).flow(dl["input"], dl["label"])
+    (x, labels, x_len), (zeros, labels2) = next(gen)
+    assert x.dtype == np.float32 and x.shape[0] == 2 and x.shape[2] == 26 and zeros.shape == (2,)
+    ref_feats, ref_len = omf.pad_batch([omf.MFCC(num_cep=13, d=True, dd=False)(c) for c in dl["input"]])
+    assert x_len.tolist() == ref_len.tolist() and np.abs(x - ref_feats).max() < 1e-3
+    model = models.graves2006(num_features=26, num_hiddens=100, num_classes=28, std=0.0)   # noise off for parity
+    model.compile(optimizer=models.Adam(lr=1e-3, clipnorm=400.0))
+    params = model.engine.params.export("flat")
+    rows = [np.asarray(simple_char_parser(l), np.int32) for l in dl["label"]]
+    total, ctc, grads, logits = om.loss_and_grads(params, x, x_len, rows, dtype=np.float64)
+    out = model.train_on_batch([x, labels, x_len], None)
+    assert abs(out[1] - float(ctc.mean())) <= 1e-3 * float(ctc.mean())                       # CTC loss 1e-3 rel
+    got = model.engine.params.export("grad")
+    for k in grads:                                                                         # fp32 engine: tight
+        err = np.abs(got[k] - grads[k]).max() / max(np.abs(grads[k]).max(), 1e-12)
+        assert err < 3e-2, (k, err)
+    dec = oc.greedy_decode(logits, x_len)
+    assert abs(out[3] - oc.ler(rows, dec)) < 1e-9                                           # decoder_ler metric
+
+
+def test_fit_evaluate_predict_save_load(tmp_path):
+    from asr_study_b200.core import models
+    from asr_study_b200.datasets.dataset_generator import DatasetGenerator
+    from asr_study_b200.datasets.dummy import Dummy
+    from asr_study_b200.preprocessing import audio
+    from asr_study_b200.preprocessing.text import simple_char_parser
+    dl = Dummy(num_speakers=2, num_utterances_per_speaker=4, max_duration=0.8, min_duration=0.4, max_label_length=6,
+               split=[.5, .25], seed=3).to_dict_list()
+    g = DatasetGenerator(audio.MFCC(num_cep=13, d=True, dd=False), simple_char_parser, batch_size=2, seed=0)
+    tr, va, te = g.flow_from_dl(dl, ["train", "valid", "test"])
+    assert (tr.len, va.len, te.len) == (4, 2, 2)
+    m = models.brsmv1(num_features=26, num_hiddens=64, num_layers=2, dropout=0.0)
+    m.compile(optimizer=models.Adam(lr=3e-3, clipnorm=400.0))
+    hist = m.fit_generator(tr, samples_per_epoch=tr.len, nb_epoch=4, validation_data=va, nb_val_samples=va.len, verbose=0)
+    assert len(hist["loss"]) == 4 and hist["loss"][-1] < hist["loss"][0]                     # it learns
+    ev = m.evaluate_generator(te, te.len)
+    assert len(ev) == 4 and m.metrics_names == ["loss", "ctc_loss", "decoder_loss", "decoder_ler"]
+    x, y = next(te)
+    pred = m.predict([x[0], x[2]])
+    assert pred.shape[0] == 2 and pred.dtype == np.int32
+    p = str(tmp_path / "model.pkl")
+    m.save(p, meta={"epochs": [0, 1, 2, 3]})
+    m2, meta = models.CTCModel.load(p)
+    assert meta["epochs"] == [0, 1, 2, 3]
+    assert np.array_equal(m2.predict([x[0], x[2]]), pred)
+    with pytest.raises(NotImplementedError):
+        models.brsmv1(dropout=0.2)                        # built later; never silently ignored
+
+
+def test_train_and_eval_cli(tmp_path):
+    sys.path.insert(0, ROOT)
+    import eval as eval_cli
+    import train as train_cli
+    out = str(tmp_path / "run")
+    train_cli.main(["--dataset", "dummy:num_speakers=2,num_utterances_per_speaker=4,max_duration=0.7,min_duration=0.4,"
+                    "max_label_length=5,split=[.5,.25]", "--input_parser", "mfcc", "--input_parser_params", "num_cep", "13",
+                    "dd", "False", "--model", "graves2006", "--model_params", "num_features", "26", "num_hiddens", "100",
+                    "--batch_size", "2", "--num_epochs", "2", "--save", out])
+    assert os.path.exists(os.path.join(out, "model.pkl")) and os.path.exists(os.path.join(out, "results.txt"))
+    m = eval_cli.main(["--model", os.path.join(out, "model.pkl"), "--dataset",
+                       "dummy:num_speakers=2,num_utterances_per_speaker=4,max_duration=0.7,min_duration=0.4,"
+                       "max_label_length=5,split=[.5,.25]", "--batch_size", "2", "--greedy"])
+    assert len(m) == 4 and np.isfinite(m[1])
