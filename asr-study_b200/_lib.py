@@ -30,14 +30,14 @@ class LstmFwdArgs(C.Structure):
     _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("training", C.c_int32),
                 ("zx", C.c_void_p), ("bias", C.c_void_p), ("U", C.c_void_p), ("U16", C.c_void_p),
                 ("h16", C.c_void_p), ("hT16", C.c_void_p), ("h32", C.c_void_p),
-                ("gates", C.c_void_p), ("cell", C.c_void_p), ("flags", C.c_void_p)]
+                ("gates", C.c_void_p), ("cell", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p)]
 
 
 class LstmBwdArgs(C.Structure):
     _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("H", C.c_int32),
                 ("dh", C.c_void_p), ("gates", C.c_void_p), ("cell", C.c_void_p),
                 ("U", C.c_void_p), ("U16", C.c_void_p), ("dz16", C.c_void_p), ("dzT16", C.c_void_p),
-                ("dz32", C.c_void_p), ("dbias", C.c_void_p), ("flags", C.c_void_p)]
+                ("dz32", C.c_void_p), ("dbias", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -69,6 +69,8 @@ SIGNATURES = {
     "asr_cast_rows": (_I32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
     "asr_cast_transpose": (_I32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
     "asr_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P]),
+    "asr_mask_cast": (_I32, [_P, _I32, _I64, _P, _I32, _P, _I32, _I64, _I64, _I32, _I32, _P]),
+    "asr_mask_combine": (_I32, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),
 }
 
 

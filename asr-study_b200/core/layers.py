@@ -3,7 +3,7 @@
 LSTM.step (core/layers.py:432-469) lives in the persistent CUDA kernels; the model factories
 collect these records into the engine's ModelSpec.
 
-Built: the default step (no LN / MI / zoneout / dropout).  The variant switches are accepted
+Built: the default step plus variational dropout (dropout_W / dropout_U); no LN / MI / zoneout.  The variant switches are accepted
 and rejected loudly when set (SURVEY 8f rank 1 — next rows), never silently ignored.
 """
 
@@ -20,11 +20,12 @@ class LSTM(object):
             raise NotImplementedError("multiplicative integration is not built yet (core/layers.py:441-443)")
         if activation != "tanh" or inner_activation != "hard_sigmoid":
             raise NotImplementedError("only tanh / hard_sigmoid (the Keras-1 defaults) are built")
-        if dropout_W or dropout_U:
-            raise NotImplementedError("variational dropout is not built yet (core/layers.py:438-439); pass dropout=0")
+        if not (0.0 <= dropout_W < 1.0 and 0.0 <= dropout_U < 1.0):
+            raise ValueError("dropout must be in [0, 1)")
         if not return_sequences:
             raise NotImplementedError("return_sequences=False is not used by any reference topology")
         self.output_dim = int(output_dim)
+        self.dropout_W, self.dropout_U = float(dropout_W), float(dropout_U)
         self.W_regularizer, self.U_regularizer = W_regularizer, U_regularizer
         self.consume_less = "gpu"
 

@@ -233,7 +233,11 @@ def ctc_model(inputs, output, **kwargs):
     if not layers or len(hs) != 1 or not all(isinstance(l, LSTM) for l in layers):
         raise NotImplementedError("the engine stacks identical-width BiLSTM layers")
     wd = kwargs.pop("weight_decay", 0.0)
-    spec = ModelSpec(int(inputs), hs.pop(), len(layers), int(num_classes), float(wd), kwargs.pop("name", "ctc_model"))
+    dps = {(l.dropout_W, l.dropout_U) for l in layers}
+    if len(dps) != 1 or len(set(dps.pop())) != 1:
+        raise NotImplementedError("dropout_W and dropout_U are tied and equal across layers (core/models.py:229-230)")
+    spec = ModelSpec(int(inputs), hs.pop(), len(layers), int(num_classes), float(wd), kwargs.pop("name", "ctc_model"),
+                     float(layers[0].dropout_W))
     return CTCModel(spec, **kwargs)
 
 
@@ -262,8 +266,8 @@ def brsmv1(num_features=39, num_classes=28, num_hiddens=256, num_layers=5, dropo
            input_dropout=False, input_std_noise=.0, weight_decay=1e-4, residual=None, layer_norm=None, mi=None,
            activation='tanh', **kw):
     """core/models.py:217-281.  Built: the N x BiLSTM + Dense trunk with l2(weight_decay).  The regulariser
-    switches (variational dropout, zoneout, LN, MI, residual) are next rows: any non-off value
-    raises instead of being ignored — pass dropout=0 explicitly."""
+    and variational dropout (dropout_W = dropout_U = dropout, masks constant over time).  The other switches
+    (zoneout, LN, MI, residual, input_dropout) are next rows: a non-off value raises."""
     if residual is not None or input_dropout:
         raise NotImplementedError("residual / input_dropout are not built yet")
     layers = [LSTM(num_hiddens, zoneout_c=zoneout, zoneout_h=zoneout, mi=mi, layer_norm=layer_norm,

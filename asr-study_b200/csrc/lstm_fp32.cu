@@ -106,6 +106,7 @@ lstm_fwd_kernel(asr_lstm_fwd_args a, float* __restrict__ xbuf /* [2 dir][2 parit
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = a.bias[(size_t)dir * 4 * H + g * H + u];
   float c_state = 0.0f;
+  const float mu = (own && a.mask_u) ? a.mask_u[((size_t)dir * N + en) * H + u] : 1.0f;   // B_U, constant over time
 
   // matmul ownership: 8 K-slices x (8 n-quads x 4 column groups)
   const int ks = tid >> 5, lane = tid & 31, nq = lane & 7, cg = lane >> 3;
@@ -170,10 +171,10 @@ lstm_fwd_kernel(asr_lstm_fwd_args a, float* __restrict__ xbuf /* [2 dir][2 parit
         a.cell[(row * 2 + dir) * H + u] = c_state;
         if (a.hT16)
           reinterpret_cast<__nv_bfloat16*>(a.hT16)[(size_t)(dir * H + u) * ((size_t)T * N) + row] =
-              __float2bfloat16_rn(h);
+              __float2bfloat16_rn(h * mu);
       }
     }
-    if (u < H && en < NB) xb[(size_t)(s & 1) * H * NB + (size_t)u * NB + en] = own ? h : 0.0f;
+    if (u < H && en < NB) xb[(size_t)(s & 1) * H * NB + (size_t)u * NB + en] = own ? h * mu : 0.0f;
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -210,6 +211,7 @@ lstm_bwd_kernel(asr_lstm_bwd_args a, float* __restrict__ xbuf /* [2 dir][2 parit
   const bool own = (en < N) && (u < H);
   float dc_carry = 0.0f;
   float db[4] = {0, 0, 0, 0};
+  const float mu = (own && a.mask_u) ? a.mask_u[((size_t)dir * N + en) * H + u] : 1.0f;
 
   // matmul: 32 K-slices x 8 n-quads, one column group
   const int ks = tid >> 3, nq = tid & 7;
@@ -260,6 +262,7 @@ lstm_bwd_kernel(asr_lstm_bwd_args a, float* __restrict__ xbuf /* [2 dir][2 parit
       }
       __syncthreads();
       for (int q = 0; q < 32; ++q) dh_rec += sR[(size_t)q * NB * CC + (size_t)en * CC + eu];
+      dh_rec *= mu;
     }
     float dz[4] = {0, 0, 0, 0};
     if (own) {

@@ -433,8 +433,8 @@ static bool shape_ok(int T, int N, int H) {
   return T >= 1 && H >= 64 && H <= 512 && H % 64 == 0 && N >= NG && N % NG == 0 && N / NG <= 8 &&
          (H / UPC) * 2 * (N / NG) <= 148;
 }
-bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && a->h16 && shape_ok(a->T, a->N, a->H); }
-bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && shape_ok(a->T, a->N, a->H); }
+bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && a->h16 && !a->mask_u && shape_ok(a->T, a->N, a->H); }
+bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && !a->mask_u && shape_ok(a->T, a->N, a->H); }
 size_t scratch_bytes(int) { return 8192; }
 
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st) {

@@ -107,9 +107,12 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   float bias[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) bias[g] = a.bias[(size_t)dir * 4 * H + g * H + u];
-  float c_state[NPT];
+  float c_state[NPT], mu[NPT];
 #pragma unroll
-  for (int i = 0; i < NPT; ++i) c_state[i] = 0.0f;
+  for (int i = 0; i < NPT; ++i) {
+    c_state[i] = 0.0f;
+    mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;   // B_U, constant over time
+  }
 
   int* status = flags + STATUS_IDX;
   uint2* xb = xbuf + (size_t)(dir * G + grp) * 2 * WORDS;
@@ -218,10 +221,11 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       go[i] = asr::hard_sigmoid(z[i][3] + zx[i][3] + bias[3]);
       c_state[i] = gf[i] * c_state[i] + gi[i] * gg[i];
       hv[i] = go[i] * tanhf(c_state[i]);
-      // publish: even lanes pack (unit, unit+1) into one LL word {half2, tag = s+1}
-      const float other = __shfl_down_sync(0xffffffffu, hv[i], 1);
+      // publish h * B_U: even lanes pack (unit, unit+1) into one LL word {half2, tag = s+1}
+      const float hm = hv[i] * mu[i];
+      const float other = __shfl_down_sync(0xffffffffu, hm, 1);
       if (!(lane & 1)) {
-        const __half2 pk = __floats2half2_rn(hv[i], other);
+        const __half2 pk = __floats2half2_rn(hm, other);
         uint2 wv;
         wv.x = *reinterpret_cast<const uint32_t*>(&pk);
         wv.y = (uint32_t)(s + 1);
@@ -243,7 +247,8 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     }
     if (a.training && a.hT16) {   // the thread's NPT samples are contiguous in the transposed copy: one 8-byte store
       static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0], hv[1]), p1 = __floats2bfloat162_rn(hv[2], hv[3]);
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0] * mu[0], hv[1] * mu[1]),
+                           p1 = __floats2bfloat162_rn(hv[2] * mu[2], hv[3] * mu[3]);
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&p0);
       pk.y = *reinterpret_cast<const uint32_t*>(&p1);
@@ -331,9 +336,12 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   const uint32_t idesc = tc::umma_idesc_f16(128, NG, 1);
   const uint32_t sB_addr = tc::smem_u32(sB);
   const int u = u0 + lane;
-  float dc_carry[NPT], db[4] = {0, 0, 0, 0};
+  float dc_carry[NPT], mu[NPT], db[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int i = 0; i < NPT; ++i) dc_carry[i] = 0.0f;
+  for (int i = 0; i < NPT; ++i) {
+    dc_carry[i] = 0.0f;
+    mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;
+  }
 
   int* status = flags + STATUS_IDX;
   // hop 1: [(dir,grp)][column 4][parity 2][WORDS1]
@@ -460,8 +468,8 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         } while (!ok);
 #pragma unroll
         for (int i = 0; i < NPT; ++i)
-          dh_rec[i] = (__uint_as_float(w[i].x) + __uint_as_float(w[NPT + i].x)) +
-                      (__uint_as_float(w[2 * NPT + i].x) + __uint_as_float(w[3 * NPT + i].x));
+          dh_rec[i] = mu[i] * ((__uint_as_float(w[i].x) + __uint_as_float(w[NPT + i].x)) +
+                               (__uint_as_float(w[2 * NPT + i].x) + __uint_as_float(w[3 * NPT + i].x)));
       }
       __syncthreads();                                   // all warps done with TMEM D and sB before the next step
       if (s_dead) break;

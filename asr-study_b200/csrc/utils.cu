@@ -65,6 +65,58 @@ colsum_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols,
   }
 }
 
+template <typename S> __device__ __forceinline__ float ldf(const S* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename S, typename T>
+__global__ void __launch_bounds__(256)
+mask_rows_kernel(const S* __restrict__ src, int64_t ld_src, const float* __restrict__ mask, int nb, T* __restrict__ dst,
+                 int64_t ld_dst, int64_t rows, int cols) {
+  const int cp = min((int64_t)((cols + 7) / 8 * 8), ld_dst);
+  const int64_t total = rows * cp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cp;
+    const int c = (int)(i - r * cp);
+    float v = 0.0f;
+    if (c < cols) v = ldf<S>(src + r * ld_src + c) * mask[(int64_t)(r % nb) * cols + c];
+    dst[r * ld_dst + c] = cvt<T>(v);
+  }
+}
+
+template <typename S, typename T>
+__global__ void __launch_bounds__(256)
+mask_transpose_kernel(const S* __restrict__ src, int64_t ld_src, const float* __restrict__ mask, int nb,
+                      T* __restrict__ dst, int64_t ld_dst, int64_t rows, int cols) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = r0 + k;
+    const int c = c0 + tx;
+    tile[k][tx] = (r < rows && c < cols) ? ldf<S>(src + r * ld_src + c) * mask[(int64_t)(r % nb) * cols + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < rows) dst[(int64_t)c * ld_dst + r] = cvt<T>(tile[tx][k]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mask_combine_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ ma,
+                    const float* __restrict__ mb, int nb, float* __restrict__ out, int64_t rows, int cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int64_t mi = (r % nb) * cols + (i - r * cols);
+    out[i] = a[i] * ma[mi] + b[i] * mb[mi];
+  }
+}
+
 inline int grid_1d(int64_t total) {
   const int64_t b = (total + 255) / 256;
   return (int)(b < 148 * 8 ? (b < 1 ? 1 : b) : 148 * 8);
@@ -96,6 +148,41 @@ extern "C" int32_t asr_cast_transpose(const float* src, int64_t ld_src, void* ds
   else
     cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst16,
                                                                                  ld_dst, rows, cols);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+template <typename S>
+static int32_t mask_cast_dispatch(const S* src, int64_t ld_src, const float* mask, int nb, void* dst16, int dtype,
+                                  int64_t ld_dst, int64_t rows, int cols, int transpose, cudaStream_t st) {
+  if (transpose) {
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+    if (dtype == 0) mask_transpose_kernel<S, __half><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__half*)dst16, ld_dst, rows, cols);
+    else mask_transpose_kernel<S, __nv_bfloat16><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__nv_bfloat16*)dst16, ld_dst, rows, cols);
+  } else {
+    const int grid = grid_1d(rows * ((cols + 7) / 8 * 8));
+    if (dtype == 0) mask_rows_kernel<S, __half><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__half*)dst16, ld_dst, rows, cols);
+    else mask_rows_kernel<S, __nv_bfloat16><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__nv_bfloat16*)dst16, ld_dst, rows, cols);
+  }
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+extern "C" int32_t asr_mask_cast(const void* src, int32_t src_dtype, int64_t ld_src, const float* mask, int32_t n_batch,
+                                 void* dst16, int32_t dtype, int64_t ld_dst, int64_t rows, int32_t cols,
+                                 int32_t transpose, void* stream) {
+  ASR_CHECK_ARG(src && mask && dst16 && rows > 0 && cols > 0 && n_batch > 0 && ld_src >= cols, "asr_mask_cast: bad argument");
+  ASR_CHECK_ARG(transpose ? ld_dst >= rows : ld_dst >= cols, "asr_mask_cast: ld_dst too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == 0) return mask_cast_dispatch((const __half*)src, ld_src, mask, n_batch, dst16, dtype, ld_dst, rows, cols, transpose, st);
+  if (src_dtype == 1) return mask_cast_dispatch((const __nv_bfloat16*)src, ld_src, mask, n_batch, dst16, dtype, ld_dst, rows, cols, transpose, st);
+  return mask_cast_dispatch((const float*)src, ld_src, mask, n_batch, dst16, dtype, ld_dst, rows, cols, transpose, st);
+}
+
+extern "C" int32_t asr_mask_combine(const float* a, const float* b, const float* mask_a, const float* mask_b,
+                                    int32_t n_batch, float* out, int64_t rows, int32_t cols, void* stream) {
+  ASR_CHECK_ARG(a && b && mask_a && mask_b && out && rows > 0 && cols > 0 && n_batch > 0, "asr_mask_combine: bad argument");
+  mask_combine_kernel<<<grid_1d(rows * cols), 256, 0, (cudaStream_t)stream>>>(a, b, mask_a, mask_b, n_batch, out, rows, cols);
   ASR_LAUNCH_CHECK();
   return ASR_OK;
 }

@@ -35,6 +35,7 @@ class ModelSpec:
     num_classes: int = 28
     weight_decay: float = 0.0        # l2 on W, U of every LSTM and the Dense kernel (models.py:263-264,279)
     name: str = "brsmv1"
+    dropout: float = 0.0             # variational dropout_W = dropout_U (core/models.py:265-266), train phase only
 
 
 class ParamBucket:
@@ -108,6 +109,22 @@ class AcousticEngine:
         self._sqnorm = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._flags = torch.zeros(lib.asr_lstm_flags_bytes() // 4, dtype=torch.int32, device=self.device)
         self._weights_version = -1
+        self._mask_rng = torch.Generator(device=self.device)
+        self._mask_rng.manual_seed(seed + 17)
+
+    # ------------------------------------------------------------ dropout masks
+    def sample_masks(self, N):
+        """Keras-1 LSTM.get_constants: one B_W [N, D] and one B_U [N, H] mask per direction and layer, sampled
+        once per batch, constant over time, scaled by 1/(1-p) (K.dropout).  Returns {layer: {Wf,Wb,Uf,Ub}}."""
+        sp, p = self.spec, float(self.spec.dropout)
+        out, D = {}, sp.num_features
+        for l in range(sp.num_layers):
+            out[l] = {}
+            for k, w in (("Wf", D), ("Wb", D), ("Uf", sp.num_hiddens), ("Ub", sp.num_hiddens)):
+                keep = torch.rand(N, w, device=self.device, generator=self._mask_rng) >= p
+                out[l][k] = keep.float() / (1.0 - p)
+            D = 2 * sp.num_hiddens
+        return out
 
     # ------------------------------------------------------------------ init
     @staticmethod
@@ -211,8 +228,10 @@ class AcousticEngine:
                         cur_stream())
 
     # ---------------------------------------------------------------- forward
-    def forward(self, feats_tm: torch.Tensor, training=False) -> torch.Tensor:
-        """feats_tm: f32 [T, N, F] time-major on device -> logits f32 [T, N, C]."""
+    def forward(self, feats_tm: torch.Tensor, training=False, masks=None) -> torch.Tensor:
+        """feats_tm: f32 [T, N, F] time-major on device -> logits f32 [T, N, C].
+        masks: {layer: {Wf,Wb [N,D], Uf,Ub [N,H]}} variational-dropout masks (training only); sampled when
+        spec.dropout > 0 and none are given."""
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
         assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
@@ -220,6 +239,10 @@ class AcousticEngine:
         R = T * N
         w = self._alloc(T, N, training)
         self._w, self._T, self._N = w, T, N
+        if training and masks is None and sp.dropout > 0:
+            masks = self.sample_masks(N)
+        self._masks = masks if training else None
+        masks = self._masks
         st = cur_stream()
         self._prep_weights(training)
         feats_tm = feats_tm.contiguous()
@@ -228,8 +251,24 @@ class AcousticEngine:
         if training:
             lib.asr_cast_transpose(ptr(feats_tm), Fd, ptr(w["xT16"]), R, R, Fd, BF16, st)
         x16, D = w["x16"], D0
+        src, src_dt, src_ld, Dl = feats_tm, 2, Fd, Fd              # layer input before masking
         for l in range(L):
-            self._gemm(F16, OUT_F32, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, w["zx"], 8 * H)
+            mask_u = None
+            if masks is None:
+                self._gemm(F16, OUT_F32, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, w["zx"], 8 * H)
+            else:
+                mk = masks[l]
+                mask_u = self._buf(f"maskU.{l}", (2, N, H), torch.float32)
+                mask_u[0].copy_(mk["Uf"]); mask_u[1].copy_(mk["Ub"])
+                for i, d in enumerate("fb"):
+                    mw = mk["W" + d].contiguous()
+                    xm = self._buf(f"xm16.{i}", (R, D), torch.float16)
+                    lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xm), F16, D, R, Dl, 0, st)
+                    lib.asr_gemm_tn(F16, OUT_F32, R, 4 * H, D, ptr(xm), D, ptr(self._ws[f"WcatT16.{l}"][i * 4 * H:]), D,
+                                    ptr(w["zx"][:, i * 4 * H:]), 8 * H, None, 1.0, 0, st)
+                    if training:
+                        xmT = self._buf(f"xmT16.{l}.{i}", (Dl, R), torch.bfloat16)
+                        lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xmT), BF16, R, R, Dl, 1, st)
             a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(w["zx"]).value,
                             bias=ptr(P.p(f"l{l}.bf")).value, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"UT16.{l}"]).value,
@@ -237,9 +276,10 @@ class AcousticEngine:
                             hT16=ptr(w[f"hT16.{l}"]).value if training else None, h32=None,
                             gates=ptr(w[f"gates.{l}"]).value if training else None,
                             cell=ptr(w[f"cell.{l}"]).value if training else None,
-                            flags=ptr(self._flags).value)
+                            flags=ptr(self._flags).value, mask_u=ptr(mask_u).value if mask_u is not None else None)
             lib.asr_lstm_forward(C.byref(a), st)
             x16, D = w[f"h16.{l}"], 2 * H
+            src, src_dt, src_ld, Dl = w[f"h16.{l}"], 0, 2 * H, 2 * H
         self._gemm(F16, OUT_F32, R, Cc, 2 * H, x16, 2 * H, self._ws["WdT16"], 2 * H, w["logits"], Cc,
                    bias=P.p("dense.b"))
         return w["logits"]
@@ -292,20 +332,24 @@ class AcousticEngine:
         # dTop [R, 2H] = dl16 [R, Cpad] . Wd16 [2H, Cpad]^T
         dh, other = w["dhA"], w["dhB"]
         self._gemm(BF16, OUT_F32, R, 2 * H, cp, w["dl16"], cp, self._ws["Wd16"], cp, dh, 2 * H)
+        masks = self._masks
         for l in range(L - 1, -1, -1):
+            mask_u = self._ws[f"maskU.{l}"][:2 * N * H].view(2, N, H) if masks is not None else None
             a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(w[f"gates.{l}"]).value,
                             cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"Ub16.{l}"]).value,
                             dz16=ptr(w["dz16"]).value, dzT16=ptr(w["dzT16"]).value, dz32=None,
-                            dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value)
+                            dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value,
+                            mask_u=ptr(mask_u).value if mask_u is not None else None)
             lib.asr_lstm_backward(C.byref(a), st)
             D = sp.num_features if l == 0 else 2 * H
             xT = w["xT16"] if l == 0 else w[f"hT16.{l - 1}"]
             hT = w[f"hT16.{l}"]
             dzT = w["dzT16"]
             for i, d in enumerate("fb"):
-                # dW_dir [D, 4H] = xT [D, R] . dzT_dir [4H, R]^T
-                self._gemm(BF16, OUT_F32, D, 4 * H, R, xT, R, dzT[i * 4 * H:], R, P.g(f"l{l}.W{d}"), 4 * H)
+                # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
+                xTd = xT if masks is None else self._ws[f"xmT16.{l}.{i}"][:D * R].view(D, R)
+                self._gemm(BF16, OUT_F32, D, 4 * H, R, xTd, R, dzT[i * 4 * H:], R, P.g(f"l{l}.W{d}"), 4 * H)
                 # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
                 if T > 1:
                     Kk = (T - 1) * N
@@ -319,10 +363,21 @@ class AcousticEngine:
                                     C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, st)
                 else:
                     P.g(f"l{l}.U{d}").zero_()
-            if l > 0:
+            if l > 0 and masks is None:
                 # dX [R, 2H] = dz16 [R, 8H] . Wcat16 [2H, 8H]^T
                 self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w["dz16"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
                            other, 2 * H)
+                dh, other = other, dh
+            elif l > 0:
+                # dX = (dz_f . Wf^T) * B_Wf + (dz_b . Wb^T) * B_Wb   (each direction's LSTM masked its own input)
+                part = [self._buf(f"dxpart.{i}", (R, 2 * H), torch.float32) for i in range(2)]
+                wc = self._ws[f"Wcat16.{l}"]
+                for i in range(2):
+                    lib.asr_gemm_tn(BF16, OUT_F32, R, 2 * H, 4 * H, ptr(w["dz16"][:, i * 4 * H:]), 8 * H,
+                                    ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), 2 * H, None, 1.0, 0, st)
+                mk = masks[l]
+                lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
+                                     ptr(other), R, 2 * H, st)
                 dh, other = other, dh
 
     # -------------------------------------------------------------- optimiser
@@ -350,10 +405,10 @@ class AcousticEngine:
 
     # ------------------------------------------------------------ whole step
     def train_step(self, feats_tm, in_len, labels_flat, label_off, max_label_len, global_batch=None,
-                   allreduce=None, **opt):
+                   allreduce=None, masks=None, **opt):
         """One optimisation step on time-major features; returns the per-utterance CTC loss tensor [N]."""
         N = feats_tm.shape[1]
-        logits = self.forward(feats_tm, training=True)
+        logits = self.forward(feats_tm, training=True, masks=masks)
         loss, dlogits = self.ctc(logits, in_len, labels_flat, label_off, max_label_len,
                                  grad_scale=1.0 / float(global_batch or N))
         self.backward(dlogits)

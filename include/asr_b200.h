@@ -129,6 +129,9 @@ typedef struct {
   float* gates;             /* f32 [T, N, 2, 4H] activated i,f,g,o (training) */
   float* cell;              /* f32 [T, N, 2, H]  c_t             (training)   */
   int32_t* flags;           /* device scratch, asr_lstm_flags_bytes(), zeroed */
+  const float* mask_u;      /* f32 [2, N, H] variational-dropout mask B_U (already /(1-p)) applied to
+                               h_{t-1} in the recurrence (core/layers.py:438), or NULL.  When set,
+                               hT16 holds h*mask (the operand of dU); h16/h32 stay unmasked.        */
 } asr_lstm_fwd_args;
 
 typedef struct {
@@ -143,6 +146,7 @@ typedef struct {
   float* dz32;              /* f32 [T, N, 2, 4H] optional                     */
   float* dbias;             /* f32 [2, 4H]  (overwritten)                     */
   int32_t* flags;
+  const float* mask_u;      /* same mask as in the forward call, or NULL      */
 } asr_lstm_bwd_args;
 
 size_t  asr_lstm_flags_bytes(void);
@@ -207,6 +211,16 @@ int32_t asr_cast_rows(const float* src, int64_t ld_src, void* dst16, int64_t ld_
 /* dst16[c, r] = cast(src[r, c])  (transpose), ld_dst >= rows */
 int32_t asr_cast_transpose(const float* src, int64_t ld_src, void* dst16, int64_t ld_dst,
                            int64_t rows, int32_t cols, int32_t dtype, void* stream);
+/* variational-dropout operand views (core/layers.py:439: x * B_W[0], mask constant over time):
+ * rows are time-major r = t*n_batch + n; mask f32 [n_batch, cols] (already scaled by 1/(1-p)).
+ * src_dtype: 0 = fp16, 1 = bf16, 2 = fp32.  dst16[r, c] = cast(src[r, c] * mask[r % n_batch, c]);
+ * transpose != 0 writes dst16[c, r] instead (ld_dst >= rows).  Zero-fills the K padding like asr_cast_rows. */
+int32_t asr_mask_cast(const void* src, int32_t src_dtype, int64_t ld_src, const float* mask, int32_t n_batch,
+                      void* dst16, int32_t dtype, int64_t ld_dst, int64_t rows, int32_t cols,
+                      int32_t transpose, void* stream);
+/* out[r, c] = a[r, c] * mask_a[r % n_batch, c] + b[r, c] * mask_b[r % n_batch, c]   (dX of the two directions) */
+int32_t asr_mask_combine(const float* a, const float* b, const float* mask_a, const float* mask_b,
+                         int32_t n_batch, float* out, int64_t rows, int32_t cols, void* stream);
 /* out[c] = sum_r src[r, c]  (fp32; bias gradients) */
 int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_t cols,
                    float* out, void* stream);

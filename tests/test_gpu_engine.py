@@ -82,3 +82,44 @@ def test_clipnorm_engages():
     newp = eng.params.export("flat")
     for k in p0:
         np.testing.assert_allclose(newp[k], p0[k], atol=2e-6)
+
+
+@pytest.mark.parametrize("N,T,F,H,L", [(8, 20, 26, 64, 2), (16, 24, 26, 512, 2)])
+def test_variational_dropout_forward_backward_parity(N, T, F, H, L):
+    """dropout_W / dropout_U masks (per sample, constant over time; core/layers.py:438-439, core/models.py:265-266)
+    with the SAME masks on both sides: logits, loss and every parameter gradient vs the oracle."""
+    C = 28
+    eng, params, x, lens, labels, pack = _setup(N, T, F, H, L, C, seed=11 + N)
+    rng = np.random.RandomState(5)
+    masks_np, D = {}, F
+    for l in range(L):
+        masks_np[l] = {k: ((rng.rand(N, w) >= 0.2) / 0.8).astype(np.float32)
+                       for k, w in (("Wf", D), ("Wb", D), ("Uf", H), ("Ub", H))}
+        D = 2 * H
+    masks_dev = {l: {k: dev(v) for k, v in m.items()} for l, m in masks_np.items()}
+    flat, off, mx = pack(labels, "cuda")
+    feats = dev(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    loss = eng.train_step(feats, dev(lens), flat, off, mx, masks=masks_dev, lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    assert eng.lstm_status() == 0
+    ref_logits, _ = om.forward(params, x, masks=masks_np, dtype=np.float64)
+    got_logits = eng._w["logits"].cpu().numpy().transpose(1, 0, 2)
+    assert norm_err(got_logits, ref_logits) < 1e-3
+    _, ctc, grads, _ = om.loss_and_grads(params, x, lens, labels, masks=masks_np, dtype=np.float64)
+    np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
+    got = eng.params.export("grad")
+    for k, g in grads.items():
+        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+    # and it differs from the no-dropout forward (the masks really act)
+    plain, _ = om.forward(params, x, dtype=np.float64)
+    assert norm_err(got_logits, plain) > 1e-2
+
+
+def test_sampled_masks_have_keras_statistics():
+    from asr_study_b200.engine import AcousticEngine, ModelSpec
+    eng = AcousticEngine(ModelSpec(26, 64, 2, 28, dropout=0.2))
+    m = eng.sample_masks(64)
+    assert set(m) == {0, 1} and m[0]["Wf"].shape == (64, 26) and m[1]["Wb"].shape == (64, 128) and m[1]["Uf"].shape == (64, 64)
+    v = torch.cat([t.flatten() for l in m.values() for t in l.values()])
+    assert set(np.unique(v.cpu().numpy()).round(4).tolist()) <= {0.0, 1.25}
+    assert abs(float((v > 0).float().mean()) - 0.8) < 0.02

@@ -84,7 +84,7 @@ def test_fit_evaluate_predict_save_load(tmp_path):
     assert meta["epochs"] == [0, 1, 2, 3]
     assert np.array_equal(m2.predict([x[0], x[2]]), pred)
     with pytest.raises(NotImplementedError):
-        models.brsmv1(dropout=0.2)                        # built later; never silently ignored
+        models.brsmv1(zoneout=0.1)                        # next row; never silently ignored
 
 
 def test_train_and_eval_cli(tmp_path):
