@@ -105,6 +105,7 @@ class AcousticEngine:
         self.params.load(init_params)
         self.step_count = 0
         self._ws = {}
+        self._views = {}
         self._shape = None
         self._sqnorm = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._flags = torch.zeros(lib.asr_lstm_flags_bytes() // 4, dtype=torch.int32, device=self.device)
@@ -164,7 +165,9 @@ class AcousticEngine:
         if t is None or t.numel() < n or t.dtype != dtype:
             t = (torch.zeros if zero else torch.empty)(n, dtype=dtype, device=self.device)
             self._ws[name] = t
-        return t[:n].view(*shape)
+        v = t[:n].view(*shape)
+        self._views[name] = v          # last shaped view (self._ws holds the flat storage)
+        return v
 
     def _alloc(self, T, N, training):
         sp = self.spec
@@ -264,7 +267,7 @@ class AcousticEngine:
                     mw = mk["W" + d].contiguous()
                     xm = self._buf(f"xm16.{i}", (R, D), torch.float16)
                     lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xm), F16, D, R, Dl, 0, st)
-                    lib.asr_gemm_tn(F16, OUT_F32, R, 4 * H, D, ptr(xm), D, ptr(self._ws[f"WcatT16.{l}"][i * 4 * H:]), D,
+                    lib.asr_gemm_tn(F16, OUT_F32, R, 4 * H, D, ptr(xm), D, ptr(self._views[f"WcatT16.{l}"][i * 4 * H:]), D,
                                     ptr(w["zx"][:, i * 4 * H:]), 8 * H, None, 1.0, 0, st)
                     if training:
                         xmT = self._buf(f"xmT16.{l}.{i}", (Dl, R), torch.bfloat16)
@@ -327,14 +330,21 @@ class AcousticEngine:
         lib.asr_cast_transpose(ptr(dlogits), Cc, ptr(w["dlT16"]), R, R, Cc, BF16, st)
         lib.asr_colsum(ptr(dlogits), Cc, R, Cc, ptr(P.g("dense.b")), st)
         top = L - 1
+        topT = w[f"hT16.{top}"]
+        if self._masks is not None:
+            # with dropout hT16 holds h * B_U (the dU operand); the Dense kernel saw the unmasked h
+            ones = self._buf("ones_mask", (N, 2 * H), torch.float32)
+            ones.fill_(1.0)
+            topT = self._buf("topT16", (2 * H, R), torch.bfloat16)
+            lib.asr_mask_cast(ptr(w[f"h16.{top}"]), 0, 2 * H, ptr(ones), N, ptr(topT), BF16, R, R, 2 * H, 1, st)
         # dWd [2H, C] = topT [2H, R] . dlT [C, R]^T
-        self._gemm(BF16, OUT_F32, 2 * H, Cc, R, w[f"hT16.{top}"], R, w["dlT16"], R, P.g("dense.W"), Cc)
+        self._gemm(BF16, OUT_F32, 2 * H, Cc, R, topT, R, w["dlT16"], R, P.g("dense.W"), Cc)
         # dTop [R, 2H] = dl16 [R, Cpad] . Wd16 [2H, Cpad]^T
         dh, other = w["dhA"], w["dhB"]
         self._gemm(BF16, OUT_F32, R, 2 * H, cp, w["dl16"], cp, self._ws["Wd16"], cp, dh, 2 * H)
         masks = self._masks
         for l in range(L - 1, -1, -1):
-            mask_u = self._ws[f"maskU.{l}"][:2 * N * H].view(2, N, H) if masks is not None else None
+            mask_u = self._views[f"maskU.{l}"] if masks is not None else None
             a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(w[f"gates.{l}"]).value,
                             cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"Ub16.{l}"]).value,
@@ -348,7 +358,7 @@ class AcousticEngine:
             dzT = w["dzT16"]
             for i, d in enumerate("fb"):
                 # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
-                xTd = xT if masks is None else self._ws[f"xmT16.{l}.{i}"][:D * R].view(D, R)
+                xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
                 self._gemm(BF16, OUT_F32, D, 4 * H, R, xTd, R, dzT[i * 4 * H:], R, P.g(f"l{l}.W{d}"), 4 * H)
                 # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
                 if T > 1:
@@ -371,7 +381,7 @@ class AcousticEngine:
             elif l > 0:
                 # dX = (dz_f . Wf^T) * B_Wf + (dz_b . Wb^T) * B_Wb   (each direction's LSTM masked its own input)
                 part = [self._buf(f"dxpart.{i}", (R, 2 * H), torch.float32) for i in range(2)]
-                wc = self._ws[f"Wcat16.{l}"]
+                wc = self._views[f"Wcat16.{l}"]
                 for i in range(2):
                     lib.asr_gemm_tn(BF16, OUT_F32, R, 2 * H, 4 * H, ptr(w["dz16"][:, i * 4 * H:]), 8 * H,
                                     ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), 2 * H, None, 1.0, 0, st)
