@@ -60,7 +60,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one_sync()) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -73,7 +73,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one_sync()) {
       const uint32_t idesc = tc::umma_idesc_f16(BM, BN, p.ab_fmt);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;

@@ -77,7 +77,11 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  // the CTA owns all 512 TMEM columns, so the allocation starts at column 0: use compile-time TMEM
+  // addresses (a run-time base forces an ELECT/R2UR waterfall loop around every tcgen05.mma — measured
+  // ~70 cycles per MMA, see profiles/lstm_phases_r1.md)
+  if (*tmem_slot != 0u) { if (tid == 0) atomicExch(flags + STATUS_IDX, 2); }
+  constexpr uint32_t tmem = 0u;
 
   // ---- one-time: U^T slice -> TMEM.  TMEM lane r = g*32 + j holds row (g*H + u0 + j) of U^T, two fp16
   //      K-elements per 32-bit column (the kind::f16 A-operand layout). --------------------------------
@@ -168,7 +172,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       __syncthreads();
       PROF(1);
       if (s_dead) break;
-      if (tid == 0) {
+      if (warp == 0 && tc::elect_one_sync()) {
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < H / 16; ++kb) {
@@ -305,7 +309,8 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  if (*tmem_slot != 0u) { if (tid == 0) atomicExch(flags + STATUS_IDX, 2); }
+  constexpr uint32_t tmem = 0u;           // whole TMEM allocated -> base column 0 (see forward kernel)
 
   // one-time: U tile -> TMEM.  lane m <-> unit 128r + m ; K index k = (r'*4 + g)*32 + j <-> gate column
   // g*H + 128r' + 32c + j   (two bf16 per 32-bit column)
@@ -351,7 +356,9 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __nv_bfloat16* dz16 = reinterpret_cast<__nv_bfloat16*>(a.dz16);
   const size_t R = (size_t)T * N;
 
+  PROF_DECL;
   for (int s = 0; s < T; ++s) {
+    PROF(7);
     const int t = dir ? s : (T - 1 - s);
     const int t_fprev = dir ? (t + 1) : (t - 1);
     const bool has_fprev = dir ? (t + 1 < T) : (t > 0);
@@ -396,6 +403,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
             }
           }
         } while (!ok);
+        PROF(0);
 #pragma unroll
         for (int q = 0; q < WPT1; ++q) {
           const int i = tid + q * THREADS;
@@ -405,8 +413,9 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
       tc::fence_proxy_async_smem();
       __syncthreads();
+      PROF(1);
       if (s_dead) break;
-      if (tid == 0) {
+      if (warp == 0 && tc::elect_one_sync()) {
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 32; ++kb) {
@@ -420,6 +429,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         s_dead = 1;
       }
       tc::tcgen05_fence_after();
+      PROF(2);
       // ---- hop 2 (send): my warp's 32 rows are the units of CTA (r, warp) -----------------------------
       {
         uint32_t r0[NG], r1[NG], r2[NG], r3[NG];
@@ -437,6 +447,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         }
       }
       tc::tcgen05_fence_before();
+      PROF(3);
       // ---- hop 2 (receive): four partials for each of my (unit, sample) ---------------------------------
       {
         uint2 w[4 * NPT];
@@ -472,6 +483,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
                                (__uint_as_float(w[2 * NPT + i].x) + __uint_as_float(w[3 * NPT + i].x)));
       }
       __syncthreads();                                   // all warps done with TMEM D and sB before the next step
+      PROF(4);
       if (s_dead) break;
     }
     float dz[NPT][4];
@@ -500,6 +512,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         }
       }
     }
+    PROF(5);
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
       const size_t row = (size_t)t * N + n0 + warp * NPT + i;
@@ -522,7 +535,9 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
                                   (size_t)t * N + n0 + warp * NPT) = pk;
       }
     }
+    PROF(6);
   }
+  PROF_DUMP(8);
 #pragma unroll
   for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);
   tc::tcgen05_fence_before();

@@ -33,4 +33,5 @@ for rep in range(2):
     e0.record(); lib.asr_lstm_backward(C.byref(b), cur_stream()); e1.record(); torch.cuda.synchronize()
     p = flags[1024:1024 + 64].view(torch.int64).cpu().numpy()
     print("bwd ms", e0.elapsed_time(e1), "status", int(flags[64]))
-    print("  bwd cycles/step:", {n: int(v / T) for n, v in zip(names, p[8:16])}, "sum", int(p[8:16].sum() / T))
+    bn = ["hop1_poll", "smem+fence+sync", "issue+mma_wait", "tmem_ld+hop2_send", "hop2_poll+sync", "bptt+publish", "side_stores", "loop_top"]
+    print("  bwd cycles/step:", {n: int(v / T) for n, v in zip(bn, p[8:16])}, "sum", int(p[8:16].sum() / T))
