@@ -24,10 +24,13 @@ __device__ __forceinline__ float lse2(float a, float b) {
   if (m == -CUDART_INF_F) return -CUDART_INF_F;
   return m + log1pf(expf(fminf(a, b) - m));
 }
+// lattice recursion: the single alpha / beta warp is instruction-bound (4 states per lane x 3 exp + log per
+// frame), so the recursion uses the SFU approximations (ex2/lg2, rel. error ~2^-21 — far inside the 5e-4
+// gradient bar; rows are renormalised against fp64 offsets every frame so arguments stay O(10)).
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   const float m = fmaxf(a, fmaxf(b, c));
   if (m == -CUDART_INF_F) return -CUDART_INF_F;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
 // NJ = states per lane (S <= 32*NJ)
@@ -121,21 +124,23 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
         if (j * 32 + lane < S) w_alpha[j * 32 + lane] = a[j];
       if (lane == 0) w_offA[0] = offA;
     }
+    float z = 0.0f;
     if (len > 1) {
       const float* row = logits + ((size_t)1 * N + n) * C;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) x[j] = row[lab[j]];
+      z = w_lse[1];
     }
     for (int t = 1; t < len; ++t) {
 #pragma unroll
       for (int j = 0; j < NJ; ++j) prev[j * 32 + lane] = a[j];
       __syncwarp();
-      const float z = w_lse[t];
-      float xn[NJ];
+      float xn[NJ], zn = 0.0f;          // next frame's operands are fetched a whole frame ahead
       if (t + 1 < len) {
         const float* row = logits + ((size_t)(t + 1) * N + n) * C;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) xn[j] = row[lab[j]];
+        zn = w_lse[t + 1];
       }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
@@ -164,6 +169,7 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
       if (t + 1 < len) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) x[j] = xn[j];
+        z = zn;
       }
     }
     // log p(l|x) = lse(alpha[len-1][S-1], alpha[len-1][S-2])
@@ -212,21 +218,23 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
         if (j * 32 + lane < S) w_beta[(size_t)(len - 1) * s_max + j * 32 + lane] = b[j];
       if (lane == 0) w_offB[len - 1] = offB;
     }
+    float z = 0.0f;
     if (len > 1) {
       const float* row = logits + ((size_t)(len - 2) * N + n) * C;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) x[j] = row[lab[j]];
+      z = w_lse[len - 2];
     }
     for (int t = len - 2; t >= 0; --t) {
 #pragma unroll
       for (int j = 0; j < NJ; ++j) nxt[j * 32 + lane] = b[j];
       __syncwarp();
-      const float z = w_lse[t];
-      float xn[NJ];
+      float xn[NJ], zn = 0.0f;
       if (t > 0) {
         const float* row = logits + ((size_t)(t - 1) * N + n) * C;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) xn[j] = row[lab[j]];
+        zn = w_lse[t - 1];
       }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
@@ -255,6 +263,7 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
       if (t > 0) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) x[j] = xn[j];
+        z = zn;
       }
     }
   }

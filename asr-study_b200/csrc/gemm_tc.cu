@@ -91,48 +91,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) ----
+    // TMEM -> registers (thread = one accumulator row) -> per-warp smem transpose -> COALESCED global stores
+    // (8 lanes x 16 B = one 128-byte row segment; 4 rows per instruction).  The staging area is pipeline stage 0,
+    // free by now: the accumulator-complete barrier implies every TMA load landed and every MMA has read it.
     const int q = warp & 3;
     if (!tc::mbar_wait(tmem_full, 0)) __trap();
     tc::tcgen05_fence_after();
-    const int row = m0 + q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem) + q * (32 * 36);     // [32 rows][36] (16-byte aligned, conflict-light)
     const bool split = gridDim.z > 1;
     const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+    const int sub = lane >> 3, l8 = lane & 7;                         // 4 rows per pass, 8 lanes per row
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, r);
       tc::tmem_ld_wait();
-      if (nkb <= 0) {
+      if (n0 + c0 >= p.N) continue;                                   // warp-uniform
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0;
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * 36 + j) =
+            (nkb > 0) ? make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                    __uint_as_float(r[j + 3]))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      const int col = n0 + c0 + l8 * 4;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add_bias) {
+        if (col < p.N) bv.x = __ldg(p.bias + col);
+        if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
+        if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
+        if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
       }
-      if (row >= p.M) continue;
-      const int ncol = min(32, p.N - (n0 + c0));
-      if (ncol <= 0) continue;
-      float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = p.alpha * __uint_as_float(r[j]);
-        if (add_bias && j < ncol) v[j] += __ldg(p.bias + n0 + c0 + j);
-      }
-      const int64_t o = (int64_t)row * p.ldc + n0 + c0;
-      if (p.dtype_out == 0) {
-        float* cp = reinterpret_cast<float*>(p.C) + o;
-        if (split) {
-          for (int j = 0; j < ncol; ++j) atomicAdd(cp + j, v[j]);
-        } else if (ncol == 32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int pass = 0; pass < 8; ++pass) {
+        const int rl = pass * 4 + sub;
+        const int row = m0 + q * 32 + rl;
+        const float4 a = *reinterpret_cast<const float4*>(stg + rl * 36 + l8 * 4);
+        float v[4] = {p.alpha * a.x + bv.x, p.alpha * a.y + bv.y, p.alpha * a.z + bv.z, p.alpha * a.w + bv.w};
+        if (row >= p.M || col >= p.N) continue;
+        const int64_t o = (int64_t)row * p.ldc + col;
+        const int nc = min(4, p.N - col);
+        if (p.dtype_out == 0) {
+          float* cp = reinterpret_cast<float*>(p.C) + o;
+          if (split) {
+            for (int j = 0; j < nc; ++j) atomicAdd(cp + j, v[j]);
+          } else if (nc == 4 && !p.accumulate && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            for (int j = 0; j < nc; ++j) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
+          }
+        } else if (p.dtype_out == 1) {
+          __half* cp = reinterpret_cast<__half*>(p.C) + o;
+          for (int j = 0; j < nc; ++j) cp[j] = __float2half_rn(v[j]);
         } else {
-          for (int j = 0; j < ncol; ++j) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + o;
+          for (int j = 0; j < nc; ++j) cp[j] = __float2bfloat16_rn(v[j]);
         }
-      } else if (p.dtype_out == 1) {
-        __half* cp = reinterpret_cast<__half*>(p.C) + o;
-        for (int j = 0; j < ncol; ++j) cp[j] = __float2half_rn(v[j]);
-      } else {
-        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + o;
-        for (int j = 0; j < ncol; ++j) cp[j] = __float2bfloat16_rn(v[j]);
       }
+      __syncwarp();
     }
   }
   tc::tcgen05_fence_before();

@@ -123,6 +123,35 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __half* h16 = reinterpret_cast<__half*>(a.h16);
   const size_t R = (size_t)T * N;
 
+  // side outputs of a finished step (h16 for the next layer, saved activations, transposed copy); issued while the
+  // NEXT step's LL poll loads are in flight, so they are off the recurrence's critical path
+  auto side_stores = [&](int t, const float (&hv)[NPT], const float (&gi)[NPT], const float (&gf)[NPT],
+                         const float (&gg)[NPT], const float (&go)[NPT], const float (&cs)[NPT]) {
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
+      h16[row * 2 * H + dir * H + u] = __float2half_rn(hv[i]);
+      if (a.h32) a.h32[row * 2 * H + dir * H + u] = hv[i];
+      if (a.training) {
+        float* gp = a.gates + (row * 2 + dir) * 4 * H;
+        gp[u] = gi[i]; gp[H + u] = gf[i]; gp[2 * H + u] = gg[i]; gp[3 * H + u] = go[i];
+        a.cell[(row * 2 + dir) * H + u] = cs[i];
+      }
+    }
+    if (a.training && a.hT16) {   // the thread's NPT samples are contiguous in the transposed copy: one 8-byte store
+      static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0] * mu[0], hv[1] * mu[1]),
+                           p1 = __floats2bfloat162_rn(hv[2] * mu[2], hv[3] * mu[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.hT16) + (size_t)(dir * H + u) * R +
+                                (size_t)t * N + n0 + warp * NPT) = pk;
+    }
+  };
+  float p_hv[NPT], p_gi[NPT], p_gf[NPT], p_gg[NPT], p_go[NPT], p_cs[NPT];
+  int p_t = -1;
+
   PROF_DECL;
   for (int s = 0; s < T; ++s) {
     PROF(7);
@@ -142,6 +171,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       uint2 w[WPT];
 #pragma unroll
       for (int q = 0; q < WPT; ++q) w[q] = ld_volatile_v2(src + q * THREADS);
+      if (p_t >= 0) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);   // overlaps the L2 round trip
       bool ok;
       long long t0 = 0;
       do {
@@ -237,30 +267,15 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
     }
     PROF(5);
-    // side outputs (not on the recurrence's critical path)
+    // stash this step's side outputs; they are written after the next step's poll loads have been issued
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
-      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
-      h16[row * 2 * H + dir * H + u] = __float2half_rn(hv[i]);
-      if (a.h32) a.h32[row * 2 * H + dir * H + u] = hv[i];
-      if (a.training) {
-        float* gp = a.gates + (row * 2 + dir) * 4 * H;
-        gp[u] = gi[i]; gp[H + u] = gf[i]; gp[2 * H + u] = gg[i]; gp[3 * H + u] = go[i];
-        a.cell[(row * 2 + dir) * H + u] = c_state[i];
-      }
+      p_hv[i] = hv[i]; p_gi[i] = gi[i]; p_gf[i] = gf[i]; p_gg[i] = gg[i]; p_go[i] = go[i]; p_cs[i] = c_state[i];
     }
-    if (a.training && a.hT16) {   // the thread's NPT samples are contiguous in the transposed copy: one 8-byte store
-      static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0] * mu[0], hv[1] * mu[1]),
-                           p1 = __floats2bfloat162_rn(hv[2] * mu[2], hv[3] * mu[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&p0);
-      pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.hT16) + (size_t)(dir * H + u) * R +
-                                (size_t)t * N + n0 + warp * NPT) = pk;
-    }
+    p_t = t;
     PROF(6);
   }
+  if (p_t >= 0 && !s_dead) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);   // last step
   PROF_DUMP(0);
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -356,6 +371,32 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __nv_bfloat16* dz16 = reinterpret_cast<__nv_bfloat16*>(a.dz16);
   const size_t R = (size_t)T * N;
 
+  auto side_stores = [&](int t, const float (&dz)[NPT][4]) {
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        dz16[(row * 2 + dir) * K4 + g * H + u] = __float2bfloat16_rn(dz[i][g]);
+        if (a.dz32) a.dz32[(row * 2 + dir) * K4 + g * H + u] = dz[i][g];
+      }
+    }
+    if (a.dzT16) {
+      static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]), p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.dzT16) + (size_t)(dir * K4 + g * H + u) * R +
+                                  (size_t)t * N + n0 + warp * NPT) = pk;
+      }
+    }
+  };
+  float p_dz[NPT][4];
+  int p_t = -1;
+
   PROF_DECL;
   for (int s = 0; s < T; ++s) {
     PROF(7);
@@ -384,6 +425,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         uint2 w[WPT1];
 #pragma unroll
         for (int q = 0; q < WPT1; ++q) w[q] = ld_volatile_v2(src + q * THREADS);
+        if (p_t >= 0) side_stores(p_t, p_dz);              // overlaps the L2 round trip
         bool ok;
         long long t0 = 0;
         do {
@@ -513,30 +555,18 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
     }
     PROF(5);
+    // stash the side outputs (dz for the dW/dU/dX GEMMs); written while the next hop-1 poll is in flight
 #pragma unroll
-    for (int i = 0; i < NPT; ++i) {
-      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
+    for (int i = 0; i < NPT; ++i)
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         db[g] += dz[i][g];
-        dz16[(row * 2 + dir) * K4 + g * H + u] = __float2bfloat16_rn(dz[i][g]);
-        if (a.dz32) a.dz32[(row * 2 + dir) * K4 + g * H + u] = dz[i][g];
+        p_dz[i][g] = dz[i][g];
       }
-    }
-    if (a.dzT16) {
-      static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]), p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&p0);
-        pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.dzT16) + (size_t)(dir * K4 + g * H + u) * R +
-                                  (size_t)t * N + n0 + warp * NPT) = pk;
-      }
-    }
+    p_t = t;
     PROF(6);
   }
+  if (p_t >= 0 && !s_dead) side_stores(p_t, p_dz);
   PROF_DUMP(8);
 #pragma unroll
   for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);

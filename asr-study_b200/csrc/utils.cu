@@ -85,6 +85,28 @@ mask_rows_kernel(const S* __restrict__ src, int64_t ld_src, const float* __restr
   }
 }
 
+// 16-bit source, 16-bit destination, cols % 8 == 0, 16-byte aligned rows: 8 elements per thread
+template <typename S, typename T>
+__global__ void __launch_bounds__(256)
+mask_rows_vec8_kernel(const S* __restrict__ src, int64_t ld_src, const float* __restrict__ mask, int nb,
+                      T* __restrict__ dst, int64_t ld_dst, int rows, int cols) {
+  const int c8n = cols >> 3;
+  const int total = rows * c8n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / c8n, c = (i - r * c8n) << 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (int64_t)r * ld_src + c);
+    const float4 m0 = *reinterpret_cast<const float4*>(mask + (int64_t)(r % nb) * cols + c);
+    const float4 m1 = *reinterpret_cast<const float4*>(mask + (int64_t)(r % nb) * cols + c + 4);
+    const S* e = reinterpret_cast<const S*>(&v);
+    const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) oe[k] = cvt<T>(ldf<S>(e + k) * mm[k]);
+    *reinterpret_cast<uint4*>(dst + (int64_t)r * ld_dst + c) = o;
+  }
+}
+
 template <typename S, typename T>
 __global__ void __launch_bounds__(256)
 mask_transpose_kernel(const S* __restrict__ src, int64_t ld_src, const float* __restrict__ mask, int nb,
@@ -159,6 +181,11 @@ static int32_t mask_cast_dispatch(const S* src, int64_t ld_src, const float* mas
     dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
     if (dtype == 0) mask_transpose_kernel<S, __half><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__half*)dst16, ld_dst, rows, cols);
     else mask_transpose_kernel<S, __nv_bfloat16><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__nv_bfloat16*)dst16, ld_dst, rows, cols);
+  } else if (sizeof(S) == 2 && cols % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0 && rows * (int64_t)(cols / 8) < (1LL << 31) &&
+             ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst16) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0) {
+    const int grid = grid_1d(rows * (int64_t)(cols / 8));
+    if (dtype == 0) mask_rows_vec8_kernel<S, __half><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__half*)dst16, ld_dst, (int)rows, cols);
+    else mask_rows_vec8_kernel<S, __nv_bfloat16><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__nv_bfloat16*)dst16, ld_dst, (int)rows, cols);
   } else {
     const int grid = grid_1d(rows * ((cols + 7) / 8 * 8));
     if (dtype == 0) mask_rows_kernel<S, __half><<<grid, 256, 0, st>>>(src, ld_src, mask, nb, (__half*)dst16, ld_dst, rows, cols);
