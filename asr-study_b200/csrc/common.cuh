@@ -61,6 +61,13 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// tanh through one ex2.approx and one fast divide: |abs error| ~1e-6 (the libdevice tanhf costs ~10x more
+// instructions and sits on the recurrence's critical path twice per step)
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
 // Keras-1 hard_sigmoid: clip(0.2x + 0.5, 0, 1)
 __device__ __forceinline__ float hard_sigmoid(float x) {
   return fminf(fmaxf(fmaf(0.2f, x, 0.5f), 0.0f), 1.0f);

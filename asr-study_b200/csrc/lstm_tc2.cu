@@ -251,10 +251,10 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     for (int i = 0; i < NPT; ++i) {
       gi[i] = asr::hard_sigmoid(z[i][0] + zx[i][0] + bias[0]);
       gf[i] = asr::hard_sigmoid(z[i][1] + zx[i][1] + bias[1]);
-      gg[i] = tanhf(z[i][2] + zx[i][2] + bias[2]);
+      gg[i] = asr::tanh_fast(z[i][2] + zx[i][2] + bias[2]);
       go[i] = asr::hard_sigmoid(z[i][3] + zx[i][3] + bias[3]);
       c_state[i] = gf[i] * c_state[i] + gi[i] * gg[i];
-      hv[i] = go[i] * tanhf(c_state[i]);
+      hv[i] = go[i] * asr::tanh_fast(c_state[i]);
       // publish h * B_U: even lanes pack (unit, unit+1) into one LL word {half2, tag = s+1}
       const float hm = hv[i] * mu[i];
       const float other = __shfl_down_sync(0xffffffffu, hm, 1);
@@ -533,7 +533,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
       const float dh = dho[i] + dh_rec[i];
-      const float tch = tanhf(cc[i]);
+      const float tch = asr::tanh_fast(cc[i]);
       const float d_o = dh * tch * asr::hard_sigmoid_grad(go[i]);
       const float dc = dc_carry[i] + dh * go[i] * (1.0f - tch * tch);
       dz[i][0] = dc * gg[i] * asr::hard_sigmoid_grad(gi[i]);

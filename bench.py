@@ -296,6 +296,66 @@ def kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch):
     return {k: round(v, 4) for k, v in res.items()}
 
 
+def run_infer(args):
+    """configs[4] (C5): MFCC -> 3xBiLSTM-512 forward -> CTC beam search (width 100) over synthetic 10 s clips on one
+    B200; prints clips/s and checks LER parity of the device decode against the oracle's TF-order beam search on a
+    sample of the same logits (identical label sequences => identical LER)."""
+    import torch
+
+    from asr_study_b200._lib import lib
+    from asr_study_b200.engine import AcousticEngine, ModelSpec
+    from asr_study_b200.preprocessing import audio
+    from oracle import ctc as oc
+    from oracle.model import synth_clip, synth_labels
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    nb, total, W = 64, args.clips, args.beam_width
+    feat = audio.MFCC(num_cep=13, d=True, dd=False)
+    eng = AcousticEngine(ModelSpec(F, H, L, C), device=dev, seed=4321)
+    # sharpen the random-init posteriors a little so beams are not degenerate
+    eng.params.p("dense.W").mul_(6.0)
+    pcm_np = np.stack([synth_clip(777, i, SECONDS, FS) for i in range(nb)])
+    pcm_host = torch.from_numpy(pcm_np.reshape(-1)).pin_memory()
+    off = (torch.arange(nb + 1, dtype=torch.int64) * pcm_np.shape[1]).to(dev)
+    truth = synth_labels(778, nb, 50)
+
+    def batch():
+        pcm = pcm_host.to(dev, non_blocking=True)
+        x, lens = feat.batch(pcm, off, t_max=T_FRAMES, time_major=True)
+        logits = eng.forward(x, training=False)
+        out, out_len = eng.beam(logits, lens, W, True)
+        return logits, lens, out.cpu(), out_len.cpu()
+
+    for _ in range(2):
+        logits, lens, out, out_len = batch()
+    torch.cuda.synchronize()
+    nbatches = max(1, total // nb)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.asr_launch_count()
+    e0.record()
+    for _ in range(nbatches):
+        logits, lens, out, out_len = batch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = (lib.asr_launch_count() - l0) // nbatches
+    # LER parity on a sample: oracle beam on the SAME logits
+    k = min(args.ler_sample, nb)
+    lg = logits[:, :k].transpose(0, 1).contiguous().cpu().numpy()
+    ref = oc.beam_decode(lg, [T_FRAMES] * k, beam_width=W)
+    got = [[int(v) for v in out[i, :int(out_len[i])]] for i in range(k)]
+    same = sum(int(a == b) for a, b in zip(got, ref))
+    res = {"metric": "clips/sec (inference: MFCC -> 3xBiLSTM-512 fwd -> CTC beam search width %d)" % W,
+           "value": nb * nbatches / (ms / 1e3), "unit": "clips/s", "n_gpus": 1, "clips": nb * nbatches,
+           "ms_per_batch": ms / nbatches, "batch": nb, "higher_is_better": True, "data": "synthetic",
+           "config": {"workload": "C5: synthetic 16 kHz 10 s clips, 26-MFCC, 3xBiLSTM-512, beam %d, host pcm -> labels" % W},
+           "gpu_launches": int(launches),
+           "ler_parity": {"sample": k, "identical_label_sequences": same,
+                          "ler_device_vs_truth": oc.ler(truth[:k], got), "ler_oracle_vs_truth": oc.ler(truth[:k], ref)}}
+    print(json.dumps(res), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -305,9 +365,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dropout", type=float, default=0.2, help="brsmv1 dropout_W = dropout_U (reference default 0.2)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train = C2/C3 (default), infer = C5")
+    ap.add_argument("--clips", type=int, default=1024)
+    ap.add_argument("--beam_width", type=int, default=100)
+    ap.add_argument("--ler_sample", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "infer":
+        run_infer(args)
     else:
         run_ours(args)
 
