@@ -17,6 +17,10 @@ size_t scratch_bytes(int H);
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
 int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st);
 }
+namespace lstmtc3 {
+bool supports_fwd(const asr_lstm_fwd_args* a);
+int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
+}
 namespace lstmtc2 {
 bool supports_fwd(const asr_lstm_fwd_args* a);
 bool supports_bwd(const asr_lstm_bwd_args* a);
@@ -74,7 +78,9 @@ extern "C" int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream) {
   ASR_CHECK_ARG(!a->training || (a->gates && a->cell), "asr_lstm_forward: training needs gates/cell buffers");
   cudaStream_t st = (cudaStream_t)stream;
   if (!env_is("ASR_B200_LSTM", "fp32")) {
-    if (!env_is("ASR_B200_LSTM", "tc1") && lstmtc2::supports_fwd(a)) return lstmtc2::forward(a, st);
+    const bool pin1 = env_is("ASR_B200_LSTM", "tc1"), pin3 = env_is("ASR_B200_LSTM", "tc3");
+    if (pin3 && lstmtc3::supports_fwd(a)) return lstmtc3::forward(a, st);              // cluster / DSMEM exchange (same speed, kept selectable)
+    if (!pin1 && lstmtc2::supports_fwd(a)) return lstmtc2::forward(a, st);             // LL ring through L2 (default)
     if (lstmtc::supports_fwd(a)) return lstmtc::forward(a, st);
   }
   ASR_CHECK_ARG(a->U, "asr_lstm_forward: fp32 engine needs U");

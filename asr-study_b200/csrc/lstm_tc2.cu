@@ -43,6 +43,11 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) {
   asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {      // two LL words per access
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_volatile_v2(uint2* p, uint2 v) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
@@ -166,20 +171,23 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     float z[NPT][4];
     if (s > 0) {
       // ---- pull h_{t-1} of this group: poll the LL words (data + tag in one 8-byte access) ----------
-      const uint2* src = xb + (size_t)((s - 1) & 1) * WORDS + tid;
+      // side outputs of the previous step first: the extra ~350 cycles let the peers' LL words land in L2, so
+      // the first probe usually hits (a probe that races the store costs a second full L2 round trip)
+      if (p_t >= 0) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);
+      const uint4* src = reinterpret_cast<const uint4*>(xb + (size_t)((s - 1) & 1) * WORDS) + tid;
       const uint32_t tag = (uint32_t)s;
-      uint2 w[WPT];
+      constexpr int QPT = WPT / 2;                        // 16-byte accesses per thread (2 LL words each)
+      uint4 w[QPT];
 #pragma unroll
-      for (int q = 0; q < WPT; ++q) w[q] = ld_volatile_v2(src + q * THREADS);
-      if (p_t >= 0) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);   // overlaps the L2 round trip
+      for (int q = 0; q < QPT; ++q) w[q] = ld_volatile_v4(src + q * THREADS);
       bool ok;
       long long t0 = 0;
       do {
         ok = true;
 #pragma unroll
-        for (int q = 0; q < WPT; ++q)
-          if (w[q].y != tag) {
-            w[q] = ld_volatile_v2(src + q * THREADS);
+        for (int q = 0; q < QPT; ++q)
+          if (w[q].y != tag || w[q].w != tag) {
+            w[q] = ld_volatile_v4(src + q * THREADS);
             ok = false;
           }
         if (!ok) {
@@ -193,10 +201,10 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       } while (!ok);
       PROF(0);
 #pragma unroll
-      for (int q = 0; q < WPT; ++q) {
-        const int i = tid + q * THREADS;
-        const int n = i / (H / 2), k = 2 * (i % (H / 2));
-        *reinterpret_cast<uint32_t*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = w[q].x;
+      for (int q = 0; q < QPT; ++q) {
+        const int i = 2 * (tid + q * THREADS);             // first of the two LL words (consecutive K pairs)
+        const int n = i / (H / 2), k = 2 * (i % (H / 2));  // k % 4 == 0: both pairs sit in one 8-byte smem slot
+        *reinterpret_cast<uint2*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = make_uint2(w[q].x, w[q].z);
       }
       tc::fence_proxy_async_smem();
       __syncthreads();
@@ -421,19 +429,20 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       const int par = (s - 1) & 1;
       // ---- hop 1: dz_{prev} of my column block -> smem B ------------------------------------------
       {
-        const uint2* src = x1 + (size_t)par * WORDS1 + tid;
-        uint2 w[WPT1];
+        if (p_t >= 0) side_stores(p_t, p_dz);              // first: gives the peers' LL words time to land in L2
+        const uint4* src = reinterpret_cast<const uint4*>(x1 + (size_t)par * WORDS1) + tid;
+        constexpr int QPT1 = WPT1 / 2;
+        uint4 w[QPT1];
 #pragma unroll
-        for (int q = 0; q < WPT1; ++q) w[q] = ld_volatile_v2(src + q * THREADS);
-        if (p_t >= 0) side_stores(p_t, p_dz);              // overlaps the L2 round trip
+        for (int q = 0; q < QPT1; ++q) w[q] = ld_volatile_v4(src + q * THREADS);
         bool ok;
         long long t0 = 0;
         do {
           ok = true;
 #pragma unroll
-          for (int q = 0; q < WPT1; ++q)
-            if (w[q].y != tag) {
-              w[q] = ld_volatile_v2(src + q * THREADS);
+          for (int q = 0; q < QPT1; ++q)
+            if (w[q].y != tag || w[q].w != tag) {
+              w[q] = ld_volatile_v4(src + q * THREADS);
               ok = false;
             }
           if (!ok) {
@@ -447,10 +456,10 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         } while (!ok);
         PROF(0);
 #pragma unroll
-        for (int q = 0; q < WPT1; ++q) {
-          const int i = tid + q * THREADS;
+        for (int q = 0; q < QPT1; ++q) {
+          const int i = 2 * (tid + q * THREADS);
           const int n = i >> 8, k = 2 * (i & 255);
-          *reinterpret_cast<uint32_t*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = w[q].x;
+          *reinterpret_cast<uint2*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = make_uint2(w[q].x, w[q].z);
         }
       }
       tc::fence_proxy_async_smem();

@@ -30,8 +30,8 @@ def _device_fwd(p, x_ntd, training=True, engine=None):
     """x [N,T,D] -> runs zx GEMM in torch fp32 (operand prep is not under test here) + asr_lstm_forward."""
     from asr_study_b200._lib import LstmFwdArgs, lib, ptr, cur_stream
     os.environ.pop("ASR_B200_LSTM", None)
-    if engine == "fp32":
-        os.environ["ASR_B200_LSTM"] = "fp32"
+    if engine in ("fp32", "tc1", "tc3"):
+        os.environ["ASR_B200_LSTM"] = engine
     N, T, D = x_ntd.shape
     H = p["Uf"].shape[0]
     x = dev(x_ntd.transpose(1, 0, 2)).reshape(T * N, D)
@@ -199,3 +199,21 @@ def test_tensor_core_engine_T999_drift():
     fwd, _ = _device_fwd(p, x, training=False, engine="tc")
     h = fwd["h32"].cpu().numpy().reshape(T, N, 2 * H).transpose(1, 0, 2)
     assert norm_err(h, ref) < 1e-3, norm_err(h, ref)
+
+
+@pytest.mark.parametrize("engine", ["tc3", "tc"])
+@pytest.mark.parametrize("N,T,D,H", [(32, 60, 26, 512), (16, 33, 26, 256), (16, 20, 26, 128)])
+def test_forward_engines_agree_and_match_oracle(engine, N, T, D, H):
+    """LL-ring engine (default 'tc') and cluster/DSMEM engine (tc3) against the oracle on the same inputs."""
+    rng = np.random.RandomState(H + T)
+    p = _params(rng, D, H, scale=1.5)
+    x = rng.randn(N, T, D).astype(np.float32)
+    ref, caches, _, _ = _oracle(p, x, np.zeros((N, T, 2 * H), np.float32))
+    fwd, _ = _device_fwd(p, x, engine=engine)
+    h32 = fwd["h32"].cpu().numpy().reshape(T, N, 2 * H).transpose(1, 0, 2)
+    assert norm_err(h32, ref) < 1e-3, norm_err(h32, ref)
+    c = fwd["cell"].cpu().numpy().reshape(T, N, 2, H)
+    for d in range(2):
+        assert norm_err(c[:, :, d].transpose(1, 0, 2), caches[d]["cs"]) < 1e-3
+    hT = fwd["hT16"].float().cpu().numpy().reshape(2 * H, T, N).transpose(2, 1, 0)
+    assert norm_err(hT, ref) < 8e-3
