@@ -16,6 +16,7 @@
 // Semantics: core/layers.py:432-469 under Keras-1 Bidirectional, no masking (see lstm_fp32.cu).
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace lstmtc2 {
 
@@ -54,7 +55,7 @@ __device__ __forceinline__ void st_volatile_v2(uint2* p, uint2 v) {
 
 template <int H>
 __global__ void __launch_bounds__(THREADS, 1)
-fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf) {
+fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf, int delay1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int KC = H / 64;
@@ -174,6 +175,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       // side outputs of the previous step first: the extra ~350 cycles let the peers' LL words land in L2, so
       // the first probe usually hits (a probe that races the store costs a second full L2 round trip)
       if (p_t >= 0) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);
+      if (delay1 > 0) __nanosleep(delay1);
       const uint4* src = reinterpret_cast<const uint4*>(xb + (size_t)((s - 1) & 1) * WORDS) + tid;
       const uint32_t tag = (uint32_t)s;
       constexpr int QPT = WPT / 2;                        // 16-byte accesses per thread (2 LL words each)
@@ -302,7 +304,8 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 //          element-wise BPTT -> dz (published to hop 1 of the next step) + side outputs
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
-bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf1, uint2* __restrict__ xbuf2) {
+bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf1, uint2* __restrict__ xbuf2, int delay1,
+           int delay2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int H = 512, K4 = 4 * H;
@@ -430,6 +433,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       // ---- hop 1: dz_{prev} of my column block -> smem B ------------------------------------------
       {
         if (p_t >= 0) side_stores(p_t, p_dz);              // first: gives the peers' LL words time to land in L2
+        if (delay1 > 0) __nanosleep(delay1);
         const uint4* src = reinterpret_cast<const uint4*>(x1 + (size_t)par * WORDS1) + tid;
         constexpr int QPT1 = WPT1 / 2;
         uint4 w[QPT1];
@@ -502,6 +506,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       // ---- hop 2 (receive): four partials for each of my (unit, sample) ---------------------------------
       {
         uint2 w[4 * NPT];
+        if (delay2 > 0) __nanosleep(delay2);
         const uint2* src = x2row + ((size_t)(c * 4) * 2 + par) * WORDS2 + lane;   // + send*2*WORDS2 + n*32
 #pragma unroll
         for (int sd = 0; sd < 4; ++sd)
@@ -597,6 +602,11 @@ constexpr size_t X1_BYTES_PER_DG = (size_t)4 * 2 * NG * 256 * sizeof(uint2);    
 constexpr size_t X2_BYTES_PER_DG = (size_t)4 * 4 * 4 * 2 * NG * 32 * sizeof(uint2);     // hop 2 per (dir, grp)
 size_t scratch_bytes(int) { return HEADER_BYTES + (size_t)2 * 8 * (X1_BYTES_PER_DG + X2_BYTES_PER_DG); }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <int H>
 static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   constexpr int KC = H / 64;
@@ -608,7 +618,8 @@ static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   asr_lstm_fwd_args args = *a;
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
-  void* kargs[] = {&args, &flags, &xbuf};
+  int delay1 = env_int("ASR_LSTM_FWD_DELAY_NS", 0);
+  void* kargs[] = {&args, &flags, &xbuf, &delay1};
   ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
   asr::count_launch();
   return ASR_OK;
@@ -625,7 +636,8 @@ int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
   int* flags = a->flags;
   uint2* xbuf1 = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
   uint2* xbuf2 = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES + x1);
-  void* kargs[] = {&args, &flags, &xbuf1, &xbuf2};
+  int delay1 = env_int("ASR_LSTM_BWD_DELAY1_NS", 0), delay2 = env_int("ASR_LSTM_BWD_DELAY2_NS", 0);
+  void* kargs[] = {&args, &flags, &xbuf1, &xbuf2, &delay1, &delay2};
   ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd_kernel, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
   asr::count_launch();
   return ASR_OK;

@@ -110,6 +110,8 @@ class AcousticEngine:
         self._sqnorm = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._flags = torch.zeros(lib.asr_lstm_flags_bytes() // 4, dtype=torch.int32, device=self.device)
         self._weights_version = -1
+        self._side = torch.cuda.Stream(device=self.device)      # gradient GEMMs that overlap the next recurrence
+        self.overlap = False     # measured: no gain — GEMM CTAs cannot co-reside with the recurrence CTAs (whole TMEM owned)
         self._mask_rng = torch.Generator(device=self.device)
         self._mask_rng.manual_seed(seed + 17)
 
@@ -191,8 +193,9 @@ class AcousticEngine:
             w["dlT16"] = self._buf("dlT16", (Cc, R), torch.bfloat16)
             w["dhA"] = self._buf("dhA", (R, 2 * H), torch.float32)
             w["dhB"] = self._buf("dhB", (R, 2 * H), torch.float32)
-            w["dz16"] = self._buf("dz16", (R, 8 * H), torch.bfloat16)
-            w["dzT16"] = self._buf("dzT16", (8 * H, R), torch.bfloat16)
+            for l in range(L):      # per layer: the dW/dU GEMMs of layer l overlap the recurrence of layer l-1
+                w[f"dz16.{l}"] = self._buf(f"dz16.{l}", (R, 8 * H), torch.bfloat16)
+                w[f"dzT16.{l}"] = self._buf(f"dzT16.{l}", (8 * H, R), torch.bfloat16)
             w["loss"] = self._buf("loss", (N,), torch.float32)
         return w
 
@@ -348,34 +351,41 @@ class AcousticEngine:
             a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(w[f"gates.{l}"]).value,
                             cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"Ub16.{l}"]).value,
-                            dz16=ptr(w["dz16"]).value, dzT16=ptr(w["dzT16"]).value, dz32=None,
+                            dz16=ptr(w[f"dz16.{l}"]).value, dzT16=ptr(w[f"dzT16.{l}"]).value, dz32=None,
                             dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value,
                             mask_u=ptr(mask_u).value if mask_u is not None else None)
             lib.asr_lstm_backward(C.byref(a), st)
             D = sp.num_features if l == 0 else 2 * H
             xT = w["xT16"] if l == 0 else w[f"hT16.{l - 1}"]
             hT = w[f"hT16.{l}"]
-            dzT = w["dzT16"]
-            for i, d in enumerate("fb"):
-                # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
-                xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
-                self._gemm(BF16, OUT_F32, D, 4 * H, R, xTd, R, dzT[i * 4 * H:], R, P.g(f"l{l}.W{d}"), 4 * H)
-                # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
-                if T > 1:
-                    Kk = (T - 1) * N
-                    hA = hT[i * H:(i + 1) * H]
-                    dzB = dzT[i * 4 * H:(i + 1) * 4 * H]
-                    if i == 0:   # forward direction: h_{t-1} with dz_t
-                        Ap, Bp = hA, dzB[:, N:]
-                    else:        # reverse direction: h_{t+1} with dz_t
-                        Ap, Bp = hA[:, N:], dzB
-                    lib.asr_gemm_tn(BF16, OUT_F32, H, 4 * H, Kk, C.c_void_p(Ap.data_ptr()), R,
-                                    C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, st)
-                else:
-                    P.g(f"l{l}.U{d}").zero_()
+            dzT = w[f"dzT16.{l}"]
+            main = torch.cuda.current_stream()
+            side = self._side if self.overlap else main
+            if side is not main:
+                side.wait_stream(main)                      # dz of this layer is complete
+            with torch.cuda.stream(side):
+                sst = cur_stream()
+                for i, d in enumerate("fb"):
+                    # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
+                    xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
+                    lib.asr_gemm_tn(BF16, OUT_F32, D, 4 * H, R, ptr(xTd), R, ptr(dzT[i * 4 * H:]), R,
+                                    ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, sst)
+                    # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
+                    if T > 1:
+                        Kk = (T - 1) * N
+                        hA = hT[i * H:(i + 1) * H]
+                        dzB = dzT[i * 4 * H:(i + 1) * 4 * H]
+                        if i == 0:   # forward direction: h_{t-1} with dz_t
+                            Ap, Bp = hA, dzB[:, N:]
+                        else:        # reverse direction: h_{t+1} with dz_t
+                            Ap, Bp = hA[:, N:], dzB
+                        lib.asr_gemm_tn(BF16, OUT_F32, H, 4 * H, Kk, C.c_void_p(Ap.data_ptr()), R,
+                                        C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, sst)
+                    else:
+                        P.g(f"l{l}.U{d}").zero_()
             if l > 0 and masks is None:
                 # dX [R, 2H] = dz16 [R, 8H] . Wcat16 [2H, 8H]^T
-                self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w["dz16"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
+                self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w[f"dz16.{l}"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
                            other, 2 * H)
                 dh, other = other, dh
             elif l > 0:
@@ -383,12 +393,14 @@ class AcousticEngine:
                 part = [self._buf(f"dxpart.{i}", (R, 2 * H), torch.float32) for i in range(2)]
                 wc = self._views[f"Wcat16.{l}"]
                 for i in range(2):
-                    lib.asr_gemm_tn(BF16, OUT_F32, R, 2 * H, 4 * H, ptr(w["dz16"][:, i * 4 * H:]), 8 * H,
+                    lib.asr_gemm_tn(BF16, OUT_F32, R, 2 * H, 4 * H, ptr(w[f"dz16.{l}"][:, i * 4 * H:]), 8 * H,
                                     ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), 2 * H, None, 1.0, 0, st)
                 mk = masks[l]
                 lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
                                      ptr(other), R, 2 * H, st)
                 dh, other = other, dh
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self._side)
 
     # -------------------------------------------------------------- optimiser
     def optimizer_step(self, lr=1e-3, clipnorm=400.0, beta1=0.9, beta2=0.999, eps=1e-8, opt="adam",

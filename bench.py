@@ -219,16 +219,31 @@ def run_ours(args):
     out = None
     if rank == 0:
         step_tf = value * GFLOP_TRAIN_PER_UTT / 1e3 / world                       # TFLOP/s per GPU
-        roof = {"bound": "tensor", "kernel": "whole step (LSTM-GEMM roofline, BASELINE.md section 4)",
-                "achieved": step_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": step_tf / pk["tf_sust"],
-                "peak_source": pk["src"] + " bf16_tflops_sustained", "traffic": None,
-                "mma_precision": "fp16 fwd / bf16 bwd operands, fp32 accumulate"}
-        if kern.get("lstm_fwd_ms"):
-            gf = 2 * 2.0 * T_FRAMES * nb * H * 4 * H / 1e9                       # one launch: both directions
-            roof["dominant_kernel"] = {"name": "lstm_fwd (per layer launch)", "gflop_per_launch": gf,
-                                       "ms_per_launch": kern["lstm_fwd_ms"] / L,
-                                       "achieved_tflops": gf / (kern["lstm_fwd_ms"] / L),
-                                       "frac": gf / (kern["lstm_fwd_ms"] / L) / pk["tf_burst"]}
+        gf = 2 * 2.0 * T_FRAMES * nb * H * 4 * H / 1e9                           # recurrent matmul of ONE launch (2 dirs)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
+        # dominant kernel = the backward recurrence (largest share of the step, profiles/ncu_summary_*.md)
+        ms_bwd = kern.get("lstm_bwd_ms", 0.0) / L
+        ms_fwd = kern.get("lstm_fwd_ms", 0.0) / L
+        roof = {"bound": "tensor", "kernel": "lstmtc2::bwd_kernel (persistent BiLSTM BPTT, one launch per layer)",
+                "achieved": gf / ms_bwd if ms_bwd else None, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                "frac": (gf / ms_bwd / pk["tf_burst"]) if ms_bwd else None,
+                "peak_source": pk["src"] + " bf16_tflops (burst; kernel timed alone with CUDA events)",
+                "flop_per_launch": gf * 1e9, "ms_per_launch": ms_bwd,
+                "traffic": (traffic or {}).get("lstm_bwd_bytes_per_launch"),
+                "mma_precision": "bf16 operands, fp32 accumulate (TS-mode tcgen05.mma, U tile resident in TMEM)",
+                "note": "latency-bound by design at N=32: 999 dependent steps per launch; see profiles/lstm_phases_r1.md",
+                "others": {
+                    "lstm_fwd": {"achieved": gf / ms_fwd if ms_fwd else None, "ms_per_launch": ms_fwd,
+                                 "frac": (gf / ms_fwd / pk["tf_burst"]) if ms_fwd else None,
+                                 "traffic": (traffic or {}).get("lstm_fwd_bytes_per_launch")},
+                    "gemm_all": {"achieved": (2.0 / 3.0) * gb / world * GFLOP_TRAIN_PER_UTT / kern["gemm_ms"] if kern.get("gemm_ms") else None,
+                                 "ms_per_step": kern.get("gemm_ms"), "unit": "TFLOP/s"},
+                    "whole_step_vs_lstm_gemm_roofline": {"achieved": step_tf, "peak": pk["tf_sust"],
+                                                         "frac": step_tf / pk["tf_sust"],
+                                                         "peak_source": pk["src"] + " bf16_tflops_sustained"}}}
         out = {"metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "fp16/bf16 tensor-core operands, fp32 accumulate+state",
