@@ -319,6 +319,185 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
   }
 }
 
+// ---- multi-warp lattice variant (S <= 128): warps 0-3 walk alpha, warps 4-7 walk beta, one lattice state per
+// lane; the previous frame's row lives in double-buffered shared memory, one 128-thread named barrier per frame.
+// Rows are stored un-normalised for ONE frame (the row maximum is published next to the row and subtracted by
+// the readers), and the running sum of maxima is the fp64 offset: alpha_t(s) = stored + offA[t].
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(CTC_THREADS)
+ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, const int* __restrict__ in_len,
+                        const int* __restrict__ labels, const int* __restrict__ label_off, int s_max, int blank,
+                        float grad_scale, float* __restrict__ loss, float* __restrict__ grad, float* __restrict__ ws) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = min(max(in_len[n], 0), T);
+  const int l0 = label_off[n], L = label_off[n + 1] - l0;
+  const int S = 2 * L + 1;
+  const float NEG = -CUDART_INF_F;
+  const size_t fl_per = ((size_t)2 * T * s_max + T + 1) & ~(size_t)1;
+  float* w_alpha = ws + (size_t)n * (fl_per + 4 * (size_t)T);
+  float* w_beta = w_alpha + (size_t)T * s_max;
+  float* w_lse = w_beta + (size_t)T * s_max;
+  double* w_offA = reinterpret_cast<double*>(w_alpha + fl_per);
+  double* w_offB = w_offA + T;
+
+  int* ext = reinterpret_cast<int*>(sm);              // [132]
+  float* rowA = sm + 132;                             // [2][132]: 2 pads in front
+  float* rowB = rowA + 2 * 132;                       // [2][132]: states at [0,128), 2 pads at [128,130)
+  float* mxA = rowB + 2 * 132;                        // [2][4]
+  float* mxB = mxA + 8;                               // [2][4]
+  float* acc = mxB + 8;                               // [CTC_WARPS][C]
+  __shared__ double s_logp;
+
+  for (int s = tid; s < 132; s += CTC_THREADS) ext[s] = (s < S && (s & 1)) ? labels[l0 + (s >> 1)] : blank;
+  for (int t = warp; t < len; t += CTC_WARPS) {
+    const float* row = logits + ((size_t)t * N + n) * C;
+    float m = NEG;
+    for (int k = lane; k < C; k += 32) m = fmaxf(m, row[k]);
+    m = asr::warp_max(m);
+    float sx = 0.0f;
+    for (int k = lane; k < C; k += 32) sx += expf(row[k] - m);
+    sx = asr::warp_sum(sx);
+    if (lane == 0) w_lse[t] = m + logf(sx);
+  }
+  if (tid < 2) { rowA[tid] = NEG; rowA[132 + tid] = NEG; rowB[128 + tid] = NEG; rowB[132 + 128 + tid] = NEG; }
+  __syncthreads();
+  if (len == 0) {
+    if (tid == 0) loss[n] = CUDART_INF_F;
+    for (int i = tid; i < T * C; i += CTC_THREADS) grad[((size_t)(i / C) * N + n) * C + (i % C)] = 0.0f;
+    return;
+  }
+
+  if (warp < 4) {                                     // ---------------- alpha ----------------
+    const int s = warp * 32 + lane;
+    const int lab = ext[s];
+    const bool skip = (s >= 2) && (s < S) && (lab != blank) && (lab != ext[s - 2]);
+    double off = 0.0;
+    float a = (s < 2 && s < S) ? logits[(size_t)n * C + lab] - w_lse[0] : NEG;
+    {
+      if (s < S) w_alpha[s] = a;
+      (rowA + 2)[s] = a;
+      const float wm = asr::warp_max(a);
+      if (lane == 0) mxA[warp] = wm;
+      if (tid == 0) w_offA[0] = 0.0;
+    }
+    float x = 0.0f, z = 0.0f;
+    if (len > 1) { x = logits[((size_t)1 * N + n) * C + lab]; z = w_lse[1]; }
+    named_bar_sync(1, 128);
+    for (int t = 1; t < len; ++t) {
+      const float* prev = rowA + ((t - 1) & 1) * 132 + 2;
+      const float* pm = mxA + ((t - 1) & 1) * 4;
+      const float M = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
+      float xn = 0.0f, zn = 0.0f;
+      if (t + 1 < len) { xn = logits[((size_t)(t + 1) * N + n) * C + lab]; zn = w_lse[t + 1]; }
+      const float p0 = prev[s], p1 = prev[s - 1], p2 = skip ? prev[s - 2] : NEG;
+      float v = lse3(p0, p1, p2);
+      v = (v > NEG && M > NEG) ? v - M + (x - z) : NEG;
+      a = (s < S) ? v : NEG;
+      off += (M > NEG) ? (double)M : 0.0;
+      if (s < S) w_alpha[(size_t)t * s_max + s] = a;
+      (rowA + (t & 1) * 132 + 2)[s] = a;
+      const float wm = asr::warp_max(a);
+      if (lane == 0) mxA[(t & 1) * 4 + warp] = wm;
+      if (tid == 0) w_offA[t] = off;
+      x = xn; z = zn;
+      named_bar_sync(1, 128);
+    }
+    if (tid == 0) {
+      const float* last = rowA + ((len - 1) & 1) * 132 + 2;
+      const float tail = (S > 1) ? lse2(last[S - 1], last[S - 2]) : last[S - 1];
+      s_logp = (tail > NEG) ? off + (double)tail : -(double)CUDART_INF;
+    }
+  } else {                                            // ---------------- beta ----------------
+    const int w4 = warp - 4;
+    const int s = w4 * 32 + lane;
+    const int lab = ext[s];
+    const bool skip = (s + 2 < S) && (ext[s + 2] != blank) && (ext[s + 2] != lab);
+    double off = 0.0;
+    float b = (s < S && s >= S - 2) ? logits[((size_t)(len - 1) * N + n) * C + lab] - w_lse[len - 1] : NEG;
+    {
+      if (s < S) w_beta[(size_t)(len - 1) * s_max + s] = b;
+      (rowB + ((len - 1) & 1) * 132)[s] = b;
+      const float wm = asr::warp_max(b);
+      if (lane == 0) mxB[((len - 1) & 1) * 4 + w4] = wm;
+      if (tid == 128) w_offB[len - 1] = 0.0;
+    }
+    float x = 0.0f, z = 0.0f;
+    if (len > 1) { x = logits[((size_t)(len - 2) * N + n) * C + lab]; z = w_lse[len - 2]; }
+    named_bar_sync(2, 128);
+    for (int t = len - 2; t >= 0; --t) {
+      const float* nxt = rowB + ((t + 1) & 1) * 132;
+      const float* pm = mxB + ((t + 1) & 1) * 4;
+      const float M = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
+      float xn = 0.0f, zn = 0.0f;
+      if (t > 0) { xn = logits[((size_t)(t - 1) * N + n) * C + lab]; zn = w_lse[t - 1]; }
+      const float p0 = nxt[s], p1 = nxt[s + 1], p2 = skip ? nxt[s + 2] : NEG;
+      float v = lse3(p0, p1, p2);
+      v = (v > NEG && M > NEG) ? v - M + (x - z) : NEG;
+      b = (s < S) ? v : NEG;
+      off += (M > NEG) ? (double)M : 0.0;
+      if (s < S) w_beta[(size_t)t * s_max + s] = b;
+      (rowB + (t & 1) * 132)[s] = b;
+      const float wm = asr::warp_max(b);
+      if (lane == 0) mxB[(t & 1) * 4 + w4] = wm;
+      if (tid == 128) w_offB[t] = off;
+      x = xn; z = zn;
+      named_bar_sync(2, 128);
+    }
+  }
+  __syncthreads();
+
+  const double logp = s_logp;
+  if (tid == 0) loss[n] = (float)(-logp);
+  const bool feasible = logp > -(double)CUDART_INF;
+  float* my = acc + warp * C;
+  for (int t = warp; t < T; t += CTC_WARPS) {
+    float* g = grad + ((size_t)t * N + n) * C;
+    if (t >= len || !feasible) {
+      for (int k = lane; k < C; k += 32) g[k] = 0.0f;
+      continue;
+    }
+    const float* row = logits + ((size_t)t * N + n) * C;
+    const float z = w_lse[t];
+    const float kf = (float)(w_offA[t] + w_offB[t] - logp);
+    for (int k = lane; k < C; k += 32) my[k] = 0.0f;
+    float v[4], m = NEG;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int s = j * 32 + lane;
+      v[j] = (s < S) ? w_alpha[(size_t)t * s_max + s] + w_beta[(size_t)t * s_max + s] : NEG;
+      m = fmaxf(m, v[j]);
+    }
+    m = asr::warp_max(m);
+    __syncwarp();
+    float bsum = 0.0f;
+    if (m > NEG) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s = j * 32 + lane;
+        if (s < S) {
+          const float e = expf(v[j] - m);
+          if (s & 1) atomicAdd(my + ext[s], e);
+          else bsum += e;
+        }
+      }
+    }
+    bsum = asr::warp_sum(bsum);
+    if (lane == 0) atomicAdd(my + blank, bsum);
+    __syncwarp();
+    for (int k = lane; k < C; k += 32) {
+      const float lp = row[k] - z;
+      float occ = 0.0f;
+      if (my[k] > 0.0f) occ = my[k] * expf(m + kf - lp);
+      g[k] = grad_scale * (expf(lp) - occ);
+    }
+    __syncwarp();
+  }
+}
+
 // ---- best path ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ctc_greedy_kernel(const float* __restrict__ logits, int T, int N, int C,
@@ -387,8 +566,8 @@ extern "C" int32_t asr_ctc_loss_grad(const float* logits, int32_t T, int32_t N, 
   const int s_max = 2 * max_label_len + 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (s_max <= 128) {
-    const size_t smem = (size_t)(3 * 32 * 4 + 4 + CTC_WARPS * C) * sizeof(float);
-    ctc_loss_grad_kernel<4><<<N, CTC_THREADS, smem, st>>>(logits, T, N, C, in_len, labels, label_off, s_max, blank,
+    const size_t smem = (size_t)(132 + 4 * 132 + 16 + CTC_WARPS * C) * sizeof(float);
+    ctc_loss_grad_mw_kernel<<<N, CTC_THREADS, smem, st>>>(logits, T, N, C, in_len, labels, label_off, s_max, blank,
                                                            grad_scale, loss, grad, (float*)ws);
   } else {
     const size_t smem = (size_t)(3 * 32 * 16 + 4 + CTC_WARPS * C) * sizeof(float);
