@@ -25,7 +25,11 @@ namespace {
 __device__ __forceinline__ float lse2f(float a, float b) {
   const float m = fmaxf(a, b);
   if (m == -CUDART_INF_F) return m;
-  return m + log1pf(expf(fminf(a, b) - m));
+  // TF: max + log1pf(expf(-|a-b|)) with glibc's (practically correctly rounded) float functions.  Evaluated in
+  // fp64 and rounded to fp32 at the same two points so the device and the CPU oracle agree bit for bit; with the
+  // device's own expf/log1pf (1-2 ulp) a 999-frame, width-100 search drifts onto a different beam at near ties.
+  const float e = (float)exp((double)(fminf(a, b) - m));
+  return m + (float)log1p((double)e);
 }
 
 struct Br {           // branch arrays (one buffer)

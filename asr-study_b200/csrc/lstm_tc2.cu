@@ -31,7 +31,7 @@ namespace lstmtc2 {
 #endif
 
 constexpr int UPC = 32;
-constexpr int NG = 16;
+constexpr int NM = 16;                                    // MMA N (M = 128 needs a multiple of 16); sample rows of the B operand
 constexpr int THREADS = 128;
 constexpr int STATUS_IDX = 64;
 constexpr int HEADER_BYTES = 8192;
@@ -53,24 +53,27 @@ __device__ __forceinline__ void st_volatile_v2(uint2* p, uint2 v) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
-template <int H>
+// NB = samples per CTA group (8 or 16).  NB = 8 spreads N = 32 over 128 CTAs instead of 64: the MMA still runs at
+// N = 16 (rows 8..15 of the B operand stay zero, their accumulator columns are never read) and costs the same issue
+// slots, while the LL exchange, the shared-memory staging and the gate math per CTA are halved.
+template <int H, int NB>
 __global__ void __launch_bounds__(THREADS, 1)
 fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf, int delay1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int KC = H / 64;
-  constexpr int B_CHUNK = NG * 128;
-  constexpr int WORDS = NG * H / 2;                      // LL words per (dir, group, parity)
+  constexpr int B_CHUNK = NM * 128;
+  constexpr int WORDS = NB * H / 2;                      // LL words per (dir, group, parity)
   constexpr int WPT = WORDS / THREADS;
-  constexpr int NPT = NG / 4;
+  constexpr int NPT = NB / 4;
   const int T = a.T, N = a.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
-  const int u0 = cta * UPC, n0 = grp * NG;
+  const int u0 = cta * UPC, n0 = grp * NB;
 
-  uint8_t* sB = smem;                                    // KC chunks of [NG rows x 128 B], SW128 K-major
-  float* sZ = reinterpret_cast<float*>(sB + KC * B_CHUNK);   // [4 gates][NG][32 units]
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sZ + 4 * NG * 32);
+  uint8_t* sB = smem;                                    // KC chunks of [NM rows x 128 B], SW128 K-major
+  float* sZ = reinterpret_cast<float*>(sB + KC * B_CHUNK);   // [4 gates][NB][32 units]
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sZ + 4 * NB * 32);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
   __shared__ int s_dead;
 
@@ -80,6 +83,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     s_dead = 0;
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < KC * B_CHUNK / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -111,7 +115,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __syncthreads();
   tc::tcgen05_fence_after();
 
-  const uint32_t idesc = tc::umma_idesc_f16(128, NG, 0);
+  const uint32_t idesc = tc::umma_idesc_f16(128, NM, 0);
   const uint32_t sB_addr = tc::smem_u32(sB);
   const int u = u0 + lane;
   float bias[4];
@@ -145,14 +149,18 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
     }
     if (a.training && a.hT16) {   // the thread's NPT samples are contiguous in the transposed copy: one 8-byte store
-      static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0] * mu[0], hv[1] * mu[1]),
-                           p1 = __floats2bfloat162_rn(hv[2] * mu[2], hv[3] * mu[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&p0);
-      pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.hT16) + (size_t)(dir * H + u) * R +
-                                (size_t)t * N + n0 + warp * NPT) = pk;
+      static_assert(NPT == 4 || NPT == 2, "packed transposed store: 2 or 4 samples per thread");
+      __nv_bfloat16* dstT = reinterpret_cast<__nv_bfloat16*>(a.hT16) + (size_t)(dir * H + u) * R + (size_t)t * N + n0 + warp * NPT;
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0] * mu[0], hv[1] * mu[1]);
+      if constexpr (NPT == 4) {
+        const __nv_bfloat162 p1 = __floats2bfloat162_rn(hv[2] * mu[2], hv[3] * mu[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(dstT) = pk;
+      } else {
+        *reinterpret_cast<__nv_bfloat162*>(dstT) = p0;
+      }
     }
   };
   float p_hv[NPT], p_gi[NPT], p_gf[NPT], p_gg[NPT], p_go[NPT], p_cs[NPT];
@@ -217,7 +225,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 #pragma unroll
         for (int kb = 0; kb < H / 16; ++kb) {
           const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-          tc::umma_ts(tmem + D_COL + (kb % NACC) * NG, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
+          tc::umma_ts(tmem + D_COL + (kb % NACC) * NM, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
         }
         tc::umma_commit(mma_bar);
       }
@@ -229,16 +237,16 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       tc::tcgen05_fence_after();
       PROF(3);
       {
-        uint32_t r0[NG], r1[NG], r2[NG], r3[NG];
+        uint32_t r0[NB], r1[NB], r2[NB], r3[NB];
         const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
-        tc::tmem_ld16(tq, r0);
-        tc::tmem_ld16(tq + NG, r1);
-        tc::tmem_ld16(tq + 2 * NG, r2);
-        tc::tmem_ld16(tq + 3 * NG, r3);
+        tc::tmem_ldn(tq, r0);
+        tc::tmem_ldn(tq + NM, r1);
+        tc::tmem_ldn(tq + 2 * NM, r2);
+        tc::tmem_ldn(tq + 3 * NM, r3);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int n = 0; n < NG; ++n)
-          sZ[(warp * NG + n) * 32 + lane] = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) +
+        for (int n = 0; n < NB; ++n)
+          sZ[(warp * NB + n) * 32 + lane] = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) +
                                             (__uint_as_float(r2[n]) + __uint_as_float(r3[n]));
       }
       tc::tcgen05_fence_before();
@@ -248,7 +256,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 #pragma unroll
       for (int i = 0; i < NPT; ++i)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) z[i][g] = sZ[(g * NG + warp * NPT + i) * 32 + lane];
+        for (int g = 0; g < 4; ++g) z[i][g] = sZ[(g * NB + warp * NPT + i) * 32 + lane];
     } else {
 #pragma unroll
       for (int i = 0; i < NPT; ++i)
@@ -303,6 +311,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 //                 and sum the four partials that arrive for my own units -> dh_rec
 //          element-wise BPTT -> dz (published to hop 1 of the next step) + side outputs
 // ------------------------------------------------------------------------------------------------
+template <int NB>
 __global__ void __launch_bounds__(THREADS, 1)
 bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf1, uint2* __restrict__ xbuf2, int delay1,
            int delay2) {
@@ -310,16 +319,16 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int H = 512, K4 = 4 * H;
   constexpr int KC = 8;                                  // 512-wide K block = 8 chunks of 64
-  constexpr int B_CHUNK = NG * 128;
-  constexpr int WORDS1 = NG * 256;                       // hop-1 LL words per (dir, grp, column, parity)
-  constexpr int WPT1 = WORDS1 / THREADS;                 // 32
-  constexpr int WORDS2 = NG * 32;                        // hop-2 LL words per (dir, grp, r, recv, send, parity)
-  constexpr int NPT = NG / 4;
+  constexpr int B_CHUNK = NM * 128;
+  constexpr int WORDS1 = NB * 256;                       // hop-1 LL words per (dir, grp, column, parity)
+  constexpr int WPT1 = WORDS1 / THREADS;
+  constexpr int WORDS2 = NB * 32;                        // hop-2 LL words per (dir, grp, r, recv, send, parity)
+  constexpr int NPT = NB / 4;
   const int T = a.T, N = a.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
   const int r = cta >> 2, c = cta & 3;
-  const int u0 = cta * UPC, n0 = grp * NG;
+  const int u0 = cta * UPC, n0 = grp * NB;
 
   uint8_t* sB = smem;
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sB + KC * B_CHUNK);
@@ -332,6 +341,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     s_dead = 0;
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < KC * B_CHUNK / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -364,7 +374,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __syncthreads();
   tc::tcgen05_fence_after();
 
-  const uint32_t idesc = tc::umma_idesc_f16(128, NG, 1);
+  const uint32_t idesc = tc::umma_idesc_f16(128, NM, 1);
   const uint32_t sB_addr = tc::smem_u32(sB);
   const int u = u0 + lane;
   float dc_carry[NPT], mu[NPT], db[4] = {0, 0, 0, 0};
@@ -393,15 +403,20 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
     }
     if (a.dzT16) {
-      static_assert(NPT == 4, "packed transposed store assumes 4 samples per thread");
+      static_assert(NPT == 4 || NPT == 2, "packed transposed store: 2 or 4 samples per thread");
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]), p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&p0);
-        pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.dzT16) + (size_t)(dir * K4 + g * H + u) * R +
-                                  (size_t)t * N + n0 + warp * NPT) = pk;
+        __nv_bfloat16* dstT = reinterpret_cast<__nv_bfloat16*>(a.dzT16) + (size_t)(dir * K4 + g * H + u) * R + (size_t)t * N + n0 + warp * NPT;
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]);
+        if constexpr (NPT == 4) {
+          const __nv_bfloat162 p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(dstT) = pk;
+        } else {
+          *reinterpret_cast<__nv_bfloat162*>(dstT) = p0;
+        }
       }
     }
   };
@@ -475,7 +490,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 #pragma unroll
         for (int kb = 0; kb < 32; ++kb) {
           const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-          tc::umma_ts(tmem + D_COL + (kb % NACC) * NG, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
+          tc::umma_ts(tmem + D_COL + (kb % NACC) * NM, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
         }
         tc::umma_commit(mma_bar);
       }
@@ -487,16 +502,16 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       PROF(2);
       // ---- hop 2 (send): my warp's 32 rows are the units of CTA (r, warp) -----------------------------
       {
-        uint32_t r0[NG], r1[NG], r2[NG], r3[NG];
+        uint32_t r0[NB], r1[NB], r2[NB], r3[NB];
         const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
-        tc::tmem_ld16(tq, r0);
-        tc::tmem_ld16(tq + NG, r1);
-        tc::tmem_ld16(tq + 2 * NG, r2);
-        tc::tmem_ld16(tq + 3 * NG, r3);
+        tc::tmem_ldn(tq, r0);
+        tc::tmem_ldn(tq + NM, r1);
+        tc::tmem_ldn(tq + 2 * NM, r2);
+        tc::tmem_ldn(tq + 3 * NM, r3);
         tc::tmem_ld_wait();
         uint2* dst = x2row + ((size_t)(warp * 4 + c) * 2 + par) * WORDS2 + lane;
 #pragma unroll
-        for (int n = 0; n < NG; ++n) {
+        for (int n = 0; n < NB; ++n) {
           const float pv = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) + (__uint_as_float(r2[n]) + __uint_as_float(r3[n]));
           st_volatile_v2(dst + n * 32, make_uint2(__float_as_uint(pv), tag));
         }
@@ -590,46 +605,52 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 }
 
 // ---- host ---------------------------------------------------------------------------------------
+// samples per CTA group: 8 when that still fits one cooperative wave (more SMs, half the exchange per CTA), else 16
+static int group_size(int N, int H) {
+  const char* e = getenv("ASR_LSTM_GROUP");
+  if (e && atoi(e) == 16) return (N % 16 == 0) ? 16 : 0;
+  if (N % 8 == 0 && N / 8 <= 8 && (H / UPC) * 2 * (N / 8) <= 148) return 8;
+  if (N % 16 == 0 && N / 16 <= 8 && (H / UPC) * 2 * (N / 16) <= 148) return 16;
+  return 0;
+}
 static bool shape_ok(int T, int N, int H) {
-  return T >= 1 && (H == 128 || H == 256 || H == 384 || H == 512) && N >= NG && N % NG == 0 && N / NG <= 8 &&
-         (H / UPC) * 2 * (N / NG) <= 148;
+  return T >= 1 && (H == 128 || H == 256 || H == 384 || H == 512) && N >= 8 && group_size(N, H) != 0;
 }
 bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && a->h16 && shape_ok(a->T, a->N, a->H); }
-bool supports_bwd(const asr_lstm_bwd_args* a) {
-  return a->U16 && a->dz16 && a->H == 512 && a->T >= 1 && a->N >= NG && a->N % NG == 0 && a->N / NG <= 4;
-}
-constexpr size_t X1_BYTES_PER_DG = (size_t)4 * 2 * NG * 256 * sizeof(uint2);            // hop 1 per (dir, grp)
-constexpr size_t X2_BYTES_PER_DG = (size_t)4 * 4 * 4 * 2 * NG * 32 * sizeof(uint2);     // hop 2 per (dir, grp)
-size_t scratch_bytes(int) { return HEADER_BYTES + (size_t)2 * 8 * (X1_BYTES_PER_DG + X2_BYTES_PER_DG); }
+bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && a->H == 512 && shape_ok(a->T, a->N, a->H); }
+static size_t x1_bytes_per_dg(int NB) { return (size_t)4 * 2 * NB * 256 * sizeof(uint2); }           // hop 1 per (dir, grp)
+static size_t x2_bytes_per_dg(int NB) { return (size_t)4 * 4 * 4 * 2 * NB * 32 * sizeof(uint2); }    // hop 2 per (dir, grp)
+size_t scratch_bytes(int) { return HEADER_BYTES + (size_t)2 * 8 * (x1_bytes_per_dg(16) + x2_bytes_per_dg(16)); }
 
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
 
-template <int H>
+template <int H, int NB>
 static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   constexpr int KC = H / 64;
-  const size_t smem = 1024 + (size_t)KC * NG * 128 + 4 * NG * 32 * 4 + 64;
-  const int G = a->N / NG;
-  ASR_CUDA(cudaFuncSetAttribute(fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const size_t xbytes = (size_t)2 * G * 2 * NG * (H / 2) * sizeof(uint2);
+  const size_t smem = 1024 + (size_t)KC * NM * 128 + 4 * NB * 32 * 4 + 64;
+  const int G = a->N / NB;
+  ASR_CUDA(cudaFuncSetAttribute(fwd_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t xbytes = (size_t)2 * G * 2 * NB * (H / 2) * sizeof(uint2);
   ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + xbytes, st));
   asr_lstm_fwd_args args = *a;
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
   int delay1 = env_int("ASR_LSTM_FWD_DELAY_NS", 0);
   void* kargs[] = {&args, &flags, &xbuf, &delay1};
-  ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
+  ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H, NB>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
   asr::count_launch();
   return ASR_OK;
 }
 
-int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
-  const int G = a->N / NG;
-  const size_t smem = 1024 + (size_t)8 * NG * 128 + 64;
-  const size_t x1 = (size_t)2 * G * X1_BYTES_PER_DG, x2 = (size_t)2 * G * X2_BYTES_PER_DG;
-  ASR_CUDA(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int NB>
+static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
+  const int G = a->N / NB;
+  const size_t smem = 1024 + (size_t)8 * NM * 128 + 64;
+  const size_t x1 = (size_t)2 * G * x1_bytes_per_dg(NB), x2 = (size_t)2 * G * x2_bytes_per_dg(NB);
+  ASR_CUDA(cudaFuncSetAttribute(bwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + x1 + x2, st));
   ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));
   asr_lstm_bwd_args args = *a;
@@ -638,17 +659,22 @@ int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
   uint2* xbuf2 = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES + x1);
   int delay1 = env_int("ASR_LSTM_BWD_DELAY1_NS", 0), delay2 = env_int("ASR_LSTM_BWD_DELAY2_NS", 0);
   void* kargs[] = {&args, &flags, &xbuf1, &xbuf2, &delay1, &delay2};
-  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd_kernel, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
+  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd_kernel<NB>, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
   asr::count_launch();
   return ASR_OK;
 }
 
+int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
+  return group_size(a->N, a->H) == 8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
+}
+
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st) {
+  const bool g8 = group_size(a->N, a->H) == 8;
   switch (a->H) {
-    case 128: return launch_fwd<128>(a, st);
-    case 256: return launch_fwd<256>(a, st);
-    case 384: return launch_fwd<384>(a, st);
-    case 512: return launch_fwd<512>(a, st);
+    case 128: return g8 ? launch_fwd<128, 8>(a, st) : launch_fwd<128, 16>(a, st);
+    case 256: return g8 ? launch_fwd<256, 8>(a, st) : launch_fwd<256, 16>(a, st);
+    case 384: return g8 ? launch_fwd<384, 8>(a, st) : launch_fwd<384, 16>(a, st);
+    case 512: return g8 ? launch_fwd<512, 8>(a, st) : launch_fwd<512, 16>(a, st);
   }
   asr::set_error("lstmtc2: unsupported H=%d", a->H);
   return ASR_ERR_INVALID;

@@ -180,8 +180,13 @@ def _lse2(a, b):
         return b
     if b == NEG_INF:
         return a
-    m = max(a, b)
-    return m + np.log(np.exp(a - m) + np.exp(b - m))
+    # TF ctc_loss_util.h LogSumExp: max + log1pf(expf(-|a-b|)); the two float functions are emulated as
+    # "fp64 then round to fp32" (what a correctly rounded libm returns) so any platform reproduces it.
+    f32 = np.float32
+    a, b = f32(a), f32(b)
+    m, mn = (a, b) if a >= b else (b, a)
+    e = f32(np.exp(np.float64(f32(mn - m))))
+    return f32(m + f32(np.log1p(np.float64(e))))
 
 
 def beam_decode_single(logits, seq_len, blank, beam_width=100,

@@ -61,3 +61,14 @@ def test_beam_width_1_and_ler_on_model_like_posteriors():
     assert got == ref
     assert abs(oc.ler(truth, got) - oc.ler(truth, ref)) < 1e-12
     assert _beam(logits, [T] * N, 1) == oc.beam_decode(logits, [T] * N, beam_width=1)
+
+
+def test_beam_full_length_c5_shape():
+    """BASELINE configs[4] shape: 999 frames, 28 classes, width 100 — flat (random-init-like) posteriors, where near
+    ties are the rule and only a bit-identical log-sum-exp keeps the device on the oracle's beam for 999 frames."""
+    rng = np.random.RandomState(99)
+    T, C = 999, 28
+    logits = np.stack([rng.randn(T, C) * 0.7, rng.randn(T, C) * 3.0]).astype(np.float32)
+    got = _beam(logits, [T, T - 11], 100)
+    ref = oc.beam_decode(logits, [T, T - 11], beam_width=100)
+    assert got == ref
