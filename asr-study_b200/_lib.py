@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libasr_b200.so")
+# ASR_B200_LIB selects another build of the SAME library (e.g. the -DASR_LSTM_PROFILE build); never a fallback
+LIB_PATH = os.environ.get("ASR_B200_LIB") or os.path.join(_HERE, "libasr_b200.so")
 
 
 class AsrError(RuntimeError):

@@ -24,7 +24,16 @@ namespace lstmtc2 {
 #define PROF_DECL long long pt0 = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define PROF(i) do { const long long now = clock64(); pacc[i] += now - pt0; pt0 = now; } while (0)
 #define PROF_DUMP(base) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int i = 0; i < 8; ++i) reinterpret_cast<long long*>(flags + 1024)[(base) + i] = pacc[i]; } while (0)
+// finer split of the MMA issue phase (elected lane only): slots 16.. of the dump area
+#define PROF2_DECL long long qacc[6] = {0, 0, 0, 0, 0, 0}, qt0 = 0
+#define PROF2_START qt0 = clock64()
+#define PROF2(i) do { const long long now = clock64(); qacc[i] += now - qt0; qt0 = now; } while (0)
+#define PROF2_DUMP(base) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int i = 0; i < 6; ++i) reinterpret_cast<long long*>(flags + 1024)[(base) + i] = qacc[i]; } while (0)
 #else
+#define PROF2_DECL
+#define PROF2_START
+#define PROF2(i)
+#define PROF2_DUMP(base)
 #define PROF_DECL
 #define PROF(i)
 #define PROF_DUMP(base)
@@ -167,6 +176,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   int p_t = -1;
 
   PROF_DECL;
+  PROF2_DECL;
   for (int s = 0; s < T; ++s) {
     PROF(7);
     const int t = dir ? (T - 1 - s) : s;
@@ -221,13 +231,22 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       PROF(1);
       if (s_dead) break;
       if (warp == 0 && tc::elect_one_sync()) {
+        PROF2_START;
         tc::tcgen05_fence_after();
+        PROF2(0);
 #pragma unroll
         for (int kb = 0; kb < H / 16; ++kb) {
           const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
           tc::umma_ts(tmem + D_COL + (kb % NACC) * NM, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
+#ifdef ASR_LSTM_PROFILE
+          if (kb == 0) PROF2(1);
+          if (kb == 7) PROF2(2);
+          if (kb == 15) PROF2(3);
+          if (kb == H / 16 - 1) PROF2(4);
+#endif
         }
         tc::umma_commit(mma_bar);
+        PROF2(5);
       }
       PROF(2);
       if (!tc::mbar_wait(mma_bar, (uint32_t)((s - 1) & 1), WATCHDOG_CYCLES)) {
@@ -295,6 +314,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   }
   if (p_t >= 0 && !s_dead) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);   // last step
   PROF_DUMP(0);
+  PROF2_DUMP(16);
   tc::tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
@@ -626,11 +646,19 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
+// The recurrence CTAs own their SM: they hold all 512 TMEM columns, and any co-resident CTA would steal issue
+// slots from a latency-bound chain.  Requesting (almost) the whole shared memory keeps every other kernel's CTAs
+// (e.g. the gradient GEMMs of the previous layer running on a low-priority side stream) on the SMs this grid
+// does not use.  ASR_LSTM_EXCLUSIVE=0 turns it off.
+static size_t exclusive_smem(size_t need) {
+  const size_t want = 200 * 1024;
+  return (env_int("ASR_LSTM_EXCLUSIVE", 1) && need < want) ? want : need;
+}
 
 template <int H, int NB>
 static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   constexpr int KC = H / 64;
-  const size_t smem = 1024 + (size_t)KC * NM * 128 + 4 * NB * 32 * 4 + 64;
+  const size_t smem = exclusive_smem(1024 + (size_t)KC * NM * 128 + 4 * NB * 32 * 4 + 64);
   const int G = a->N / NB;
   ASR_CUDA(cudaFuncSetAttribute(fwd_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t xbytes = (size_t)2 * G * 2 * NB * (H / 2) * sizeof(uint2);
@@ -648,7 +676,7 @@ static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
 template <int NB>
 static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
   const int G = a->N / NB;
-  const size_t smem = 1024 + (size_t)8 * NM * 128 + 64;
+  const size_t smem = exclusive_smem(1024 + (size_t)8 * NM * 128 + 64);
   const size_t x1 = (size_t)2 * G * x1_bytes_per_dg(NB), x2 = (size_t)2 * G * x2_bytes_per_dg(NB);
   ASR_CUDA(cudaFuncSetAttribute(bwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + x1 + x2, st));

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -110,8 +111,12 @@ class AcousticEngine:
         self._sqnorm = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._flags = torch.zeros(lib.asr_lstm_flags_bytes() // 4, dtype=torch.int32, device=self.device)
         self._weights_version = -1
-        self._side = torch.cuda.Stream(device=self.device)      # gradient GEMMs that overlap the next recurrence
-        self.overlap = False     # measured: no gain — GEMM CTAs cannot co-reside with the recurrence CTAs (whole TMEM owned)
+        # dW/dU GEMMs of layer l run on a low-priority side stream while the BPTT recurrence of layer l-1 (128 of the
+        # 148 SMs, which it owns exclusively — see exclusive_smem() in csrc/lstm_tc2.cu) runs on the high-priority
+        # main stream; the GEMM CTAs fill the 20 idle SMs and never delay the critical path.
+        self._main = torch.cuda.Stream(device=self.device, priority=-1)
+        self._side = torch.cuda.Stream(device=self.device, priority=0)
+        self.overlap = os.environ.get("ASR_B200_OVERLAP", "1") != "0"
         self._mask_rng = torch.Generator(device=self.device)
         self._mask_rng.manual_seed(seed + 17)
 
@@ -430,13 +435,20 @@ class AcousticEngine:
                    allreduce=None, masks=None, **opt):
         """One optimisation step on time-major features; returns the per-utterance CTC loss tensor [N]."""
         N = feats_tm.shape[1]
-        logits = self.forward(feats_tm, training=True, masks=masks)
-        loss, dlogits = self.ctc(logits, in_len, labels_flat, label_off, max_label_len,
-                                 grad_scale=1.0 / float(global_batch or N))
-        self.backward(dlogits)
-        if allreduce is not None:
-            allreduce(self.params.grad)
-        self.optimizer_step(**opt)
+        caller = torch.cuda.current_stream()
+        main = self._main if self.overlap else caller
+        if main is not caller:
+            main.wait_stream(caller)
+        with torch.cuda.stream(main):
+            logits = self.forward(feats_tm, training=True, masks=masks)
+            loss, dlogits = self.ctc(logits, in_len, labels_flat, label_off, max_label_len,
+                                     grad_scale=1.0 / float(global_batch or N))
+            self.backward(dlogits)
+            if allreduce is not None:
+                allreduce(self.params.grad)
+            self.optimizer_step(**opt)
+        if main is not caller:
+            caller.wait_stream(main)
         return loss
 
 

@@ -23,6 +23,7 @@ for rep in range(2):
     p = flags[1024:1024 + 64].view(torch.int64).cpu().numpy()
     print("fwd ms", e0.elapsed_time(e1), "status", int(flags[64]))
     print("  fwd cycles/step:", {n: int(v / T) for n, v in zip(names, p[:8])}, "sum", int(p[:8].sum() / T))
+    print("  fwd issue split (fence_after, mma 0, mma 1-7, mma 8-15, mma 16-31, commit):", [int(v / T) for v in p[16:22]])
 dh = torch.randn(R, 2 * H, device=dev, generator=g) * 0.01
 dz16 = torch.empty(R, 8 * H, dtype=torch.bfloat16, device=dev); dzT16 = torch.empty(8 * H, R, dtype=torch.bfloat16, device=dev)
 dbias = torch.zeros(8 * H, device=dev)
