@@ -41,6 +41,20 @@ class LstmBwdArgs(C.Structure):
                 ("dz32", C.c_void_p), ("dbias", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p)]
 
 
+class LstmVariant(C.Structure):
+    _fields_ = [("mi_alpha", C.c_void_p), ("mi_beta1", C.c_void_p), ("mi_beta2", C.c_void_p),
+                ("ln_gain_uh", C.c_void_p), ("ln_bias_uh", C.c_void_p), ("ln_gain_wx", C.c_void_p),
+                ("ln_bias_wx", C.c_void_p), ("ln_gain_c", C.c_void_p), ("ln_bias_c", C.c_void_p),
+                ("ln_eps", C.c_float), ("zoneout_h", C.c_float), ("zoneout_c", C.c_float),
+                ("zmask_h", C.c_void_p), ("zmask_c", C.c_void_p)]
+
+
+class LstmVariantGrads(C.Structure):
+    _fields_ = [("mi_alpha", C.c_void_p), ("mi_beta1", C.c_void_p), ("mi_beta2", C.c_void_p),
+                ("ln_gain_uh", C.c_void_p), ("ln_bias_uh", C.c_void_p), ("ln_gain_wx", C.c_void_p),
+                ("ln_bias_wx", C.c_void_p), ("ln_gain_c", C.c_void_p), ("ln_bias_c", C.c_void_p)]
+
+
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/asr_b200.h declares
@@ -59,6 +73,9 @@ SIGNATURES = {
     "asr_lstm_flags_bytes": (_SZ, []),
     "asr_lstm_forward": (_I32, [C.POINTER(LstmFwdArgs), _P]),
     "asr_lstm_backward": (_I32, [C.POINTER(LstmBwdArgs), _P]),
+    "asr_lstm_cell_forward": (_I32, [C.POINTER(LstmFwdArgs), C.POINTER(LstmVariant), _P, _P]),
+    "asr_lstm_cell_backward": (_I32, [C.POINTER(LstmBwdArgs), C.POINTER(LstmVariant), _P, _P, _P,
+                                      C.POINTER(LstmVariantGrads), _P]),
     "asr_ctc_workspace_bytes": (_SZ, [_I32, _I32, _I32]),
     "asr_ctc_loss_grad": (_I32, [_P, _I32, _I32, _I32, _P, _P, _P, _I32, _I32, _F, _P, _P, _P, _P]),
     "asr_ctc_greedy": (_I32, [_P, _I32, _I32, _I32, _P, _I32, _I32, _P, _P, _P]),

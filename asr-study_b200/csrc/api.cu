@@ -17,6 +17,11 @@ size_t scratch_bytes(int H);
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
 int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st);
 }
+namespace lstmcell {
+int32_t forward(const asr_lstm_fwd_args* a, const asr_lstm_variant* v, float* uh_raw, cudaStream_t st);
+int32_t backward(const asr_lstm_bwd_args* a, const asr_lstm_variant* v, const float* zx, const float* uh_raw, float* duh,
+                 const asr_lstm_variant_grads* g, cudaStream_t st);
+}
 namespace lstmtc3 {
 bool supports_fwd(const asr_lstm_fwd_args* a);
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
@@ -97,4 +102,18 @@ extern "C" int32_t asr_lstm_backward(const asr_lstm_bwd_args* a, void* stream) {
   }
   ASR_CHECK_ARG(a->U, "asr_lstm_backward: fp32 engine needs U");
   return lstm32::backward(a, st);
+}
+
+extern "C" int32_t asr_lstm_cell_forward(const asr_lstm_fwd_args* a, const asr_lstm_variant* v, float* uh_raw, void* stream) {
+  ASR_CHECK_ARG(a && a->zx && a->bias && (a->h32 || a->h16), "asr_lstm_cell_forward: null argument");
+  if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
+  ASR_CHECK_ARG(!a->training || (a->gates && a->cell), "asr_lstm_cell_forward: training needs gates/cell buffers");
+  return lstmcell::forward(a, v, uh_raw, (cudaStream_t)stream);
+}
+
+extern "C" int32_t asr_lstm_cell_backward(const asr_lstm_bwd_args* a, const asr_lstm_variant* v, const float* zx,
+                                          const float* uh_raw, float* duh, const asr_lstm_variant_grads* g, void* stream) {
+  ASR_CHECK_ARG(a && a->dh && a->gates && a->cell && a->dbias, "asr_lstm_cell_backward: null argument");
+  if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
+  return lstmcell::backward(a, v, zx, uh_raw, duh, g, (cudaStream_t)stream);
 }

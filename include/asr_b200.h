@@ -154,6 +154,56 @@ int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream);
 int32_t asr_lstm_backward(const asr_lstm_bwd_args* a, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * K3/K4 (general cell)  LSTM.step with the brsmv1 switches
+ * replaces core/layers.py:432-469 with layer normalisation (:407-430,
+ * core/layers_utils.py:16-19), multiplicative integration (:441-443) and
+ * zoneout (:457-467, layers_utils.py:34-42).  fp32 throughout; takes the same
+ * argument records as the default engine (zx = K.dot(x*B_W, W) WITHOUT bias).
+ * Every vector is f32 [2, 4H] (fwd|bwd direction) unless noted; a NULL group
+ * switches the feature off.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  const float* mi_alpha;    /* z = alpha*Wx*Uh + beta1*Uh + beta2*Wx + b             */
+  const float* mi_beta1;
+  const float* mi_beta2;
+  const float* ln_gain_uh;  /* LN on K.dot(h*B_U, U)                                  */
+  const float* ln_bias_uh;
+  const float* ln_gain_wx;  /* LN on K.dot(x*B_W, W)                                  */
+  const float* ln_bias_wx;
+  const float* ln_gain_c;   /* f32 [2, H]  LN on the new cell (h = o * tanh(LN(c)))   */
+  const float* ln_bias_c;
+  float ln_eps;             /* 1e-5 in the reference                                  */
+  float zoneout_h;          /* level in [0,1); 0 = off                                */
+  float zoneout_c;
+  const float* zmask_h;     /* f32 [2, T, H] keep masks of the train phase (one per time step,
+                               shared by the batch), NULL = inference blend with (1 - level)   */
+  const float* zmask_c;
+} asr_lstm_variant;
+
+typedef struct {            /* parameter gradients, overwritten; same shapes as above */
+  float* mi_alpha;
+  float* mi_beta1;
+  float* mi_beta2;
+  float* ln_gain_uh;
+  float* ln_bias_uh;
+  float* ln_gain_wx;
+  float* ln_bias_wx;
+  float* ln_gain_c;
+  float* ln_bias_c;
+} asr_lstm_variant_grads;
+
+/* forward: needs a->U (fp32) and a->h32 or a->h16; training also fills gates/cell and
+ * uh_raw f32 [T, N, 2, 4H] (the pre-LN recurrent product the backward pass re-normalises). */
+int32_t asr_lstm_cell_forward(const asr_lstm_fwd_args* a, const asr_lstm_variant* v,
+                              float* uh_raw, void* stream);
+/* backward: a->dz32 receives dL/d(zx) (the W-side gradient: dW, dX), duh f32 [T, N, 2, 4H]
+ * receives dL/d(uh_raw) (the U-side gradient: dU); a->dbias and g->* are overwritten.
+ * a->dz16 / a->dzT16 are not written by this engine. */
+int32_t asr_lstm_cell_backward(const asr_lstm_bwd_args* a, const asr_lstm_variant* v,
+                               const float* zx, const float* uh_raw, float* duh,
+                               const asr_lstm_variant_grads* g, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * K6  CTC loss + gradient      replaces tf.nn.ctc_loss, core/ctc_utils.py:68-70
  * logits f32 [T, N, C] time-major; softmax applied inside; blank = C-1 in the
  * reference.  labels: flat i32 + offsets i32 [N+1].  loss f32 [N];
