@@ -88,6 +88,7 @@ SIGNATURES = {
     "asr_cast_transpose": (_I32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
     "asr_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P]),
     "asr_mask_cast": (_I32, [_P, _I32, _I64, _P, _I32, _P, _I32, _I64, _I64, _I32, _I32, _P]),
+    "asr_add_mask": (_I32, [_P, _P, _P, _I64, _P, _I64, _I32, _P]),
     "asr_mask_combine": (_I32, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),
 }
 

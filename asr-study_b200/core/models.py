@@ -236,8 +236,13 @@ def ctc_model(inputs, output, **kwargs):
     dps = {(l.dropout_W, l.dropout_U) for l in layers}
     if len(dps) != 1 or len(set(dps.pop())) != 1:
         raise NotImplementedError("dropout_W and dropout_U are tied and equal across layers (core/models.py:229-230)")
+    sw = {(l.zoneout_h, l.layer_norm, l.mi) for l in layers}
+    if len(sw) != 1:
+        raise NotImplementedError("zoneout / layer_norm / mi are tied across layers (core/models.py:260-271)")
+    zo, ln, mi = sw.pop()
     spec = ModelSpec(int(inputs), hs.pop(), len(layers), int(num_classes), float(wd), kwargs.pop("name", "ctc_model"),
-                     float(layers[0].dropout_W))
+                     float(layers[0].dropout_W), zoneout=zo, layer_norm=ln, mi=mi, residual=kwargs.pop("residual", None),
+                     input_dropout=bool(kwargs.pop("input_dropout", False)))
     return CTCModel(spec, **kwargs)
 
 
@@ -265,12 +270,13 @@ def deep_speech(*a, **k):
 def brsmv1(num_features=39, num_classes=28, num_hiddens=256, num_layers=5, dropout=0.2, zoneout=0.,
            input_dropout=False, input_std_noise=.0, weight_decay=1e-4, residual=None, layer_norm=None, mi=None,
            activation='tanh', **kw):
-    """core/models.py:217-281.  Built: the N x BiLSTM + Dense trunk with l2(weight_decay).  The regulariser
-    and variational dropout (dropout_W = dropout_U = dropout, masks constant over time).  The other switches
-    (zoneout, LN, MI, residual, input_dropout) are next rows: a non-off value raises."""
-    if residual is not None or input_dropout:
-        raise NotImplementedError("residual / input_dropout are not built yet")
+    """core/models.py:217-281: N x BiLSTM + Dense trunk with l2(weight_decay) and variational dropout
+    (dropout_W = dropout_U = dropout, masks constant over time) on the tensor-core engines.  zoneout, layer_norm,
+    mi, residual='sum' (with its TimeDistributed(Dense(2H)) input projection) and input_dropout switch the
+    recurrence to the general-cell engine (csrc/lstm_cell.cu)."""
+    if residual not in (None, "sum"):
+        raise NotImplementedError("merge mode %r: only 'sum' keeps the layer width the next Bidirectional expects" % residual)
     layers = [LSTM(num_hiddens, zoneout_c=zoneout, zoneout_h=zoneout, mi=mi, layer_norm=layer_norm,
                    activation=activation, dropout_W=dropout, dropout_U=dropout) for _ in range(num_layers)]
     return ctc_model(num_features, layers + [num_classes], name="brsmv1", weight_decay=weight_decay,
-                     input_std_noise=input_std_noise, **kw)
+                     input_std_noise=input_std_noise, residual=residual, input_dropout=input_dropout, **kw)

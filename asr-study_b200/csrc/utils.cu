@@ -7,7 +7,15 @@ template <typename T> __device__ __forceinline__ T cvt(float v);
 template <> __device__ __forceinline__ __half cvt<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-template <typename T>
+// LO = true writes the rounding residual cvt(v - float(cvt(v))): with it a 16-bit operand pair (hi, lo) carries
+// ~22 mantissa bits, and hi*hi + hi*lo + lo*hi on the tensor cores reproduces the fp32 product to ~1e-6
+// (used where layer normalisation amplifies operand rounding, see engine._forward_general)
+template <typename T, bool LO> __device__ __forceinline__ T cvt2(float v) {
+  if (LO) return cvt<T>(v - (float)cvt<T>(v));
+  return cvt<T>(v);
+}
+
+template <typename T, bool LO = false>
 __global__ void __launch_bounds__(256)
 cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, T* __restrict__ dst, int64_t ld_dst, int64_t rows,
                  int cols) {
@@ -18,12 +26,12 @@ cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, T* __restrict__ 
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cp;
     const int c = (int)(i - r * cp);
-    dst[r * ld_dst + c] = cvt<T>(c < cols ? src[r * ld_src + c] : 0.0f);
+    dst[r * ld_dst + c] = cvt2<T, LO>(c < cols ? src[r * ld_src + c] : 0.0f);
   }
 }
 
 // 32x32 tiles through shared memory: coalesced on both sides
-template <typename T>
+template <typename T, bool LO = false>
 __global__ void __launch_bounds__(256)
 cast_transpose_kernel(const float* __restrict__ src, int64_t ld_src, T* __restrict__ dst, int64_t ld_dst, int64_t rows,
                       int cols) {
@@ -40,7 +48,7 @@ cast_transpose_kernel(const float* __restrict__ src, int64_t ld_src, T* __restri
   for (int k = ty; k < 32; k += 8) {
     const int c = c0 + k;
     const int64_t r = r0 + tx;
-    if (c < cols && r < rows) dst[(int64_t)c * ld_dst + r] = cvt<T>(tile[tx][k]);
+    if (c < cols && r < rows) dst[(int64_t)c * ld_dst + r] = cvt2<T, LO>(tile[tx][k]);
   }
 }
 
@@ -150,7 +158,9 @@ extern "C" int32_t asr_cast_rows(const float* src, int64_t ld_src, void* dst16, 
                                  int32_t cols, int32_t dtype, void* stream) {
   ASR_CHECK_ARG(src && dst16 && rows > 0 && cols > 0 && ld_dst >= cols && ld_src >= cols, "asr_cast_rows: bad argument");
   const int grid = grid_1d(rows * ((cols + 7) / 8 * 8));
-  if (dtype == 0)
+  if (dtype == 16)          // fp16 rounding residual (the "lo" half of a split-precision operand)
+    cast_rows_kernel<__half, true><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst16, ld_dst, rows, cols);
+  else if (dtype == 0)
     cast_rows_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst16, ld_dst, rows, cols);
   else
     cast_rows_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst16, ld_dst,
@@ -165,7 +175,9 @@ extern "C" int32_t asr_cast_transpose(const float* src, int64_t ld_src, void* ds
                 "asr_cast_transpose: bad argument");
   dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
   ASR_CHECK_ARG(grid.y <= 65535, "asr_cast_transpose: too many columns");
-  if (dtype == 0)
+  if (dtype == 16)
+    cast_transpose_kernel<__half, true><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst16, ld_dst, rows, cols);
+  else if (dtype == 0)
     cast_transpose_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst16, ld_dst, rows, cols);
   else
     cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst16,
@@ -222,6 +234,31 @@ extern "C" int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_
   if (gy > 296) gy = 296;
   dim3 grid((cols + 31) / 32, gy);
   colsum_kernel<<<grid, 256, 0, st>>>(src, ld, rows, cols, out);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+// out[r, c] = (a[r, c] + (b ? b[r, c] : 0)) * (mask ? mask[r % n_batch, c] : 1): the residual merge(mode='sum')
+// of core/models.py:273-274, the element-wise input Dropout of :257-258 (n_batch = rows: one mask entry per
+// element) and its backward.  out may alias a.
+__global__ void add_mask_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mask,
+                                int n_batch, float* __restrict__ out, int64_t rows, int cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    float v = a[i];
+    if (b) v += b[i];
+    if (mask) v *= mask[(r % n_batch) * cols + c];
+    out[i] = v;
+  }
+}
+
+extern "C" int32_t asr_add_mask(const float* a, const float* b, const float* mask, int64_t n_batch, float* out,
+                                int64_t rows, int32_t cols, void* stream) {
+  ASR_CHECK_ARG(a && out && rows > 0 && cols > 0 && (!mask || n_batch > 0), "asr_add_mask: bad argument");
+  ASR_CHECK_ARG(n_batch <= 2147483647LL, "asr_add_mask: n_batch too large");
+  add_mask_kernel<<<grid_1d(rows * cols), 256, 0, (cudaStream_t)stream>>>(a, b, mask, (int)(mask ? n_batch : 1), out, rows, cols);
   ASR_LAUNCH_CHECK();
   return ASR_OK;
 }

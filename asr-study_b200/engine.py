@@ -18,9 +18,10 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from ._lib import LstmBwdArgs, LstmFwdArgs, cur_stream, lib, ptr
+from ._lib import LstmBwdArgs, LstmFwdArgs, LstmVariant, LstmVariantGrads, cur_stream, lib, ptr
 
 F16, BF16 = 0, 1
+F16_LO = 16          # fp16(v - fp16(v)): the low half of a split-precision operand (csrc/utils.cu)
 OUT_F32, OUT_F16, OUT_BF16 = 0, 1, 2
 
 
@@ -37,6 +38,17 @@ class ModelSpec:
     weight_decay: float = 0.0        # l2 on W, U of every LSTM and the Dense kernel (models.py:263-264,279)
     name: str = "brsmv1"
     dropout: float = 0.0             # variational dropout_W = dropout_U (core/models.py:265-266), train phase only
+    # brsmv1 switches (core/models.py:217-281); any of them routes the recurrence to the general-cell engine
+    zoneout: float = 0.0             # zoneout_c = zoneout_h (core/models.py:267-268)
+    layer_norm: tuple | None = None  # (gain_init, bias_init)            (core/layers.py:407-422)
+    mi: tuple | None = None          # (alpha_init, beta1_init, beta2_init) (core/layers.py:391-405)
+    residual: str | None = None      # merge mode; 'sum' is built (core/models.py:253-255, 273-274)
+    input_dropout: bool = False      # element-wise Dropout(dropout) on the (projected) input (core/models.py:257-258)
+
+    @property
+    def general(self) -> bool:
+        return bool(self.zoneout or self.layer_norm is not None or self.mi is not None or self.residual is not None
+                    or self.input_dropout)
 
 
 class ParamBucket:
@@ -51,10 +63,18 @@ class ParamBucket:
         H, C = spec.num_hiddens, spec.num_classes
         shapes = []
         D = spec.num_features
+        if spec.residual is not None:
+            shapes += [("proj.W", (D, 2 * H)), ("proj.b", (2 * H,))]
+            D = 2 * H
         for l in range(spec.num_layers):
             shapes += [(f"l{l}.Wf", (D, 4 * H)), (f"l{l}.Wb", (D, 4 * H)),
                        (f"l{l}.Uf", (H, 4 * H)), (f"l{l}.Ub", (H, 4 * H)),
                        (f"l{l}.bf", (4 * H,)), (f"l{l}.bb", (4 * H,))]
+            if spec.mi is not None:          # [2, 4H]: forward | backward direction
+                shapes += [(f"l{l}.{n}", (2, 4 * H)) for n in ("mi_alpha", "mi_beta1", "mi_beta2")]
+            if spec.layer_norm is not None:
+                for n, wdt in (("uh", 4 * H), ("wx", 4 * H), ("c", H)):
+                    shapes += [(f"l{l}.ln_gain_{n}", (2, wdt)), (f"l{l}.ln_bias_{n}", (2, wdt))]
             D = 2 * H
         shapes += [("dense.W", (D, C)), ("dense.b", (C,))]
         self.shapes = dict(shapes)
@@ -70,7 +90,7 @@ class ParamBucket:
         self.v = torch.zeros_like(self.flat)
         self.decay = torch.zeros(off, dtype=torch.uint8, device=device)
         for k in self.shapes:
-            if k.endswith((".Wf", ".Wb", ".Uf", ".Ub")) or k == "dense.W":
+            if k.endswith((".Wf", ".Wb", ".Uf", ".Ub")) or k in ("dense.W", "proj.W"):
                 self._view(self.decay, k).fill_(1)
 
     def _view(self, flat, k):
@@ -125,7 +145,7 @@ class AcousticEngine:
         """Keras-1 LSTM.get_constants: one B_W [N, D] and one B_U [N, H] mask per direction and layer, sampled
         once per batch, constant over time, scaled by 1/(1-p) (K.dropout).  Returns {layer: {Wf,Wb,Uf,Ub}}."""
         sp, p = self.spec, float(self.spec.dropout)
-        out, D = {}, sp.num_features
+        out, D = {}, (sp.num_features if sp.residual is None else 2 * sp.num_hiddens)
         for l in range(sp.num_layers):
             out[l] = {}
             for k, w in (("Wf", D), ("Wb", D), ("Uf", sp.num_hiddens), ("Ub", sp.num_hiddens)):
@@ -153,6 +173,10 @@ class AcousticEngine:
             return (1.1 * q.reshape(shape)).astype(np.float32)
 
         D = spec.num_features
+        if spec.residual is not None:
+            out["proj.W"] = glorot((D, 2 * H))
+            out["proj.b"] = np.zeros(2 * H, np.float32)
+            D = 2 * H
         for l in range(spec.num_layers):
             for d in ("f", "b"):
                 out[f"l{l}.W{d}"] = glorot((D, 4 * H))
@@ -160,6 +184,14 @@ class AcousticEngine:
                 b = np.zeros(4 * H, np.float32)
                 b[H:2 * H] = 1.0
                 out[f"l{l}.b{d}"] = b
+            if spec.mi is not None:          # k_init(k) = k * ones (core/initializers.py:6-10)
+                for n, k in zip(("mi_alpha", "mi_beta1", "mi_beta2"), spec.mi):
+                    out[f"l{l}.{n}"] = np.full((2, 4 * H), float(k), np.float32)
+            if spec.layer_norm is not None:
+                g0, b0 = spec.layer_norm
+                for n, wdt in (("uh", 4 * H), ("wx", 4 * H), ("c", H)):
+                    out[f"l{l}.ln_gain_{n}"] = np.full((2, wdt), float(g0), np.float32)
+                    out[f"l{l}.ln_bias_{n}"] = np.full((2, wdt), float(b0), np.float32)
             D = 2 * H
         out["dense.W"] = glorot((D, spec.num_classes))
         out["dense.b"] = np.zeros(spec.num_classes, np.float32)
@@ -210,19 +242,23 @@ class AcousticEngine:
         sp, P = self.spec, self.params
         H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
         st = cur_stream()
-        D = sp.num_features
+        D = sp.num_features if sp.residual is None else 2 * H      # with the residual projection every layer sees 2H
         for l in range(L):
             Dp = _pad8(D)
             wt = self._buf(f"WcatT16.{l}", (8 * H, Dp), torch.float16, zero=True)     # [8H, D]  fwd B operand
             for i, d in enumerate("fb"):
                 lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wt[i * 4 * H:]), Dp, D, 4 * H, F16, st)
+            if sp.layer_norm is not None:     # split-precision projection (fp16 rounding residuals), see _forward_general
+                wl = self._buf(f"WcatT16lo.{l}", (8 * H, Dp), torch.float16, zero=True)
+                for i, d in enumerate("fb"):
+                    lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wl[i * 4 * H:]), Dp, D, 4 * H, F16_LO, st)
             ut = self._buf(f"UT16.{l}", (2, 4 * H, H), torch.float16)                 # [2, 4H, H] U^T, fwd recurrence
             for i, d in enumerate("fb"):
                 lib.asr_cast_transpose(ptr(P.p(f"l{l}.U{d}")), 4 * H, ptr(ut[i]), H, H, 4 * H, F16, st)
             if training:
                 ub = self._buf(f"Ub16.{l}", (2, H, 4 * H), torch.bfloat16)             # [2, H, 4H] U, BPTT recurrence
                 lib.asr_cast_rows(ptr(P.p(f"l{l}.Uf")), 4 * H, ptr(ub), 4 * H, 2 * H, 4 * H, BF16, st)
-            if training and l > 0:
+            if training and (l > 0 or sp.residual is not None):
                 wc = self._buf(f"Wcat16.{l}", (D, 8 * H), torch.bfloat16)              # [D, 8H]  dX B operand
                 for i, d in enumerate("fb"):
                     lib.asr_cast_rows(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wc[:, i * 4 * H:]), 8 * H, D, 4 * H, BF16, st)
@@ -239,13 +275,15 @@ class AcousticEngine:
                         cur_stream())
 
     # ---------------------------------------------------------------- forward
-    def forward(self, feats_tm: torch.Tensor, training=False, masks=None) -> torch.Tensor:
+    def forward(self, feats_tm: torch.Tensor, training=False, masks=None, zmasks=None, input_mask=None) -> torch.Tensor:
         """feats_tm: f32 [T, N, F] time-major on device -> logits f32 [T, N, C].
         masks: {layer: {Wf,Wb [N,D], Uf,Ub [N,H]}} variational-dropout masks (training only); sampled when
         spec.dropout > 0 and none are given."""
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
         assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
+        if sp.general:
+            return self._forward_general(feats_tm, training, masks, zmasks, input_mask)
         H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
         R = T * N
         w = self._alloc(T, N, training)
@@ -295,6 +333,253 @@ class AcousticEngine:
                    bias=P.p("dense.b"))
         return w["logits"]
 
+    # ------------------------------------------------- general path (brsmv1 switches on)
+    def sample_zoneout_masks(self, T):
+        """One keep mask per (layer, direction, time step, unit), shared by the batch: K.dropout(h_diff, level,
+        noise_shape=(output_dim,)) inside the step (core/layers_utils.py:34-42).  {layer: {h, c: f32 [2, T, H]}}."""
+        sp = self.spec
+        return {l: {k: (torch.rand(2, T, sp.num_hiddens, device=self.device, generator=self._mask_rng) >= sp.zoneout).float()
+                    for k in ("h", "c")} for l in range(sp.num_layers)}
+
+    def _variant(self, l, zm):
+        sp, P = self.spec, self.params
+
+        def pp(name):
+            return P.p(f"l{l}.{name}").data_ptr()
+
+        kw = dict(ln_eps=1e-5, zoneout_h=float(sp.zoneout), zoneout_c=float(sp.zoneout))
+        if sp.mi is not None:
+            kw.update(mi_alpha=pp("mi_alpha"), mi_beta1=pp("mi_beta1"), mi_beta2=pp("mi_beta2"))
+        if sp.layer_norm is not None:
+            for n in ("uh", "wx", "c"):
+                kw[f"ln_gain_{n}"], kw[f"ln_bias_{n}"] = pp(f"ln_gain_{n}"), pp(f"ln_bias_{n}")
+        if zm is not None:
+            kw.update(zmask_h=zm["h"].data_ptr(), zmask_c=zm["c"].data_ptr())
+        return LstmVariant(**kw)
+
+    def _operands(self, name, src32, Dl, mk, training, split=False):
+        """16-bit GEMM operands of one layer input (fp32 [R, Dl]): fp16 [R, pad8(Dl)] for the projection and (training)
+        its bf16 transpose [Dl, R] for dW; one pair per direction when the variational masks B_W differ.
+        split=True adds the fp16 rounding residual as a third operand (split-precision projection)."""
+        R, Dp, st = src32.shape[0], _pad8(Dl), cur_stream()
+        out = []
+        for i in range(2 if mk is not None else 1):
+            a16 = self._buf(f"{name}.in16.{i}", (R, Dp), torch.float16, zero=True)
+            aT = self._buf(f"{name}.inT16.{i}", (Dl, R), torch.bfloat16) if training else None
+            if split:
+                m32 = src32
+                if mk is not None:
+                    mw = mk["W" + "fb"[i]].contiguous()
+                    m32 = self._buf(f"{name}.in32m.{i}", (R, Dl), torch.float32)
+                    lib.asr_add_mask(ptr(src32), None, ptr(mw), mw.shape[0], ptr(m32), R, Dl, st)
+                lo = self._buf(f"{name}.in16lo.{i}", (R, Dp), torch.float16, zero=True)
+                lib.asr_cast_rows(ptr(m32), Dl, ptr(a16), Dp, R, Dl, F16, st)
+                lib.asr_cast_rows(ptr(m32), Dl, ptr(lo), Dp, R, Dl, F16_LO, st)
+                if training:
+                    lib.asr_cast_transpose(ptr(m32), Dl, ptr(aT), R, R, Dl, BF16, st)
+                out.append((a16, aT, lo))
+                continue
+            if mk is None:
+                lib.asr_cast_rows(ptr(src32), Dl, ptr(a16), Dp, R, Dl, F16, st)
+                if training:
+                    lib.asr_cast_transpose(ptr(src32), Dl, ptr(aT), R, R, Dl, BF16, st)
+            else:
+                mw = mk["W" + "fb"[i]].contiguous()
+                lib.asr_mask_cast(ptr(src32), 2, Dl, ptr(mw), mw.shape[0], ptr(a16), F16, Dp, R, Dl, 0, st)
+                if training:
+                    lib.asr_mask_cast(ptr(src32), 2, Dl, ptr(mw), mw.shape[0], ptr(aT), BF16, R, R, Dl, 1, st)
+            out.append((a16, aT))
+        return out
+
+    def _forward_general(self, feats_tm, training, masks, zmasks, input_mask):
+        sp, P = self.spec, self.params
+        T, N, Fd = feats_tm.shape
+        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        R, st = T * N, cur_stream()
+        if sp.residual not in (None, "sum"):
+            raise NotImplementedError("residual merge mode %r: only 'sum' keeps the layer width (core/models.py:273-274)" % sp.residual)
+        self._T, self._N = T, N
+        if training and masks is None and sp.dropout > 0:
+            masks = self.sample_masks(N)
+        if training and zmasks is None and sp.zoneout > 0:
+            zmasks = self.sample_zoneout_masks(T)
+        if training and input_mask is None and sp.input_dropout and sp.dropout > 0:
+            Din = 2 * H if sp.residual is not None else Fd
+            input_mask = (torch.rand(R, Din, device=self.device, generator=self._mask_rng) >= sp.dropout).float() / (1.0 - sp.dropout)
+        if not training:
+            masks = zmasks = input_mask = None
+        self._masks, self._zmasks, self._input_mask = masks, zmasks, input_mask
+        self._prep_weights(training)
+        w = self._w = {}
+        x32 = feats_tm.contiguous().view(R, Fd)
+        cur32, Dl = x32, Fd
+        self._gen = dict(ops=[], x_ops=None)
+        if sp.residual is not None:
+            split = sp.layer_norm is not None      # everything that feeds a layer-normalised product runs split-precision
+            self._gen["x_ops"] = self._operands("x", x32, Fd, None, training, split)[0]
+            Fp = _pad8(Fd)
+            wp = self._buf("WpT16", (2 * H, Fp), torch.float16, zero=True)
+            lib.asr_cast_transpose(ptr(P.p("proj.W")), 2 * H, ptr(wp), Fp, Fd, 2 * H, F16, st)
+            cur32 = self._buf("res32.in", (R, 2 * H), torch.float32)
+            self._gemm(F16, OUT_F32, R, 2 * H, Fp, self._gen["x_ops"][0], Fp, wp, Fp, cur32, 2 * H, bias=P.p("proj.b"))
+            if split:
+                wpl = self._buf("WpT16lo", (2 * H, Fp), torch.float16, zero=True)
+                lib.asr_cast_transpose(ptr(P.p("proj.W")), 2 * H, ptr(wpl), Fp, Fd, 2 * H, F16_LO, st)
+                self._gemm(F16, OUT_F32, R, 2 * H, Fp, self._gen["x_ops"][0], Fp, wpl, Fp, cur32, 2 * H, acc=1)
+                self._gemm(F16, OUT_F32, R, 2 * H, Fp, self._gen["x_ops"][2], Fp, wp, Fp, cur32, 2 * H, acc=1)
+            Dl = 2 * H
+        if input_mask is not None:
+            dst = cur32 if sp.residual is not None else self._buf("x32.masked", (R, Dl), torch.float32)
+            lib.asr_add_mask(ptr(cur32), None, ptr(input_mask.contiguous()), R, ptr(dst), R, Dl, st)
+            cur32 = dst
+        w["zx"] = self._buf("zx", (R, 8 * H), torch.float32)
+        for l in range(L):
+            mk = masks[l] if masks is not None else None
+            # layer normalisation divides Wx by its row deviation, which amplifies the fp16 operand rounding of the
+            # projection ~16x (measured 4.6e-3 on the logits, CPU emulation 4.56e-3): with LN on, the projection runs
+            # split-precision (hi*hi + hi*lo + lo*hi, three tensor-core GEMMs accumulating in fp32)
+            split = sp.layer_norm is not None
+            ops = self._operands(f"l{l}", cur32, Dl, mk, training, split)
+            self._gen["ops"].append(ops)
+            Dp = _pad8(Dl)
+            wt = self._views[f"WcatT16.{l}"]
+            wl = self._views[f"WcatT16lo.{l}"] if split else None
+            for i in range(2 if mk is not None else 1):
+                ncol = 4 * H if mk is not None else 8 * H
+                cdst = w["zx"][:, i * 4 * H:] if mk is not None else w["zx"]
+                lib.asr_gemm_tn(F16, OUT_F32, R, ncol, Dp, ptr(ops[i][0]), Dp, ptr(wt[i * 4 * H:]), Dp, ptr(cdst), 8 * H,
+                                None, 1.0, 0, st)
+                if split:
+                    lib.asr_gemm_tn(F16, OUT_F32, R, ncol, Dp, ptr(ops[i][0]), Dp, ptr(wl[i * 4 * H:]), Dp, ptr(cdst), 8 * H,
+                                    None, 1.0, 1, st)
+                    lib.asr_gemm_tn(F16, OUT_F32, R, ncol, Dp, ptr(ops[i][2]), Dp, ptr(wt[i * 4 * H:]), Dp, ptr(cdst), 8 * H,
+                                    None, 1.0, 1, st)
+            mask_u = None
+            if mk is not None:
+                mask_u = self._buf(f"maskU.{l}", (2, N, H), torch.float32)
+                mask_u[0].copy_(mk["Uf"]); mask_u[1].copy_(mk["Ub"])
+            h32 = self._buf(f"h32.{l}", (R, 2 * H), torch.float32)
+            w[f"h32.{l}"] = h32
+            if training:
+                # zx is overwritten by the next layer, the backward pass needs every layer's: keep per-layer copies
+                w[f"zx.{l}"] = self._buf(f"zx.{l}", (R, 8 * H), torch.float32)
+                w[f"zx.{l}"].copy_(w["zx"])
+                w[f"hT16.{l}"] = self._buf(f"hT16.{l}", (2 * H, R), torch.bfloat16)
+                w[f"gates.{l}"] = self._buf(f"gates.{l}", (R, 8 * H), torch.float32)
+                w[f"cell.{l}"] = self._buf(f"cell.{l}", (R, 2 * H), torch.float32)
+                w[f"uh.{l}"] = self._buf(f"uh.{l}", (R, 8 * H), torch.float32)
+            a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(w["zx"]).value,
+                            bias=ptr(P.p(f"l{l}.bf")).value, U=ptr(P.p(f"l{l}.Uf")).value, U16=None, h16=None,
+                            hT16=ptr(w[f"hT16.{l}"]).value if training else None, h32=ptr(h32).value,
+                            gates=ptr(w[f"gates.{l}"]).value if training else None,
+                            cell=ptr(w[f"cell.{l}"]).value if training else None,
+                            flags=ptr(self._flags).value, mask_u=ptr(mask_u).value if mask_u is not None else None)
+            v = self._variant(l, zmasks[l] if zmasks is not None else None)
+            lib.asr_lstm_cell_forward(C.byref(a), C.byref(v), ptr(w[f"uh.{l}"]) if training else None, st)
+            if sp.residual is not None:
+                nxt = self._buf(f"res32.{l}", (R, 2 * H), torch.float32)
+                lib.asr_add_mask(ptr(h32), ptr(cur32), None, 1, ptr(nxt), R, 2 * H, st)
+                cur32 = nxt
+            else:
+                cur32 = h32
+            Dl = 2 * H
+        top = self._operands("top", cur32, 2 * H, None, training)[0]
+        self._gen["top"] = top
+        w["logits"] = self._buf("logits", (T, N, Cc), torch.float32)
+        self._gemm(F16, OUT_F32, R, Cc, 2 * H, top[0], 2 * H, self._ws["WdT16"], 2 * H, w["logits"], Cc, bias=P.p("dense.b"))
+        if training:
+            w["dlogits"] = self._buf("dlogits", (T, N, Cc), torch.float32)
+            w["loss"] = self._buf("loss", (N,), torch.float32)
+        return w["logits"]
+
+    def _backward_general(self, dlogits):
+        sp, P, w = self.spec, self.params, self._w
+        T, N = self._T, self._N
+        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        R, st, cp = T * N, cur_stream(), _pad8(Cc)
+        masks, zmasks = self._masks, self._zmasks
+        dl16 = self._buf("dl16", (R, cp), torch.bfloat16, zero=True)
+        dlT16 = self._buf("dlT16", (Cc, R), torch.bfloat16)
+        lib.asr_cast_rows(ptr(dlogits), Cc, ptr(dl16), cp, R, Cc, BF16, st)
+        lib.asr_cast_transpose(ptr(dlogits), Cc, ptr(dlT16), R, R, Cc, BF16, st)
+        lib.asr_colsum(ptr(dlogits), Cc, R, Cc, ptr(P.g("dense.b")), st)
+        self._gemm(BF16, OUT_F32, 2 * H, Cc, R, self._gen["top"][1], R, dlT16, R, P.g("dense.W"), Cc)
+        dcur, dname = self._buf("dhA", (R, 2 * H), torch.float32), "dhA"
+        self._gemm(BF16, OUT_F32, R, 2 * H, cp, dl16, cp, self._ws["Wd16"], cp, dcur, 2 * H)
+        dwx = self._buf("dwx32", (R, 8 * H), torch.float32)
+        duh = self._buf("duh32", (R, 8 * H), torch.float32)
+        dwx16 = self._buf("dwx16", (R, 8 * H), torch.bfloat16)
+        dwxT16 = self._buf("dwxT16", (8 * H, R), torch.bfloat16)
+        duhT16 = self._buf("duhT16", (8 * H, R), torch.bfloat16)
+        for l in range(L - 1, -1, -1):
+            mk = masks[l] if masks is not None else None
+            mask_u = self._views[f"maskU.{l}"] if mk is not None else None
+            b = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dcur).value, gates=ptr(w[f"gates.{l}"]).value,
+                            cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value, U16=None, dz16=None, dzT16=None,
+                            dz32=ptr(dwx).value, dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value,
+                            mask_u=ptr(mask_u).value if mask_u is not None else None)
+            v = self._variant(l, zmasks[l] if zmasks is not None else None)
+            gk = {}
+            if sp.mi is not None:
+                gk.update({n: P.g(f"l{l}.{n}").data_ptr() for n in ("mi_alpha", "mi_beta1", "mi_beta2")})
+            if sp.layer_norm is not None:
+                for n in ("uh", "wx", "c"):
+                    gk[f"ln_gain_{n}"], gk[f"ln_bias_{n}"] = P.g(f"l{l}.ln_gain_{n}").data_ptr(), P.g(f"l{l}.ln_bias_{n}").data_ptr()
+            g = LstmVariantGrads(**gk)
+            lib.asr_lstm_cell_backward(C.byref(b), C.byref(v), ptr(w[f"zx.{l}"]), ptr(w[f"uh.{l}"]), ptr(duh), C.byref(g), st)
+            lib.asr_cast_rows(ptr(dwx), 8 * H, ptr(dwx16), 8 * H, R, 8 * H, BF16, st)
+            lib.asr_cast_transpose(ptr(dwx), 8 * H, ptr(dwxT16), R, R, 8 * H, BF16, st)
+            lib.asr_cast_transpose(ptr(duh), 8 * H, ptr(duhT16), R, R, 8 * H, BF16, st)
+            ops = self._gen["ops"][l]
+            Dl = ops[0][1].shape[0]
+            hT = w[f"hT16.{l}"]
+            for i, d in enumerate("fb"):
+                xT = ops[i if mk is not None else 0][1]
+                lib.asr_gemm_tn(BF16, OUT_F32, Dl, 4 * H, R, ptr(xT), R, ptr(dwxT16[i * 4 * H:]), R,
+                                ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, st)
+                if T > 1:
+                    Kk = (T - 1) * N
+                    hA, dzB = hT[i * H:(i + 1) * H], duhT16[i * 4 * H:(i + 1) * 4 * H]
+                    Ap, Bp = (hA, dzB[:, N:]) if i == 0 else (hA[:, N:], dzB)
+                    lib.asr_gemm_tn(BF16, OUT_F32, H, 4 * H, Kk, C.c_void_p(Ap.data_ptr()), R, C.c_void_p(Bp.data_ptr()), R,
+                                    ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, st)
+                else:
+                    P.g(f"l{l}.U{d}").zero_()
+            need_dx = l > 0 or sp.residual is not None
+            if need_dx:
+                wc = self._views[f"Wcat16.{l}"]
+                res = sp.residual is not None
+                if mk is None:
+                    # dX = dWx . Wcat^T ; with the residual merge the identity branch adds d(o_{l+1}) (GEMM accumulate)
+                    if res:
+                        lib.asr_gemm_tn(BF16, OUT_F32, R, Dl, 8 * H, ptr(dwx16), 8 * H, ptr(wc), 8 * H, ptr(dcur), Dl, None, 1.0, 1, st)
+                    else:
+                        dname = "dhB" if dname == "dhA" else "dhA"
+                        nxt = self._buf(dname, (R, Dl), torch.float32)
+                        lib.asr_gemm_tn(BF16, OUT_F32, R, Dl, 8 * H, ptr(dwx16), 8 * H, ptr(wc), 8 * H, ptr(nxt), Dl, None, 1.0, 0, st)
+                        dcur = nxt
+                else:
+                    part = [self._buf(f"dxpart.{i}", (R, Dl), torch.float32) for i in range(2)]
+                    for i in range(2):
+                        lib.asr_gemm_tn(BF16, OUT_F32, R, Dl, 4 * H, ptr(dwx16[:, i * 4 * H:]), 8 * H, ptr(wc[:, i * 4 * H:]), 8 * H,
+                                        ptr(part[i]), Dl, None, 1.0, 0, st)
+                    comb = self._buf("dxcomb", (R, Dl), torch.float32)
+                    lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
+                                         ptr(comb), R, Dl, st)
+                    if res:
+                        lib.asr_add_mask(ptr(dcur), ptr(comb), None, 1, ptr(dcur), R, Dl, st)
+                    else:
+                        dcur = comb
+        if sp.residual is not None:
+            if self._input_mask is not None:
+                lib.asr_add_mask(ptr(dcur), None, ptr(self._input_mask.contiguous()), R, ptr(dcur), R, 2 * H, st)
+            dT = self._buf("dprojT16", (2 * H, R), torch.bfloat16)
+            lib.asr_cast_transpose(ptr(dcur), 2 * H, ptr(dT), R, R, 2 * H, BF16, st)
+            Fd = sp.num_features
+            lib.asr_gemm_tn(BF16, OUT_F32, Fd, 2 * H, R, ptr(self._gen["x_ops"][1]), R, ptr(dT), R, ptr(P.g("proj.W")), 2 * H,
+                            None, 1.0, 0, st)
+            lib.asr_colsum(ptr(dcur), 2 * H, R, 2 * H, ptr(P.g("proj.b")), st)
+
     # ------------------------------------------------------------------- CTC
     def ctc(self, logits, in_len, labels_flat, label_off, max_label_len, grad_scale=1.0, want_grad=True):
         T, N, Cc = logits.shape
@@ -329,6 +614,8 @@ class AcousticEngine:
     def backward(self, dlogits: torch.Tensor):
         """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad."""
         sp, P, w = self.spec, self.params, self._w
+        if sp.general:
+            return self._backward_general(dlogits)
         T, N = self._T, self._N
         H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
         R = T * N
@@ -432,7 +719,7 @@ class AcousticEngine:
 
     # ------------------------------------------------------------ whole step
     def train_step(self, feats_tm, in_len, labels_flat, label_off, max_label_len, global_batch=None,
-                   allreduce=None, masks=None, **opt):
+                   allreduce=None, masks=None, zmasks=None, input_mask=None, **opt):
         """One optimisation step on time-major features; returns the per-utterance CTC loss tensor [N]."""
         N = feats_tm.shape[1]
         caller = torch.cuda.current_stream()
@@ -440,7 +727,7 @@ class AcousticEngine:
         if main is not caller:
             main.wait_stream(caller)
         with torch.cuda.stream(main):
-            logits = self.forward(feats_tm, training=True, masks=masks)
+            logits = self.forward(feats_tm, training=True, masks=masks, zmasks=zmasks, input_mask=input_mask)
             loss, dlogits = self.ctc(logits, in_len, labels_flat, label_off, max_label_len,
                                      grad_scale=1.0 / float(global_batch or N))
             self.backward(dlogits)

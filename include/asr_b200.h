@@ -271,6 +271,10 @@ int32_t asr_mask_cast(const void* src, int32_t src_dtype, int64_t ld_src, const 
 /* out[r, c] = a[r, c] * mask_a[r % n_batch, c] + b[r, c] * mask_b[r % n_batch, c]   (dX of the two directions) */
 int32_t asr_mask_combine(const float* a, const float* b, const float* mask_a, const float* mask_b,
                          int32_t n_batch, float* out, int64_t rows, int32_t cols, void* stream);
+/* out = (a + b) * mask[r % n_batch, c]  (b, mask optional; out may alias a): residual merge(mode='sum')
+ * (core/models.py:273-274) and the element-wise input Dropout (:257-258, n_batch = rows) with its backward. */
+int32_t asr_add_mask(const float* a, const float* b, const float* mask, int64_t n_batch,
+                     float* out, int64_t rows, int32_t cols, void* stream);
 /* out[c] = sum_r src[r, c]  (fp32; bias gradients) */
 int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_t cols,
                    float* out, void* stream);

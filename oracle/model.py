@@ -129,3 +129,116 @@ def synth_labels(seed, n, max_label_length=50):
         L = rng.randint(2, max_label_length)
         out.append(rng.randint(0, 25, size=L).astype(np.int32))
     return out
+
+
+# --------------------------------------------------------------------------- #
+# brsmv1 with its switches on (core/models.py:217-281): zoneout, layer norm,
+# multiplicative integration, residual merge, input dropout
+# --------------------------------------------------------------------------- #
+def init_variant_params(params, num_features, num_hiddens, num_layers, layer_norm=None, mi=None, residual=None,
+                        seed=99):
+    """Adds the extra parameters of the switches to a dict made by init_params():
+    l{l}.mi_alpha/beta1/beta2 [2,4H] = k*ones (core/layers.py:391-405), l{l}.ln_gain_*/ln_bias_* [2,4H] / [2,H]
+    (core/layers.py:407-422), proj.W [F,2H] glorot + proj.b (the TimeDistributed(Dense(2H)) of
+    core/models.py:253-255; with it every layer sees 2H inputs, so l0.W* must be re-drawn by the caller)."""
+    H = num_hiddens
+    p = dict(params)
+    for l in range(num_layers):
+        if mi is not None:
+            for name, k in zip(("mi_alpha", "mi_beta1", "mi_beta2"), mi):
+                p[f"l{l}.{name}"] = np.full((2, 4 * H), k, np.float32)
+        if layer_norm is not None:
+            g0, b0 = layer_norm
+            for name, w in (("uh", 4 * H), ("wx", 4 * H), ("c", H)):
+                p[f"l{l}.ln_gain_{name}"] = np.full((2, w), g0, np.float32)
+                p[f"l{l}.ln_bias_{name}"] = np.full((2, w), b0, np.float32)
+    if residual is not None:
+        rng = np.random.RandomState(seed)
+        p["proj.W"] = olstm.glorot_uniform(rng, (num_features, 2 * H))
+        p["proj.b"] = np.zeros(2 * H, np.float32)
+        for d in ("f", "b"):
+            W, _, _ = olstm.init_lstm(rng, 2 * H, H)
+            p[f"l0.W{d}"] = W
+    return p
+
+
+def _layer_variant(params, l, i, H, zoneout, zmasks):
+    kw = {}
+    if f"l{l}.mi_alpha" in params:
+        kw["mi"] = tuple(params[f"l{l}.{n}"][i] for n in ("mi_alpha", "mi_beta1", "mi_beta2"))
+    if f"l{l}.ln_gain_uh" in params:
+        kw["layer_norm"] = {k: (params[f"l{l}.ln_gain_{k}"][i], params[f"l{l}.ln_bias_{k}"][i]) for k in ("uh", "wx", "c")}
+    if zoneout:
+        zm = (zmasks or {}).get(l, {})
+        kw.update(zoneout_h=zoneout, zoneout_c=zoneout, zmask_h=zm.get("h" + "fb"[i]), zmask_c=zm.get("c" + "fb"[i]))
+    return olstm.make_variant(H, **kw)
+
+
+def forward_general(params, x, masks=None, zoneout=0.0, zmasks=None, residual=None, input_mask=None, dtype=np.float64):
+    """x [N,T,F] -> logits.  masks: {layer: {Wf,Wb,Uf,Ub}} dropout masks; zmasks: {layer: {hf,hb,cf,cb: [T,H]}} zoneout
+    keep masks (None = inference blend); residual: None | 'sum' (core/models.py:273-274); input_mask: [N,T,D]
+    element-wise Dropout mask applied after the optional projection (core/models.py:257-258)."""
+    L = num_layers_of(params)
+    o = np.asarray(x, dtype=dtype)
+    N, T, _ = o.shape
+    ctx = dict(x=o, caches=[], ins=[])
+    if residual is not None:
+        assert residual == "sum"
+        o = (o.reshape(N * T, -1) @ params["proj.W"].astype(dtype)).reshape(N, T, -1) + params["proj.b"].astype(dtype)
+    if input_mask is not None:
+        o = o * input_mask
+    H = params["l0.Uf"].shape[0]
+    for l in range(L):
+        lm = (masks or {}).get(l, {})
+        outs, cs = [], []
+        for i, d in enumerate("fb"):
+            v = _layer_variant(params, l, i, H, zoneout, zmasks)
+            out, c = olstm.lstm_cell_forward(o, params[f"l{l}.W{d}"], params[f"l{l}.U{d}"], params[f"l{l}.b{d}"], v,
+                                             reverse=(d == "b"), mask_W=lm.get("W" + d), mask_U=lm.get("U" + d), dtype=dtype)
+            outs.append(out)
+            cs.append(c)
+        new_o = np.concatenate(outs, axis=2)
+        ctx["caches"].append(cs)
+        o = new_o + o if residual is not None else new_o
+    D = o.shape[2]
+    logits = (o.reshape(N * T, D) @ params["dense.W"].astype(dtype)).reshape(N, T, -1) + params["dense.b"].astype(dtype)
+    ctx.update(top=o, residual=residual, input_mask=input_mask)
+    return logits, ctx
+
+
+def loss_and_grads_general(params, x, x_len, labels, weight_decay=0.0, global_batch=None, dtype=np.float64, **kw):
+    """Returns (total, ctc[N], grads, logits) like loss_and_grads(), for forward_general()."""
+    logits, ctx = forward_general(params, x, dtype=dtype, **kw)
+    N, T, C = logits.shape
+    gb = float(global_batch or N)
+    ctc, dlogits = octc.ctc_loss_grad(logits, x_len, labels, dtype=dtype)
+    dlogits = (dlogits / gb).astype(dtype)
+    top = ctx["top"]
+    D = top.shape[2]
+    H = params["l0.Uf"].shape[0]
+    grads = {"dense.W": top.reshape(N * T, D).T @ dlogits.reshape(N * T, C), "dense.b": dlogits.sum(axis=(0, 1))}
+    do = (dlogits.reshape(N * T, C) @ params["dense.W"].T.astype(dtype)).reshape(N, T, D)
+    for l in range(len(ctx["caches"]) - 1, -1, -1):
+        dx = 0.0
+        for i, d in enumerate("fb"):
+            dxi, gp, _ = olstm.lstm_cell_backward(do[:, :, i * H:(i + 1) * H], ctx["caches"][l][i])
+            dx = dx + dxi
+            grads[f"l{l}.W{d}"], grads[f"l{l}.U{d}"], grads[f"l{l}.b{d}"] = gp["W"], gp["U"], gp["b"]
+            for k, g in gp.items():
+                if k.startswith(("mi_", "ln_")):
+                    grads.setdefault(f"l{l}.{k}", np.zeros((2,) + g.shape, dtype))[i] = g
+        do = do + dx if ctx["residual"] is not None else dx
+    if ctx["input_mask"] is not None:
+        do = do * ctx["input_mask"]
+    if ctx["residual"] is not None:
+        F = ctx["x"].shape[2]
+        grads["proj.W"] = ctx["x"].reshape(N * T, F).T @ do.reshape(N * T, -1)
+        grads["proj.b"] = do.sum(axis=(0, 1))
+    reg = 0.0
+    if weight_decay:
+        for k in params:
+            if k.endswith((".Wf", ".Uf", ".Wb", ".Ub")) or k in ("dense.W", "proj.W"):
+                reg += weight_decay * float(np.sum(np.square(params[k], dtype=np.float64)))
+                grads[k] = grads[k] + 2.0 * weight_decay * params[k]
+    total = float(ctc.astype(np.float64).sum()) / gb + reg
+    return total, ctc, {k: np.asarray(v, dtype=dtype) for k, v in grads.items()}, logits

@@ -123,3 +123,69 @@ def test_sampled_masks_have_keras_statistics():
     v = torch.cat([t.flatten() for l in m.values() for t in l.values()])
     assert set(np.unique(v.cpu().numpy()).round(4).tolist()) <= {0.0, 1.25}
     assert abs(float((v > 0).float().mean()) - 0.8) < 0.02
+
+
+# ---------------------------------------------------------------------------------------------------------
+# brsmv1 switches: zoneout, layer norm, multiplicative integration, residual, input dropout
+# ---------------------------------------------------------------------------------------------------------
+VARIANTS = [
+    dict(mi=(1.0, 0.5, 0.5)),
+    dict(layer_norm=(1.0, 0.0)),
+    dict(zoneout=0.2),
+    dict(residual="sum"),
+    dict(mi=(1.0, 0.5, 0.5), layer_norm=(1.0, 0.0), zoneout=0.15, residual="sum", input_dropout=True, dropout=0.2),
+]
+
+
+@pytest.mark.parametrize("sw", VARIANTS)
+def test_brsmv1_switches_train_step_parity(sw):
+    """Whole training step with the switches on vs the fp64 oracle, same masks on both sides: logits 1e-3,
+    CTC loss 1e-3 rel, every parameter gradient (incl. the MI / LN vectors and the residual projection) 3e-2."""
+    from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
+    N, T, F, H, L, C = 8, 18, 26, 64, 2, 28
+    rng = np.random.RandomState(17)
+    spec = ModelSpec(F, H, L, C, weight_decay=1e-4, dropout=sw.get("dropout", 0.0), zoneout=sw.get("zoneout", 0.0),
+                     layer_norm=sw.get("layer_norm"), mi=sw.get("mi"), residual=sw.get("residual"),
+                     input_dropout=sw.get("input_dropout", False))
+    params = AcousticEngine.keras_init(spec, 77)
+    for k in params:
+        params[k] = (params[k] + 0.05 * rng.randn(*params[k].shape)).astype(np.float32)
+    eng = AcousticEngine(spec, init_params=params)
+    x = rng.randn(N, T, F).astype(np.float32)
+    lens = np.array([T] + [int(rng.randint(T // 2, T + 1)) for _ in range(N - 1)], np.int32)
+    labels = [rng.randint(0, C - 1, size=rng.randint(2, 5)).astype(np.int32) for _ in range(N)]
+    Din = 2 * H if spec.residual else F
+    masks_np = zm_np = im_np = None
+    if spec.dropout:
+        masks_np, D = {}, Din
+        for l in range(L):
+            masks_np[l] = {k: ((rng.rand(N, w) >= 0.2) / 0.8).astype(np.float32)
+                           for k, w in (("Wf", D), ("Wb", D), ("Uf", H), ("Ub", H))}
+            D = 2 * H
+    if spec.zoneout:
+        zm_np = {l: {k + d: (rng.rand(T, H) >= spec.zoneout).astype(np.float32) for k in "hc" for d in "fb"} for l in range(L)}
+    if spec.input_dropout:
+        im_np = ((rng.rand(N, T, Din) >= 0.2) / 0.8).astype(np.float32)
+    masks_dev = None if masks_np is None else {l: {k: dev(v) for k, v in m.items()} for l, m in masks_np.items()}
+    zm_dev = None if zm_np is None else {l: {k: dev(np.stack([m[k + "f"], m[k + "b"]])) for k in "hc"} for l, m in zm_np.items()}
+    im_dev = None if im_np is None else dev(np.ascontiguousarray(im_np.transpose(1, 0, 2)).reshape(T * N, Din))
+    flat, off, mx = pack_labels(labels, "cuda")
+    feats = dev(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    loss = eng.train_step(feats, dev(lens), flat, off, mx, masks=masks_dev, zmasks=zm_dev, input_mask=im_dev,
+                          lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    kw = dict(masks=masks_np, zoneout=spec.zoneout, zmasks=zm_np, residual=spec.residual, input_mask=im_np)
+    _, ctc, grads, ref_logits = om.loss_and_grads_general(p64, x, lens, labels, weight_decay=0.0, **kw)
+    got_logits = eng._w["logits"].cpu().numpy().transpose(1, 0, 2)
+    assert norm_err(got_logits, ref_logits) < 1e-3
+    np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
+    got = eng.params.export("grad")
+    assert set(got) == set(grads)
+    for k, g in grads.items():
+        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+    # inference phase: zoneout blends with (1 - level), no masks
+    logits_eval = eng.forward(feats, training=False).cpu().numpy().transpose(1, 0, 2)
+    p_after = {k: v.astype(np.float64) for k, v in eng.params.export("flat").items()}
+    ref_eval, _ = om.forward_general(p_after, x, zoneout=spec.zoneout, residual=spec.residual)
+    assert norm_err(logits_eval, ref_eval) < 1e-3

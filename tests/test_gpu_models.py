@@ -84,7 +84,22 @@ def test_fit_evaluate_predict_save_load(tmp_path):
     assert meta["epochs"] == [0, 1, 2, 3]
     assert np.array_equal(m2.predict([x[0], x[2]]), pred)
     with pytest.raises(NotImplementedError):
-        models.brsmv1(zoneout=0.1)                        # next row; never silently ignored
+        models.brsmv1(residual="concat")                  # only merge mode 'sum' is built; never silently ignored
+    # the brsmv1 switches run end to end through the same surface (general-cell engine).  layer_norm is left out of
+    # this smoke run on purpose: on zero-padded frames the un-masked reverse direction normalises (near-)constant rows,
+    # 1/sqrt(var + 1e-5) ~ 316 multiplies the gradient at every step and BPTT overflows — the reference's own comment at
+    # core/layers.py:461 ("this is returning a lot of nan"); LN parity is pinned in test_gpu_engine / test_gpu_lstm_cell
+    mv = models.brsmv1(num_features=26, num_hiddens=64, num_layers=2, dropout=0.1, zoneout=0.1,
+                       mi=[1.0, 0.5, 0.5], residual="sum", input_dropout=True)
+    mv.compile(optimizer=models.Adam(lr=3e-3, clipnorm=400.0))
+    h2 = mv.fit_generator(tr, samples_per_epoch=tr.len, nb_epoch=4, verbose=0)
+    assert np.isfinite(h2["loss"]).all() and min(h2["loss"][1:]) < h2["loss"][0]
+    ml = models.brsmv1(num_features=26, num_hiddens=64, num_layers=1, dropout=0.0, layer_norm=[1.0, 0.0])
+    assert ml.spec.layer_norm == (1.0, 0.0) and np.isfinite(ml.test_on_batch(next(te)[0])[1])
+    pv = str(tmp_path / "variant.pkl")
+    mv.save(pv)
+    mv2, _ = models.CTCModel.load(pv)
+    assert mv2.spec.mi == (1.0, 0.5, 0.5) and np.array_equal(mv2.predict([x[0], x[2]]), mv.predict([x[0], x[2]]))
 
 
 def test_train_and_eval_cli(tmp_path):
