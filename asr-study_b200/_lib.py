@@ -31,14 +31,16 @@ class LstmFwdArgs(C.Structure):
     _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("training", C.c_int32),
                 ("zx", C.c_void_p), ("bias", C.c_void_p), ("U", C.c_void_p), ("U16", C.c_void_p),
                 ("h16", C.c_void_p), ("hT16", C.c_void_p), ("h32", C.c_void_p),
-                ("gates", C.c_void_p), ("cell", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p)]
+                ("gates", C.c_void_p), ("cell", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p),
+                ("mask_next", C.c_void_p), ("hm16", C.c_void_p), ("hmT16", C.c_void_p), ("hT16u", C.c_void_p)]
 
 
 class LstmBwdArgs(C.Structure):
     _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("H", C.c_int32),
                 ("dh", C.c_void_p), ("gates", C.c_void_p), ("cell", C.c_void_p),
                 ("U", C.c_void_p), ("U16", C.c_void_p), ("dz16", C.c_void_p), ("dzT16", C.c_void_p),
-                ("dz32", C.c_void_p), ("dbias", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p)]
+                ("dz32", C.c_void_p), ("dbias", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p),
+                ("dh2", C.c_void_p), ("mask_dh", C.c_void_p)]
 
 
 class LstmVariant(C.Structure):
@@ -71,6 +73,7 @@ SIGNATURES = {
     "asr_mfcc_forward_host": (_I32, [_P, _P, _I64, _P]),
     "asr_gemm_tn": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _P]),
     "asr_lstm_flags_bytes": (_SZ, []),
+    "asr_lstm_fuses_masks": (_I32, [_I32, _I32, _I32]),
     "asr_lstm_forward": (_I32, [C.POINTER(LstmFwdArgs), _P]),
     "asr_lstm_backward": (_I32, [C.POINTER(LstmBwdArgs), _P]),
     "asr_lstm_cell_forward": (_I32, [C.POINTER(LstmFwdArgs), C.POINTER(LstmVariant), _P, _P]),
@@ -88,6 +91,7 @@ SIGNATURES = {
     "asr_cast_transpose": (_I32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
     "asr_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P]),
     "asr_mask_cast": (_I32, [_P, _I32, _I64, _P, _I32, _P, _I32, _I64, _I64, _I32, _I32, _P]),
+    "asr_dropout_mask": (_I32, [_P, _I64, _F, C.c_uint64, C.c_uint64, _P]),
     "asr_add_mask": (_I32, [_P, _P, _P, _I64, _P, _I64, _I32, _P]),
     "asr_mask_combine": (_I32, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),
 }
@@ -119,7 +123,7 @@ class _Lib:
             raise AttributeError(name)
         fn = self.raw(name)
         res = SIGNATURES[name][0]
-        if res is not _I32 or name in ("asr_version", "asr_mfcc_num_feats", "asr_mfcc_num_frames"):
+        if res is not _I32 or name in ("asr_version", "asr_mfcc_num_feats", "asr_mfcc_num_frames", "asr_lstm_fuses_masks"):
             return fn
 
         def checked(*a):

@@ -27,6 +27,7 @@ bool supports_fwd(const asr_lstm_fwd_args* a);
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
 }
 namespace lstmtc2 {
+bool shape_supported(int T, int N, int H, bool bwd);
 bool supports_fwd(const asr_lstm_fwd_args* a);
 bool supports_bwd(const asr_lstm_bwd_args* a);
 int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st);
@@ -77,18 +78,27 @@ static int32_t check_common(int T, int N, int H) {
   return ASR_OK;
 }
 
+// the fused dropout fields are implemented by the default tensor-core engine (lstm_tc2.cu) only
+extern "C" int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H) {
+  if (env_is("ASR_B200_LSTM", "fp32") || env_is("ASR_B200_LSTM", "tc1") || env_is("ASR_B200_LSTM", "tc3")) return 0;
+  return lstmtc2::shape_supported(T, N, H, false) && lstmtc2::shape_supported(T, N, H, true) ? 1 : 0;
+}
+
 extern "C" int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream) {
   ASR_CHECK_ARG(a && a->zx && a->bias && a->flags, "asr_lstm_forward: null argument");
   if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
   ASR_CHECK_ARG(!a->training || (a->gates && a->cell), "asr_lstm_forward: training needs gates/cell buffers");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool fused = a->mask_next || a->hm16 || a->hmT16 || a->hT16u;
+  ASR_CHECK_ARG(!a->mask_next == !a->hm16, "asr_lstm_forward: mask_next and hm16 go together");
   if (!env_is("ASR_B200_LSTM", "fp32")) {
     const bool pin1 = env_is("ASR_B200_LSTM", "tc1"), pin3 = env_is("ASR_B200_LSTM", "tc3");
-    if (pin3 && lstmtc3::supports_fwd(a)) return lstmtc3::forward(a, st);              // cluster / DSMEM exchange (same speed, kept selectable)
-    if (!pin1 && lstmtc2::supports_fwd(a)) return lstmtc2::forward(a, st);             // LL ring through L2 (default)
-    if (lstmtc::supports_fwd(a)) return lstmtc::forward(a, st);
+    if (pin3 && !fused && lstmtc3::supports_fwd(a)) return lstmtc3::forward(a, st);    // cluster / DSMEM exchange (same speed, kept selectable)
+    if (!pin1 && !pin3 && lstmtc2::supports_fwd(a)) return lstmtc2::forward(a, st);    // LL ring through L2 (default)
+    if (!fused && lstmtc::supports_fwd(a)) return lstmtc::forward(a, st);
   }
-  ASR_CHECK_ARG(a->U, "asr_lstm_forward: fp32 engine needs U");
+  ASR_CHECK_ARG(!fused, "asr_lstm_forward: fused dropout outputs need the engine asr_lstm_fuses_masks() reports");
+  ASR_CHECK_ARG(a->U && a->h16, "asr_lstm_forward: fp32 engine needs U and h16");
   return lstm32::forward(a, st);
 }
 
@@ -96,10 +106,13 @@ extern "C" int32_t asr_lstm_backward(const asr_lstm_bwd_args* a, void* stream) {
   ASR_CHECK_ARG(a && a->dh && a->gates && a->cell && a->dbias && a->flags, "asr_lstm_backward: null argument");
   if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool fused = a->dh2 || a->mask_dh;
+  ASR_CHECK_ARG(!a->dh2 || a->mask_dh, "asr_lstm_backward: dh2 needs mask_dh");
   if (!env_is("ASR_B200_LSTM", "fp32")) {
     if (!env_is("ASR_B200_LSTM", "tc1") && lstmtc2::supports_bwd(a)) return lstmtc2::backward(a, st);
-    if (lstmtc::supports_bwd(a)) return lstmtc::backward(a, st);
+    if (!fused && lstmtc::supports_bwd(a)) return lstmtc::backward(a, st);
   }
+  ASR_CHECK_ARG(!fused, "asr_lstm_backward: fused dropout inputs need the engine asr_lstm_fuses_masks() reports");
   ASR_CHECK_ARG(a->U, "asr_lstm_backward: fp32 engine needs U");
   return lstm32::backward(a, st);
 }

@@ -130,11 +130,15 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   float bias[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) bias[g] = a.bias[(size_t)dir * 4 * H + g * H + u];
-  float c_state[NPT], mu[NPT];
+  float c_state[NPT], mu[NPT], mn0[NPT], mn1[NPT];
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     c_state[i] = 0.0f;
     mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;   // B_U, constant over time
+    // B_W of the NEXT layer's two directions (core/layers.py:439 applies it to this layer's output): the masked
+    // operand copies are written here, as side stores, instead of by separate mask kernels
+    mn0[i] = a.mask_next ? a.mask_next[((size_t)0 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
+    mn1[i] = a.mask_next ? a.mask_next[((size_t)1 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
   }
 
   int* status = flags + STATUS_IDX;
@@ -149,20 +153,26 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
       const size_t row = (size_t)t * N + n0 + warp * NPT + i;
-      h16[row * 2 * H + dir * H + u] = __float2half_rn(hv[i]);
+      if (h16) h16[row * 2 * H + dir * H + u] = __float2half_rn(hv[i]);
       if (a.h32) a.h32[row * 2 * H + dir * H + u] = hv[i];
+      if (a.hm16) {
+        __half* hm = reinterpret_cast<__half*>(a.hm16);
+        hm[row * 2 * H + dir * H + u] = __float2half_rn(hv[i] * mn0[i]);
+        hm[(R + row) * 2 * H + dir * H + u] = __float2half_rn(hv[i] * mn1[i]);
+      }
       if (a.training) {
         float* gp = a.gates + (row * 2 + dir) * 4 * H;
         gp[u] = gi[i]; gp[H + u] = gf[i]; gp[2 * H + u] = gg[i]; gp[3 * H + u] = go[i];
         a.cell[(row * 2 + dir) * H + u] = cs[i];
       }
     }
-    if (a.training && a.hT16) {   // the thread's NPT samples are contiguous in the transposed copy: one 8-byte store
-      static_assert(NPT == 4 || NPT == 2, "packed transposed store: 2 or 4 samples per thread");
-      __nv_bfloat16* dstT = reinterpret_cast<__nv_bfloat16*>(a.hT16) + (size_t)(dir * H + u) * R + (size_t)t * N + n0 + warp * NPT;
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0] * mu[0], hv[1] * mu[1]);
+    // transposed bf16 copies: the thread's NPT samples are contiguous, one 4- or 8-byte store per copy
+    static_assert(NPT == 4 || NPT == 2, "packed transposed store: 2 or 4 samples per thread");
+    auto storeT = [&](void* base, size_t plane, const float (&m)[NPT]) {
+      __nv_bfloat16* dstT = reinterpret_cast<__nv_bfloat16*>(base) + plane + (size_t)(dir * H + u) * R + (size_t)t * N + n0 + warp * NPT;
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0] * m[0], hv[1] * m[1]);
       if constexpr (NPT == 4) {
-        const __nv_bfloat162 p1 = __floats2bfloat162_rn(hv[2] * mu[2], hv[3] * mu[3]);
+        const __nv_bfloat162 p1 = __floats2bfloat162_rn(hv[2] * m[2], hv[3] * m[3]);
         uint2 pk;
         pk.x = *reinterpret_cast<const uint32_t*>(&p0);
         pk.y = *reinterpret_cast<const uint32_t*>(&p1);
@@ -170,6 +180,17 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       } else {
         *reinterpret_cast<__nv_bfloat162*>(dstT) = p0;
       }
+    };
+    if (a.training && a.hT16) storeT(a.hT16, 0, mu);                       // h * B_U: the dU operand
+    if (a.training && a.hmT16) {                                           // h * B_W(next layer, dir 0 / 1): its dW operands
+      storeT(a.hmT16, 0, mn0);
+      storeT(a.hmT16, (size_t)2 * H * R, mn1);
+    }
+    if (a.training && a.hT16u) {                                           // unmasked (the Dense kernel's dW operand)
+      float one[NPT];
+#pragma unroll
+      for (int i = 0; i < NPT; ++i) one[i] = 1.0f;
+      storeT(a.hT16u, 0, one);
     }
   };
   float p_hv[NPT], p_gi[NPT], p_gf[NPT], p_gg[NPT], p_go[NPT], p_cs[NPT];
@@ -397,11 +418,15 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   const uint32_t idesc = tc::umma_idesc_f16(128, NM, 1);
   const uint32_t sB_addr = tc::smem_u32(sB);
   const int u = u0 + lane;
-  float dc_carry[NPT], mu[NPT], db[4] = {0, 0, 0, 0};
+  float dc_carry[NPT], mu[NPT], md0[NPT], md1[NPT], db[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     dc_carry[i] = 0.0f;
     mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;
+    // dL/d(output) = (dz_f . Wf^T) * B_Wf + (dz_b . Wb^T) * B_Wb of the layer above: the two GEMM results arrive
+    // separately (dh, dh2) and are combined here with the masks (constant over time) instead of by a combine kernel
+    md0[i] = a.mask_dh ? a.mask_dh[((size_t)0 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
+    md1[i] = a.mask_dh ? a.mask_dh[((size_t)1 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
   }
 
   int* status = flags + STATUS_IDX;
@@ -449,11 +474,12 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     const int t = dir ? s : (T - 1 - s);
     const int t_fprev = dir ? (t + 1) : (t - 1);
     const bool has_fprev = dir ? (t + 1 < T) : (t > 0);
-    float dho[NPT], gi[NPT], gf[NPT], gg[NPT], go[NPT], cc[NPT], cp[NPT];
+    float dho[NPT], dho2[NPT], gi[NPT], gf[NPT], gg[NPT], go[NPT], cc[NPT], cp[NPT];
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
       const size_t row = (size_t)t * N + n0 + warp * NPT + i;
-      dho[i] = __ldg(a.dh + row * 2 * H + dir * H + u);
+      dho[i] = __ldg(a.dh + row * 2 * H + dir * H + u);            // consumed after both hops: the load latency stays hidden
+      dho2[i] = a.dh2 ? __ldg(a.dh2 + row * 2 * H + dir * H + u) : 0.0f;
       const float* gp = a.gates + (row * 2 + dir) * 4 * H;
       gi[i] = __ldg(gp + u); gf[i] = __ldg(gp + H + u); gg[i] = __ldg(gp + 2 * H + u); go[i] = __ldg(gp + 3 * H + u);
       cc[i] = __ldg(a.cell + (row * 2 + dir) * H + u);
@@ -581,7 +607,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     uint2* xo = x1 + (size_t)(s & 1) * WORDS1;
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
-      const float dh = dho[i] + dh_rec[i];
+      const float dh = fmaf(dho2[i], md1[i], fmaf(dho[i], md0[i], dh_rec[i]));
       const float tch = asr::tanh_fast(cc[i]);
       const float d_o = dh * tch * asr::hard_sigmoid_grad(go[i]);
       const float dc = dc_carry[i] + dh * go[i] * (1.0f - tch * tch);
@@ -636,7 +662,8 @@ static int group_size(int N, int H) {
 static bool shape_ok(int T, int N, int H) {
   return T >= 1 && (H == 128 || H == 256 || H == 384 || H == 512) && N >= 8 && group_size(N, H) != 0;
 }
-bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && a->h16 && shape_ok(a->T, a->N, a->H); }
+bool shape_supported(int T, int N, int H, bool bwd) { return shape_ok(T, N, H) && (!bwd || H == 512); }
+bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && (a->h16 || a->hm16) && shape_ok(a->T, a->N, a->H); }
 bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && a->H == 512 && shape_ok(a->T, a->N, a->H); }
 static size_t x1_bytes_per_dg(int NB) { return (size_t)4 * 2 * NB * 256 * sizeof(uint2); }           // hop 1 per (dir, grp)
 static size_t x2_bytes_per_dg(int NB) { return (size_t)4 * 4 * 4 * 2 * NB * 32 * sizeof(uint2); }    // hop 2 per (dir, grp)

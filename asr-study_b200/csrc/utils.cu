@@ -262,3 +262,23 @@ extern "C" int32_t asr_add_mask(const float* a, const float* b, const float* mas
   ASR_LAUNCH_CHECK();
   return ASR_OK;
 }
+
+// Bernoulli keep masks scaled by 1/(1-p) (K.dropout, Keras-1): out[i] = u_i >= p ? 1/(1-p) : 0 with u_i from a
+// counter-based generator (splitmix64 of seed and the element counter), so ONE launch fills every mask of a step
+__global__ void dropout_mask_kernel(float* __restrict__ out, int64_t n, float p, float scale, uint64_t seed, uint64_t offset) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(offset + (uint64_t)i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);      // 24 random bits -> [0, 1)
+    out[i] = u >= p ? scale : 0.0f;
+  }
+}
+
+extern "C" int32_t asr_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  ASR_CHECK_ARG(out && n > 0 && p >= 0.0f && p < 1.0f, "asr_dropout_mask: bad argument");
+  dropout_mask_kernel<<<grid_1d(n), 256, 0, (cudaStream_t)stream>>>(out, n, p, 1.0f / (1.0f - p), seed, offset);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}

@@ -139,20 +139,35 @@ class AcousticEngine:
         self.overlap = os.environ.get("ASR_B200_OVERLAP", "1") != "0"
         self._mask_rng = torch.Generator(device=self.device)
         self._mask_rng.manual_seed(seed + 17)
+        self._mask_seed, self._mask_offset = (seed + 17) * 0x9E3779B1 & 0xFFFFFFFFFFFFFFFF, 0
 
     # ------------------------------------------------------------ dropout masks
     def sample_masks(self, N):
         """Keras-1 LSTM.get_constants: one B_W [N, D] and one B_U [N, H] mask per direction and layer, sampled
-        once per batch, constant over time, scaled by 1/(1-p) (K.dropout).  Returns {layer: {Wf,Wb,Uf,Ub}}."""
+        once per batch, constant over time, scaled by 1/(1-p) (K.dropout).  Returns {layer: {Wf,Wb,Uf,Ub}} plus the
+        packed views W2 [2,N,D] / U2 [2,N,H] the kernels take.  One asr_dropout_mask launch fills all of them."""
         sp, p = self.spec, float(self.spec.dropout)
-        out, D = {}, (sp.num_features if sp.residual is None else 2 * sp.num_hiddens)
-        for l in range(sp.num_layers):
-            out[l] = {}
-            for k, w in (("Wf", D), ("Wb", D), ("Uf", sp.num_hiddens), ("Ub", sp.num_hiddens)):
-                keep = torch.rand(N, w, device=self.device, generator=self._mask_rng) >= p
-                out[l][k] = keep.float() / (1.0 - p)
-            D = 2 * sp.num_hiddens
+        H = sp.num_hiddens
+        D0 = sp.num_features if sp.residual is None else 2 * H
+        widths = [(D0 if l == 0 else 2 * H) for l in range(sp.num_layers)]
+        total = sum(2 * N * (D + H) for D in widths)
+        flat = self._buf("dropout_masks", (total,), torch.float32)
+        lib.asr_dropout_mask(ptr(flat), total, p, self._mask_seed, self._mask_offset, cur_stream())
+        self._mask_offset += total
+        out, o = {}, 0
+        for l, D in enumerate(widths):
+            W2 = flat[o:o + 2 * N * D].view(2, N, D); o += 2 * N * D
+            U2 = flat[o:o + 2 * N * H].view(2, N, H); o += 2 * N * H
+            out[l] = {"Wf": W2[0], "Wb": W2[1], "Uf": U2[0], "Ub": U2[1], "W2": W2, "U2": U2}
         return out
+
+    @staticmethod
+    def _packed(mk, key):
+        """[2, N, *] contiguous (fwd | bwd) view of a layer's masks: the packed view when sampled here, a stack when
+        the caller supplied separate tensors."""
+        if key + "2" in mk:
+            return mk[key + "2"]
+        return torch.stack([mk[key + "f"], mk[key + "b"]]).contiguous()
 
     # ------------------------------------------------------------------ init
     @staticmethod
@@ -301,32 +316,55 @@ class AcousticEngine:
             lib.asr_cast_transpose(ptr(feats_tm), Fd, ptr(w["xT16"]), R, R, Fd, BF16, st)
         x16, D = w["x16"], D0
         src, src_dt, src_ld, Dl = feats_tm, 2, Fd, Fd              # layer input before masking
+        # with dropout the recurrence of layer l-1 writes the masked operand copies of layer l itself (fused side
+        # stores) when the selected engine supports it; otherwise asr_mask_cast makes them
+        fuse = masks is not None and bool(lib.asr_lstm_fuses_masks(T, N, H))
+        self._fused = fuse
+        prev = None                                                 # fused outputs of the previous layer
         for l in range(L):
             mask_u = None
             if masks is None:
                 self._gemm(F16, OUT_F32, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, w["zx"], 8 * H)
             else:
                 mk = masks[l]
-                mask_u = self._buf(f"maskU.{l}", (2, N, H), torch.float32)
-                mask_u[0].copy_(mk["Uf"]); mask_u[1].copy_(mk["Ub"])
+                mask_u = self._packed(mk, "U")
+                self._views[f"maskU.{l}"] = mask_u
                 for i, d in enumerate("fb"):
-                    mw = mk["W" + d].contiguous()
-                    xm = self._buf(f"xm16.{i}", (R, D), torch.float16)
-                    lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xm), F16, D, R, Dl, 0, st)
+                    if prev is not None:
+                        xm = prev["hm16"][i]
+                        if training:
+                            self._views[f"xmT16.{l}.{i}"] = prev["hmT16"][i]
+                    else:
+                        mw = mk["W" + d].contiguous()
+                        xm = self._buf(f"xm16.{i}", (R, D), torch.float16)
+                        lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xm), F16, D, R, Dl, 0, st)
+                        if training:
+                            xmT = self._buf(f"xmT16.{l}.{i}", (Dl, R), torch.bfloat16)
+                            lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xmT), BF16, R, R, Dl, 1, st)
                     lib.asr_gemm_tn(F16, OUT_F32, R, 4 * H, D, ptr(xm), D, ptr(self._views[f"WcatT16.{l}"][i * 4 * H:]), D,
                                     ptr(w["zx"][:, i * 4 * H:]), 8 * H, None, 1.0, 0, st)
-                    if training:
-                        xmT = self._buf(f"xmT16.{l}.{i}", (Dl, R), torch.bfloat16)
-                        lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xmT), BF16, R, R, Dl, 1, st)
+            top = l == L - 1
+            fz = dict(mask_next=None, hm16=None, hmT16=None, hT16u=None)
+            cur = None
+            if fuse and not top:
+                cur = dict(hm16=self._buf(f"hm16.{l}", (2, R, 2 * H), torch.float16),
+                           hmT16=self._buf(f"hmT16.{l}", (2, 2 * H, R), torch.bfloat16) if training else None)
+                mnext = self._packed(masks[l + 1], "W")
+                self._views[f"maskW.{l + 1}"] = mnext
+                fz.update(mask_next=ptr(mnext).value, hm16=ptr(cur["hm16"]).value,
+                          hmT16=ptr(cur["hmT16"]).value if training else None)
+            if fuse and top and training:
+                fz["hT16u"] = ptr(self._buf("topT16", (2 * H, R), torch.bfloat16)).value
             a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(w["zx"]).value,
                             bias=ptr(P.p(f"l{l}.bf")).value, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"UT16.{l}"]).value,
-                            h16=ptr(w[f"h16.{l}"]).value,
+                            h16=ptr(w[f"h16.{l}"]).value if (top or not fuse) else None,
                             hT16=ptr(w[f"hT16.{l}"]).value if training else None, h32=None,
                             gates=ptr(w[f"gates.{l}"]).value if training else None,
                             cell=ptr(w[f"cell.{l}"]).value if training else None,
-                            flags=ptr(self._flags).value, mask_u=ptr(mask_u).value if mask_u is not None else None)
+                            flags=ptr(self._flags).value, mask_u=ptr(mask_u).value if mask_u is not None else None, **fz)
             lib.asr_lstm_forward(C.byref(a), st)
+            prev = cur
             x16, D = w[f"h16.{l}"], 2 * H
             src, src_dt, src_ld, Dl = w[f"h16.{l}"], 0, 2 * H, 2 * H
         self._gemm(F16, OUT_F32, R, Cc, 2 * H, x16, 2 * H, self._ws["WdT16"], 2 * H, w["logits"], Cc,
@@ -626,7 +664,10 @@ class AcousticEngine:
         lib.asr_colsum(ptr(dlogits), Cc, R, Cc, ptr(P.g("dense.b")), st)
         top = L - 1
         topT = w[f"hT16.{top}"]
-        if self._masks is not None:
+        fuse = self._masks is not None and getattr(self, "_fused", False)
+        if self._masks is not None and fuse:
+            topT = self._views["topT16"]          # unmasked transposed copy written by the top layer's recurrence
+        elif self._masks is not None:
             # with dropout hT16 holds h * B_U (the dU operand); the Dense kernel saw the unmasked h
             ones = self._buf("ones_mask", (N, 2 * H), torch.float32)
             ones.fill_(1.0)
@@ -638,6 +679,7 @@ class AcousticEngine:
         dh, other = w["dhA"], w["dhB"]
         self._gemm(BF16, OUT_F32, R, 2 * H, cp, w["dl16"], cp, self._ws["Wd16"], cp, dh, 2 * H)
         masks = self._masks
+        dh2, mask_dh = None, None                  # fused path: the layer above left its dX as two masked partials
         for l in range(L - 1, -1, -1):
             mask_u = self._views[f"maskU.{l}"] if masks is not None else None
             a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(w[f"gates.{l}"]).value,
@@ -645,8 +687,11 @@ class AcousticEngine:
                             U16=ptr(self._ws[f"Ub16.{l}"]).value,
                             dz16=ptr(w[f"dz16.{l}"]).value, dzT16=ptr(w[f"dzT16.{l}"]).value, dz32=None,
                             dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value,
-                            mask_u=ptr(mask_u).value if mask_u is not None else None)
+                            mask_u=ptr(mask_u).value if mask_u is not None else None,
+                            dh2=ptr(dh2).value if dh2 is not None else None,
+                            mask_dh=ptr(mask_dh).value if mask_dh is not None else None)
             lib.asr_lstm_backward(C.byref(a), st)
+            dh2, mask_dh = None, None
             D = sp.num_features if l == 0 else 2 * H
             xT = w["xT16"] if l == 0 else w[f"hT16.{l - 1}"]
             hT = w[f"hT16.{l}"]
@@ -688,9 +733,12 @@ class AcousticEngine:
                     lib.asr_gemm_tn(BF16, OUT_F32, R, 2 * H, 4 * H, ptr(w[f"dz16.{l}"][:, i * 4 * H:]), 8 * H,
                                     ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), 2 * H, None, 1.0, 0, st)
                 mk = masks[l]
-                lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
-                                     ptr(other), R, 2 * H, st)
-                dh, other = other, dh
+                if fuse:                            # the BPTT kernel of layer l-1 combines the partials with B_Wf / B_Wb
+                    dh, dh2, mask_dh = part[0], part[1], self._views[f"maskW.{l}"]
+                else:
+                    lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
+                                         ptr(other), R, 2 * H, st)
+                    dh, other = other, dh
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self._side)
 

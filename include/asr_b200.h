@@ -132,6 +132,11 @@ typedef struct {
   const float* mask_u;      /* f32 [2, N, H] variational-dropout mask B_U (already /(1-p)) applied to
                                h_{t-1} in the recurrence (core/layers.py:438), or NULL.  When set,
                                hT16 holds h*mask (the operand of dU); h16/h32 stay unmasked.        */
+  /* fused dropout outputs (engines that report asr_lstm_fuses_masks() == 1; ignored otherwise):          */
+  const float* mask_next;   /* f32 [2, N, 2H]  B_W of the NEXT layer's fwd | bwd LSTM, or NULL             */
+  void*  hm16;              /* fp16 [2, T*N, 2H]  h * mask_next[i]: the next layer's projection operands    */
+  void*  hmT16;             /* bf16 [2, 2H, T*N]  transposed copies: the next layer's dW operands (training)*/
+  void*  hT16u;             /* bf16 [2H, T*N]  unmasked transposed copy (the Dense dW operand), or NULL     */
 } asr_lstm_fwd_args;
 
 typedef struct {
@@ -147,7 +152,15 @@ typedef struct {
   float* dbias;             /* f32 [2, 4H]  (overwritten)                     */
   int32_t* flags;
   const float* mask_u;      /* same mask as in the forward call, or NULL      */
+  /* fused dropout inputs (asr_lstm_fuses_masks() == 1): dL/d(output) = dh * mask_dh[0] + dh2 * mask_dh[1] */
+  const float* dh2;         /* f32 [T, N, 2H]  second partial (the bwd LSTM of the layer above), or NULL    */
+  const float* mask_dh;     /* f32 [2, N, 2H]  B_W of the layer above (fwd | bwd), or NULL = ones            */
 } asr_lstm_bwd_args;
+
+/* 1 when the engine asr_lstm_forward/backward would select for this shape implements the fused dropout
+ * fields above (mask_next/hm16/hmT16/hT16u, dh2/mask_dh); 0 = the caller must mask with asr_mask_cast /
+ * asr_mask_combine instead. */
+int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H);
 
 size_t  asr_lstm_flags_bytes(void);
 int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream);
@@ -275,6 +288,9 @@ int32_t asr_mask_combine(const float* a, const float* b, const float* mask_a, co
  * (core/models.py:273-274) and the element-wise input Dropout (:257-258, n_batch = rows) with its backward. */
 int32_t asr_add_mask(const float* a, const float* b, const float* mask, int64_t n_batch,
                      float* out, int64_t rows, int32_t cols, void* stream);
+/* variational-dropout masks (core/layers.py:306-339 under Keras-1 K.dropout): out[i] = keep ? 1/(1-p) : 0,
+ * keep ~ Bernoulli(1-p) from a counter-based generator keyed by (seed, offset + i): one launch per step. */
+int32_t asr_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
 /* out[c] = sum_r src[r, c]  (fp32; bias gradients) */
 int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_t cols,
                    float* out, void* stream);
