@@ -72,6 +72,7 @@ SIGNATURES = {
     "asr_mfcc_forward": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _I32, _P, _P]),
     "asr_mfcc_forward_host": (_I32, [_P, _P, _I64, _P]),
     "asr_gemm_tn": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _P]),
+    "asr_gemm_tn_ex": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I32, _P]),
     "asr_lstm_flags_bytes": (_SZ, []),
     "asr_lstm_fuses_masks": (_I32, [_I32, _I32, _I32]),
     "asr_lstm_forward": (_I32, [C.POINTER(LstmFwdArgs), _P]),

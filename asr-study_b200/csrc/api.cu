@@ -12,6 +12,11 @@ bool supports(int dtype_in, int dtype_out, int M, int N, int K, int64_t lda, int
 int32_t run(int dtype_in, int dtype_out, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
             void* C, int64_t ldc, const float* bias, float alpha, int accumulate, cudaStream_t st);
 }
+namespace gemm_tc2 {
+bool supports(int dtype_in, int dtype_out, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc);
+int32_t run(int dtype_in, int dtype_out, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
+            void* C, int64_t ldc, const float* bias, float alpha, int accumulate, cudaStream_t st);
+}
 namespace lstm32 {
 size_t scratch_bytes(int H);
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st);
@@ -49,9 +54,9 @@ static int env_is(const char* name, const char* val) {
   return e && strcmp(e, val) == 0;
 }
 
-extern "C" int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N, int32_t K, const void* A,
-                               int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
-                               float alpha, int32_t accumulate, void* stream) {
+extern "C" int32_t asr_gemm_tn_ex(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N, int32_t K, const void* A,
+                                  int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
+                                  float alpha, int32_t accumulate, int32_t flags, void* stream) {
   ASR_CHECK_ARG(A && B && C, "asr_gemm_tn: null operand");
   ASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "asr_gemm_tn: bad shape %dx%dx%d", M, N, K);
   ASR_CHECK_ARG(dtype_in >= 0 && dtype_in <= 1 && dtype_out >= 0 && dtype_out <= 2, "asr_gemm_tn: bad dtype");
@@ -60,9 +65,23 @@ extern "C" int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, i
   ASR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "asr_gemm_tn: operands must be 16-byte aligned");
   ASR_CHECK_ARG(!accumulate || dtype_out == 0, "asr_gemm_tn: accumulate needs fp32 C");
   cudaStream_t st = (cudaStream_t)stream;
-  if (!env_is("ASR_B200_GEMM", "mma") && gemm_tc::supports(dtype_in, dtype_out, M, N, K, lda, ldb, ldc))
+  if (env_is("ASR_B200_GEMM", "mma"))
+    return gemm_mma::run(dtype_in, dtype_out, M, N, K, A, lda, B, ldb, C, ldc, bias, alpha, accumulate, st);
+  // persistent 128x256 engine for the large regular projections; a GEMM that is meant to run BESIDE a persistent
+  // recurrence (ASR_GEMM_BACKGROUND: only the SMs that kernel leaves idle are free) keeps the non-persistent tiling,
+  // whose CTAs are scheduled one by one as SMs free up
+  if (!(flags & ASR_GEMM_BACKGROUND) && !env_is("ASR_B200_GEMM", "tc1") &&
+      gemm_tc2::supports(dtype_in, dtype_out, M, N, K, lda, ldb, ldc))
+    return gemm_tc2::run(dtype_in, dtype_out, M, N, K, A, lda, B, ldb, C, ldc, bias, alpha, accumulate, st);
+  if (gemm_tc::supports(dtype_in, dtype_out, M, N, K, lda, ldb, ldc))
     return gemm_tc::run(dtype_in, dtype_out, M, N, K, A, lda, B, ldb, C, ldc, bias, alpha, accumulate, st);
   return gemm_mma::run(dtype_in, dtype_out, M, N, K, A, lda, B, ldb, C, ldc, bias, alpha, accumulate, st);
+}
+
+extern "C" int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N, int32_t K, const void* A,
+                               int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
+                               float alpha, int32_t accumulate, void* stream) {
+  return asr_gemm_tn_ex(dtype_in, dtype_out, M, N, K, A, lda, B, ldb, C, ldc, bias, alpha, accumulate, 0, stream);
 }
 
 extern "C" size_t asr_lstm_flags_bytes(void) {

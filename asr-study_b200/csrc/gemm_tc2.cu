@@ -1,0 +1,276 @@
+// K2/K5 (v2) — persistent TN GEMM on tcgen05 + TMEM + TMA for the large projections of the hot path, sm_100a.
+//   C[M,N] (+)= alpha * A[M,K] * B[N,K]^T + bias        A,B 16-bit K-major, fp32 accumulate
+//
+// What changed against gemm_tc.cu (kept for small / ragged N) and why:
+//   * 128 x 256 output tiles: one M128 N256 K16 tcgen05.mma per 16 K elements.  A 128 x 128 SS-mode tile reads
+//     (128 + 128) x 64 x 2 B of shared memory per 256 tensor cycles = 128 B/clk, the whole shared-memory bandwidth
+//     of the SM; 128 x 256 reads 96 B/clk, so the tensor pipe is no longer operand-starved.
+//   * persistent CTAs (one per SM, static round-robin over (tile, k-slice) work items) with TWO 256-column TMEM
+//     accumulators: the epilogue of item i (TMEM -> registers -> smem transpose -> coalesced 128-byte stores) runs
+//     under the main loop of item i+1 instead of needing a second resident CTA.
+//   * 4-stage TMA ring of 48 KB stages (A 16 KB + B 32 KB, SWIZZLE_128B).
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane),
+// warps 2..5 = epilogue, one TMEM lane quarter each (warp % 4).
+// Split-K (fp32 C, red.global.add into a zeroed C) for the short-M/N, long-K gradient GEMMs.
+#include "common.cuh"
+#include "tc.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace gemm_tc2 {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KB
+constexpr int STG_FLOATS = 32 * 36;                                                              // per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
+
+struct Params {
+  int M, N, K;
+  void* C;
+  int64_t ldc;
+  const float* bias;
+  float alpha;
+  int dtype_out, accumulate, ab_fmt;
+  int tiles_m, tiles_n, split, kb_per_split, nkb_total;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg_base + 4 * STG_FLOATS);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = p.tiles_m * p.tiles_n * p.split;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full + s, 1);
+      tc::mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tmem_full + b, 1);
+      tc::mbar_init(tmem_empty + b, 4);      // one arrival per epilogue warp
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  if (*tmem_slot != 0u) __trap();             // the CTA owns the SM's whole tensor memory (1 CTA/SM by shared memory)
+  constexpr uint32_t tmem = 0u;
+
+  // work item -> (m tile, n tile, k slice); n fastest so concurrently running CTAs share A rows through L2
+  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
+    const int slice = item / (p.tiles_m * p.tiles_n);
+    const int t = item - slice * (p.tiles_m * p.tiles_n);
+    m0 = (t / p.tiles_n) * BM;
+    n0 = (t % p.tiles_n) * BN;
+    kb0 = slice * p.kb_per_split;
+    nkb = min(p.kb_per_split, p.nkb_total - kb0);
+  };
+
+  if (warp == 0) {
+    if (tc::elect_one_sync()) {
+      int it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        decode(item, m0, n0, kb0, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (!tc::mbar_wait(empty + s, ph ^ 1)) __trap();
+          uint8_t* a = smem + s * STAGE_BYTES;
+          tc::mbar_expect_tx(full + s, STAGE_BYTES);
+          tc::tma_load_2d(a, &tmA, full + s, (kb0 + kb) * BK, m0);
+          tc::tma_load_2d(a + A_BYTES, &tmB, full + s, (kb0 + kb) * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one_sync()) {
+      const uint32_t idesc = tc::umma_idesc_f16(BM, BN, p.ab_fmt);
+      int it = 0, w = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++w) {
+        int m0, n0, kb0, nkb;
+        decode(item, m0, n0, kb0, nkb);
+        const int b = w & 1;
+        if (!tc::mbar_wait(tmem_empty + b, (uint32_t)(((w >> 1) & 1) ^ 1))) __trap();   // epilogue drained this accumulator
+        tc::tcgen05_fence_after();
+        const uint32_t d = tmem + (uint32_t)(b * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (!tc::mbar_wait(full + s, ph)) __trap();
+          tc::tcgen05_fence_after();
+          const uint32_t a = tc::smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t ad = tc::umma_desc_sw128(a), bd = tc::umma_desc_sw128(a + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) tc::umma_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          tc::umma_commit(empty + s);
+        }
+        tc::umma_commit(tmem_full + b);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stg = stg_base + q * STG_FLOATS;
+    const int sub = lane >> 3, l8 = lane & 7;
+    const bool split = p.split > 1;
+    int w = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++w) {
+      int m0, n0, kb0, nkb;
+      decode(item, m0, n0, kb0, nkb);
+      const int b = w & 1;
+      if (!tc::mbar_wait(tmem_full + b, (uint32_t)((w >> 1) & 1))) __trap();
+      tc::tcgen05_fence_after();
+      const bool add_bias = p.bias != nullptr && kb0 == 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0), r);
+        tc::tmem_ld_wait();
+        if (c0 + 32 == BN) {                       // last read of this accumulator: hand it back to the MMA warp
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tmem_empty + b);
+        }
+        if (n0 + c0 >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * 36 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + l8 * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add_bias) {
+          if (col < p.N) bv.x = __ldg(p.bias + col);
+          if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
+          if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
+          if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
+        }
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int rl = pass * 4 + sub;
+          const int row = m0 + q * 32 + rl;
+          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 36 + l8 * 4);
+          float v[4] = {p.alpha * a.x + bv.x, p.alpha * a.y + bv.y, p.alpha * a.z + bv.z, p.alpha * a.w + bv.w};
+          if (row >= p.M || col >= p.N) continue;
+          const int64_t o = (int64_t)row * p.ldc + col;
+          const int nc = min(4, p.N - col);
+          if (p.dtype_out == 0) {
+            float* cp = reinterpret_cast<float*>(p.C) + o;
+            if (split) {
+              for (int j = 0; j < nc; ++j) atomicAdd(cp + j, v[j]);
+            } else if (nc == 4 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+              if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(cp);
+                v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
+              }
+              *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+              for (int j = 0; j < nc; ++j) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
+            }
+          } else if (p.dtype_out == 1) {
+            __half* cp = reinterpret_cast<__half*>(p.C) + o;
+            for (int j = 0; j < nc; ++j) cp[j] = __float2half_rn(v[j]);
+          } else {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + o;
+            for (int j = 0; j < nc; ++j) cp[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---- host --------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_once;
+
+static bool make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int ab_fmt, int box_rows) {
+  std::call_once(g_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  });
+  if (!g_encode) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = ab_fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  return g_encode(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// large, regular problems only: everything else stays on gemm_tc.cu
+bool supports(int dtype_in, int dtype_out, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc) {
+  (void)dtype_in; (void)dtype_out; (void)ldc;
+  // short K (the layer-0 projection, K = 32) is bound by writing C: the 2-CTA/SM engine hides that better (measured)
+  return M >= BM && N >= BN && N % 64 == 0 && K >= 256 && (lda % 8 == 0) && (ldb % 8 == 0) &&
+         (double)M * N * K >= 1e9;
+}
+
+int32_t run(int dtype_in, int dtype_out, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
+            void* C, int64_t ldc, const float* bias, float alpha, int accumulate, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  if (!make_map(&tmA, A, M, K, lda, dtype_in, BM) || !make_map(&tmB, B, N, K, ldb, dtype_in, BN)) {
+    asr::set_error("gemm_tc2: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%lld ldb=%lld)", M, N, K, (long long)lda,
+                   (long long)ldb);
+    return ASR_ERR_CUDA;
+  }
+  static bool attr_set = false;
+  static int num_sms = 148;
+  if (!attr_set) {
+    ASR_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  Params p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha;
+  p.dtype_out = dtype_out; p.accumulate = accumulate; p.ab_fmt = dtype_in;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + BN - 1) / BN;
+  p.nkb_total = (K + BK - 1) / BK;
+  const int tiles = p.tiles_m * p.tiles_n;
+  int split = 1;
+  if (dtype_out == 0 && tiles < num_sms && p.nkb_total >= 64) {      // short M*N, long K: fill the SMs with k-slices
+    split = (2 * num_sms + tiles - 1) / tiles;
+    if (split > p.nkb_total / 16) split = p.nkb_total / 16;
+    if (split < 1) split = 1;
+  }
+  p.kb_per_split = (p.nkb_total + split - 1) / split;
+  p.split = (p.nkb_total + p.kb_per_split - 1) / p.kb_per_split;
+  if (p.split > 1 && !accumulate) {
+    if (ldc == N) {
+      ASR_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st));
+    } else {
+      ASR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, st));
+    }
+  }
+  const int items = tiles * p.split;
+  const int grid = items < num_sms ? items : num_sms;
+  gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+}  // namespace gemm_tc2

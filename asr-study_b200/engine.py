@@ -705,8 +705,9 @@ class AcousticEngine:
                 for i, d in enumerate("fb"):
                     # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
                     xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
-                    lib.asr_gemm_tn(BF16, OUT_F32, D, 4 * H, R, ptr(xTd), R, ptr(dzT[i * 4 * H:]), R,
-                                    ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, sst)
+                    bg = 1 if (side is not main and l > 0) else 0      # ASR_GEMM_BACKGROUND: runs beside the next BPTT
+                    lib.asr_gemm_tn_ex(BF16, OUT_F32, D, 4 * H, R, ptr(xTd), R, ptr(dzT[i * 4 * H:]), R,
+                                       ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, bg, sst)
                     # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
                     if T > 1:
                         Kk = (T - 1) * N
@@ -716,8 +717,8 @@ class AcousticEngine:
                             Ap, Bp = hA, dzB[:, N:]
                         else:        # reverse direction: h_{t+1} with dz_t
                             Ap, Bp = hA[:, N:], dzB
-                        lib.asr_gemm_tn(BF16, OUT_F32, H, 4 * H, Kk, C.c_void_p(Ap.data_ptr()), R,
-                                        C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, sst)
+                        lib.asr_gemm_tn_ex(BF16, OUT_F32, H, 4 * H, Kk, C.c_void_p(Ap.data_ptr()), R,
+                                           C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, bg, sst)
                     else:
                         P.g(f"l{l}.U{d}").zero_()
             if l > 0 and masks is None:

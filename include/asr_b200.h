@@ -108,6 +108,14 @@ int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N,
                     int32_t K, const void* A, int64_t lda, const void* B,
                     int64_t ldb, void* C, int64_t ldc, const float* bias,
                     float alpha, int32_t accumulate, void* stream);
+/* same, with scheduling hints.  ASR_GEMM_BACKGROUND: the GEMM runs on a side stream beside a persistent
+ * recurrence (e.g. dW/dU of layer l during the BPTT of layer l-1) and only gets the SMs that kernel leaves
+ * idle; the non-persistent tiling is used so its CTAs are scheduled one by one as SMs free up. */
+#define ASR_GEMM_BACKGROUND 1
+int32_t asr_gemm_tn_ex(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N,
+                       int32_t K, const void* A, int64_t lda, const void* B,
+                       int64_t ldb, void* C, int64_t ldc, const float* bias,
+                       float alpha, int32_t accumulate, int32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K3/K4  persistent BiLSTM recurrence (both directions in one launch)

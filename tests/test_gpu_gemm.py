@@ -9,7 +9,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(128, 128, 64), (31968, 4096, 32), (4000, 2048, 1024), (26, 2048, 31968), (512, 2048, 4000),
-          (1000, 28, 1024), (777, 1024, 32), (130, 72, 200)]
+          (1000, 28, 1024), (777, 1024, 32), (130, 72, 200),
+          # the C2 projections on the persistent 128x256 engine (gemm_tc2.cu): dW / dU (split-K), dX, ragged M and N
+          (1024, 2048, 8000), (512, 2048, 7984), (7992, 1024, 4096), (300, 320, 12000)]
 
 
 def _gemm(din, dout, A, B, bias=None, alpha=1.0, acc=None, M=None, N=None, K=None, lda=None, ldb=None):
@@ -25,12 +27,12 @@ def _gemm(din, dout, A, B, bias=None, alpha=1.0, acc=None, M=None, N=None, K=Non
     return Cm
 
 
-@pytest.mark.parametrize("engine", ["default", "mma"])
+@pytest.mark.parametrize("engine", ["default", "tc1", "mma"])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 @pytest.mark.parametrize("din", [0, 1])
 def test_gemm_matches_fp32_matmul(engine, M, N, K, din):
-    if engine == "mma":
-        os.environ["ASR_B200_GEMM"] = "mma"
+    if engine != "default":
+        os.environ["ASR_B200_GEMM"] = engine
     try:
         g = torch.Generator(device="cuda").manual_seed(M + N + K)
         dt = torch.float16 if din == 0 else torch.bfloat16
