@@ -44,7 +44,8 @@ constexpr int NM = 16;                                    // MMA N (M = 128 need
 constexpr int THREADS = 128;
 constexpr int STATUS_IDX = 64;
 constexpr int HEADER_BYTES = 8192;
-constexpr int NACC = 4;                                   // independent TMEM accumulators (breaks the MMA dependency chain)
+constexpr int NACC = 4;                                   // TMEM accumulators: one per warp (its K quarter), summed in the epilogue
+static_assert(NACC == THREADS / 32, "one accumulator per warp");
 constexpr uint32_t D_COL = 0, A_COL = 64;
 constexpr long long WATCHDOG_CYCLES = 2000000000LL;
 
@@ -73,8 +74,8 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   constexpr int KC = H / 64;
   constexpr int B_CHUNK = NM * 128;
   constexpr int WORDS = NB * H / 2;                      // LL words per (dir, group, parity)
-  constexpr int WPT = WORDS / THREADS;
   constexpr int NPT = NB / 4;
+  static_assert(H % 64 == 0, "K chunks of 64; each warp owns H / 4 K columns = H / 64 MMAs");
   const int T = a.T, N = a.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
@@ -87,7 +88,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __shared__ int s_dead;
 
   if (tid == 0) {
-    tc::mbar_init(mma_bar, 1);
+    tc::mbar_init(mma_bar, 4);   // one tcgen05.commit per warp
     tc::fence_mbar_init();
     s_dead = 0;
   }
@@ -215,12 +216,22 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       // the first probe usually hits (a probe that races the store costs a second full L2 round trip)
       if (p_t >= 0) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);
       if (delay1 > 0) __nanosleep(delay1);
-      const uint4* src = reinterpret_cast<const uint4*>(xb + (size_t)((s - 1) & 1) * WORDS) + tid;
+      // warp w polls (and stages) the K range [H/4 * w, H/4 * (w + 1)) of all NB samples: V4W 16-byte accesses
+      // (2 LL words = 4 K columns each) per sample, consecutive lanes on consecutive addresses
+      const uint4* src = reinterpret_cast<const uint4*>(xb + (size_t)((s - 1) & 1) * WORDS);
       const uint32_t tag = (uint32_t)s;
-      constexpr int QPT = WPT / 2;                        // 16-byte accesses per thread (2 LL words each)
+      constexpr int V4W = H / 16;                         // 16-byte accesses per (sample, warp K range)
+      constexpr int QPT = NB * V4W / 32;                  // per lane
+      static_assert((NB * V4W) % 32 == 0, "per-warp poll set must fill whole warp accesses");
+      int vidx[QPT];
+#pragma unroll
+      for (int q = 0; q < QPT; ++q) {
+        const int f = q * 32 + lane;
+        vidx[q] = (f / V4W) * (H / 4) + warp * V4W + (f % V4W);
+      }
       uint4 w[QPT];
 #pragma unroll
-      for (int q = 0; q < QPT; ++q) w[q] = ld_volatile_v4(src + q * THREADS);
+      for (int q = 0; q < QPT; ++q) w[q] = ld_volatile_v4(src + vidx[q]);
       bool ok;
       long long t0 = 0;
       do {
@@ -228,7 +239,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 #pragma unroll
         for (int q = 0; q < QPT; ++q)
           if (w[q].y != tag || w[q].w != tag) {
-            w[q] = ld_volatile_v4(src + q * THREADS);
+            w[q] = ld_volatile_v4(src + vidx[q]);
             ok = false;
           }
         if (!ok) {
@@ -243,31 +254,27 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       PROF(0);
 #pragma unroll
       for (int q = 0; q < QPT; ++q) {
-        const int i = 2 * (tid + q * THREADS);             // first of the two LL words (consecutive K pairs)
-        const int n = i / (H / 2), k = 2 * (i % (H / 2));  // k % 4 == 0: both pairs sit in one 8-byte smem slot
+        const int f = q * 32 + lane;
+        const int n = f / V4W, k = 4 * (warp * V4W + (f % V4W));   // both fp16 pairs sit in one 8-byte smem slot
         *reinterpret_cast<uint2*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = make_uint2(w[q].x, w[q].z);
       }
+      // Each warp staged exactly the K range [KW * warp, KW * (warp + 1)) of the B operand (its lanes polled those LL
+      // words), so it issues the MMAs of that range itself, into its own TMEM accumulator, as soon as ITS words
+      // have landed: no block-wide barrier between "data arrived" and "MMA issued", and the MMAs of the early
+      // warps run under the polling of the late ones.  The four commits complete mma_bar (count 4).
       tc::fence_proxy_async_smem();
-      __syncthreads();
+      __syncwarp();
       PROF(1);
-      if (s_dead) break;
-      if (warp == 0 && tc::elect_one_sync()) {
-        PROF2_START;
+      if (tc::elect_one_sync()) {
         tc::tcgen05_fence_after();
-        PROF2(0);
+        constexpr int KBW = H / 16 / 4;                      // MMAs (K = 16 each) per warp
 #pragma unroll
-        for (int kb = 0; kb < H / 16; ++kb) {
+        for (int j = 0; j < KBW; ++j) {
+          const int kb = warp * KBW + j;
           const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-          tc::umma_ts(tmem + D_COL + (kb % NACC) * NM, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
-#ifdef ASR_LSTM_PROFILE
-          if (kb == 0) PROF2(1);
-          if (kb == 7) PROF2(2);
-          if (kb == 15) PROF2(3);
-          if (kb == H / 16 - 1) PROF2(4);
-#endif
+          tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL + kb * 8, bd, idesc, j > 0);
         }
         tc::umma_commit(mma_bar);
-        PROF2(5);
       }
       PROF(2);
       if (!tc::mbar_wait(mma_bar, (uint32_t)((s - 1) & 1), WATCHDOG_CYCLES)) {
@@ -377,7 +384,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __shared__ int s_dead;
 
   if (tid == 0) {
-    tc::mbar_init(mma_bar, 1);
+    tc::mbar_init(mma_bar, 4);   // one tcgen05.commit per warp
     tc::fence_mbar_init();
     s_dead = 0;
   }
@@ -527,16 +534,18 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
           *reinterpret_cast<uint2*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = make_uint2(w[q].x, w[q].z);
         }
       }
+      // per-warp MMA issue (see the forward kernel): thread tid staged K columns [4 tid, 4 tid + 4) of every sample,
+      // so warp w owns K range [128 w, 128 (w + 1)) = MMAs 8w .. 8w + 7 and TMEM accumulator w
       tc::fence_proxy_async_smem();
-      __syncthreads();
+      __syncwarp();
       PROF(1);
-      if (s_dead) break;
-      if (warp == 0 && tc::elect_one_sync()) {
+      if (tc::elect_one_sync()) {
         tc::tcgen05_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 32; ++kb) {
+        for (int j = 0; j < 8; ++j) {
+          const int kb = warp * 8 + j;
           const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-          tc::umma_ts(tmem + D_COL + (kb % NACC) * NM, tmem + A_COL + kb * 8, bd, idesc, kb >= NACC);
+          tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL + kb * 8, bd, idesc, j > 0);
         }
         tc::umma_commit(mma_bar);
       }
