@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace lstmtc2 {
 
@@ -659,6 +660,275 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward through time (v3): ONE exchange per step.  H = 512, 16 CTAs per (direction, batch group).
+//   CTA j owns the 32 hidden units [32j, 32j + 32) for the element-wise BPTT step, i.e. the 128 gate columns
+//   {g*H + 32j + i}, and keeps the [512 units x 128 own gate columns] slice of U (bf16) in TMEM as four
+//   M = 128 blocks.  Its own dz_t is the B operand — written to shared memory locally, no gather — and
+//       P_j[u][n] = sum_{k in own columns} U[u][k] * dz_t[n][k]            (4 blocks x 8 TS-mode tcgen05.mma)
+//   is its partial contribution to dh_rec of ALL 512 units.  Warp w of CTA j holds, for block b, the rows of the
+//   units owned by CTA 4b + w and sends them there (reduce-scatter through the LL ring); every CTA sums the 16
+//   partials that arrive for its own units.  The 4 x 4 kernel above needs two dependent exchanges per step
+//   (gather dz of a column block, then reduce partials along a row: ~2.0 k + ~1.1 k cycles of 4.5 k); this one
+//   needs one, with the same wire bytes per CTA as the forward all-gather (partials travel as bf16 pairs — the
+//   operands of the product are bf16 already, see DESIGN.md for the error budget).
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(THREADS, 1)
+bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int H = 512, K4 = 4 * H, NCTA = H / UPC;
+  constexpr int B_CHUNK = NM * 128;                      // one 64-wide K chunk of the B operand
+  constexpr int NPT = NB / 4;                            // samples per thread
+  constexpr int PPT = NPT / 2;                           // sample pairs per thread
+  constexpr int NP = NB / 2;                             // sample pairs per group
+  constexpr int SLOT = NP * NCTA * 32;                   // LL words per (parity, destination): [pair][source][unit]
+  const int T = a.T, N = a.N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
+  const int u0 = cta * UPC, n0 = grp * NB;
+
+  uint8_t* sB = smem;                                    // 2 chunks of [NM rows x 128 B]: K = 128 own gate columns
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sB + 2 * B_CHUNK);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  __shared__ int s_dead;
+
+  if (tid == 0) {
+    tc::mbar_init(mma_bar, 4);
+    tc::fence_mbar_init();
+    s_dead = 0;
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < 2 * B_CHUNK / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  if (*tmem_slot != 0u) { if (tid == 0) atomicExch(flags + STATUS_IDX, 2); }
+  constexpr uint32_t tmem = 0u;
+
+  // one-time: U slice -> TMEM.  block b, lane m <-> unit 128b + m; K index k = g*32 + i <-> gate column g*H + u0 + i
+  {
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+      const __nv_bfloat16* Ub = reinterpret_cast<const __nv_bfloat16*>(a.U16) + (size_t)dir * H * K4 +
+                                (size_t)(128 * b + tid) * K4 + u0;
+#pragma unroll 1
+      for (int hs = 0; hs < 2; ++hs) {                   // two gates (64 K elements = 32 columns) per tcgen05.st
+        uint32_t rr[32];
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          const uint4* src = reinterpret_cast<const uint4*>(Ub + (2 * hs + gg) * H);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v = __ldg(src + q);
+            rr[gg * 16 + 4 * q] = v.x; rr[gg * 16 + 4 * q + 1] = v.y; rr[gg * 16 + 4 * q + 2] = v.z; rr[gg * 16 + 4 * q + 3] = v.w;
+          }
+        }
+        tc::tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + A_COL + b * 64 + hs * 32, rr);
+      }
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+
+  const uint32_t idesc = tc::umma_idesc_f16(128, NM, 1);
+  const uint32_t sB_addr = tc::smem_u32(sB);
+  const int u = u0 + lane;
+  float dc_carry[NPT], mu[NPT], md0[NPT], md1[NPT], db[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) {
+    dc_carry[i] = 0.0f;
+    mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;
+    md0[i] = a.mask_dh ? a.mask_dh[((size_t)0 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
+    md1[i] = a.mask_dh ? a.mask_dh[((size_t)1 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
+  }
+
+  int* status = flags + STATUS_IDX;
+  uint2* xb = xbuf + (size_t)(dir * G + grp) * 2 * NCTA * SLOT;     // [(dir,grp)][parity][dst][pair][src][unit]
+  __nv_bfloat16* dz16 = reinterpret_cast<__nv_bfloat16*>(a.dz16);
+  const size_t R = (size_t)T * N;
+
+  auto side_stores = [&](int t, const float (&dz)[NPT][4]) {
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        dz16[(row * 2 + dir) * K4 + g * H + u] = __float2bfloat16_rn(dz[i][g]);
+        if (a.dz32) a.dz32[(row * 2 + dir) * K4 + g * H + u] = dz[i][g];
+      }
+    }
+    if (a.dzT16) {
+      static_assert(NPT == 4 || NPT == 2, "packed transposed store: 2 or 4 samples per thread");
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        __nv_bfloat16* dstT = reinterpret_cast<__nv_bfloat16*>(a.dzT16) + (size_t)(dir * K4 + g * H + u) * R + (size_t)t * N + n0 + warp * NPT;
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]);
+        if constexpr (NPT == 4) {
+          const __nv_bfloat162 p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(dstT) = pk;
+        } else {
+          *reinterpret_cast<__nv_bfloat162*>(dstT) = p0;
+        }
+      }
+    }
+  };
+  float p_dz[NPT][4];
+  int p_t = -1;
+
+  PROF_DECL;
+  for (int s = 0; s < T; ++s) {
+    PROF(7);
+    const int t = dir ? s : (T - 1 - s);
+    const int t_fprev = dir ? (t + 1) : (t - 1);
+    const bool has_fprev = dir ? (t + 1 < T) : (t > 0);
+    float dho[NPT], dho2[NPT], gi[NPT], gf[NPT], gg[NPT], go[NPT], cc[NPT], cp[NPT];
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
+      dho[i] = __ldg(a.dh + row * 2 * H + dir * H + u);
+      dho2[i] = a.dh2 ? __ldg(a.dh2 + row * 2 * H + dir * H + u) : 0.0f;
+      const float* gp = a.gates + (row * 2 + dir) * 4 * H;
+      gi[i] = __ldg(gp + u); gf[i] = __ldg(gp + H + u); gg[i] = __ldg(gp + 2 * H + u); go[i] = __ldg(gp + 3 * H + u);
+      cc[i] = __ldg(a.cell + (row * 2 + dir) * H + u);
+      cp[i] = has_fprev ? __ldg(a.cell + ((((size_t)t_fprev * N + n0 + warp * NPT + i) * 2 + dir) * H + u)) : 0.0f;
+    }
+    float dh_rec[NPT];
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
+    if (s > 0) {
+      // ---- receive: 16 partials (bf16 pairs of two samples) for each of my (unit, sample pair) ----------------
+      if (p_t >= 0) side_stores(p_t, p_dz);                // first: gives the peers' LL words time to land in L2
+      const uint32_t tag = (uint32_t)s;
+      const uint2* src = xb + ((size_t)((s - 1) & 1) * NCTA + cta) * SLOT + (size_t)(warp * PPT) * NCTA * 32 + lane;
+      uint2 w[PPT * NCTA];
+#pragma unroll
+      for (int q = 0; q < PPT * NCTA; ++q) w[q] = ld_volatile_v2(src + q * 32);
+      bool ok;
+      long long t0 = 0;
+      do {
+        ok = true;
+#pragma unroll
+        for (int q = 0; q < PPT * NCTA; ++q)
+          if (w[q].y != tag) {
+            w[q] = ld_volatile_v2(src + q * 32);
+            ok = false;
+          }
+        if (!ok) {
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > WATCHDOG_CYCLES) {
+            atomicExch(status, 1);
+            s_dead = 1;
+            break;
+          }
+        }
+      } while (!ok);
+#pragma unroll
+      for (int pp = 0; pp < PPT; ++pp) {
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NCTA; ++j) {
+          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[pp * NCTA + j].x);
+          s0 += __low2float(v);
+          s1 += __high2float(v);
+        }
+        dh_rec[2 * pp] = mu[2 * pp] * s0;
+        dh_rec[2 * pp + 1] = mu[2 * pp + 1] * s1;
+      }
+      PROF(0);
+    }
+    // ---- element-wise BPTT -> dz; my dz is the B operand of my own product ------------------------------------
+    float dz[NPT][4];
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const float dh = fmaf(dho2[i], md1[i], fmaf(dho[i], md0[i], dh_rec[i]));
+      const float tch = asr::tanh_fast(cc[i]);
+      const float d_o = dh * tch * asr::hard_sigmoid_grad(go[i]);
+      const float dc = dc_carry[i] + dh * go[i] * (1.0f - tch * tch);
+      dz[i][0] = dc * gg[i] * asr::hard_sigmoid_grad(gi[i]);
+      dz[i][1] = dc * cp[i] * asr::hard_sigmoid_grad(gf[i]);
+      dz[i][2] = dc * gi[i] * (1.0f - gg[i] * gg[i]);
+      dz[i][3] = d_o;
+      dc_carry[i] = dc * gf[i];
+      const int n = warp * NPT + i;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int k = g * 32 + lane;                       // K index inside my 128 gate columns
+        *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = __float2bfloat16_rn(dz[i][g]);
+      }
+    }
+    PROF(1);
+    if (s + 1 < T) {
+      tc::fence_proxy_async_smem();
+      __syncthreads();                                     // the whole B operand (all samples) is staged
+      if (s_dead) break;
+      if (tc::elect_one_sync()) {                          // warp w issues M block w (units 128w .. 128w + 127)
+        tc::tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
+          tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL + warp * 64 + kb * 8, bd, idesc, kb > 0);
+        }
+        tc::umma_commit(mma_bar);
+      }
+      if (!tc::mbar_wait(mma_bar, (uint32_t)(s & 1), WATCHDOG_CYCLES)) {
+        atomicExch(status, 1);
+        s_dead = 1;
+      }
+      tc::tcgen05_fence_after();
+      PROF(2);
+      // ---- send: my warp's rows of block b belong to CTA 4b + warp ----------------------------------------------
+      {
+        uint32_t r0[NB], r1[NB], r2[NB], r3[NB];
+        const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
+        tc::tmem_ldn(tq, r0);
+        tc::tmem_ldn(tq + NM, r1);
+        tc::tmem_ldn(tq + 2 * NM, r2);
+        tc::tmem_ldn(tq + 3 * NM, r3);
+        tc::tmem_ld_wait();
+        const uint32_t tg = (uint32_t)(s + 1);
+        uint2* out = xb + (size_t)(s & 1) * NCTA * SLOT + (size_t)cta * 32 + lane;      // + dst*SLOT + pair*NCTA*32
+#pragma unroll
+        for (int np = 0; np < NP; ++np) {
+          const __nv_bfloat162 q0 = __floats2bfloat162_rn(__uint_as_float(r0[2 * np]), __uint_as_float(r0[2 * np + 1]));
+          const __nv_bfloat162 q1 = __floats2bfloat162_rn(__uint_as_float(r1[2 * np]), __uint_as_float(r1[2 * np + 1]));
+          const __nv_bfloat162 q2 = __floats2bfloat162_rn(__uint_as_float(r2[2 * np]), __uint_as_float(r2[2 * np + 1]));
+          const __nv_bfloat162 q3 = __floats2bfloat162_rn(__uint_as_float(r3[2 * np]), __uint_as_float(r3[2 * np + 1]));
+          st_volatile_v2(out + (size_t)(0 * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q0), tg));
+          st_volatile_v2(out + (size_t)(1 * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q1), tg));
+          st_volatile_v2(out + (size_t)(2 * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q2), tg));
+          st_volatile_v2(out + (size_t)(3 * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q3), tg));
+        }
+      }
+      tc::tcgen05_fence_before();
+      PROF(3);
+    }
+    // stash the side outputs (dz for the dW/dU/dX GEMMs); written while the next poll is in flight
+#pragma unroll
+    for (int i = 0; i < NPT; ++i)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        db[g] += dz[i][g];
+        p_dz[i][g] = dz[i][g];
+      }
+    p_t = t;
+    PROF(6);
+  }
+  if (p_t >= 0 && !s_dead) side_stores(p_t, p_dz);
+  PROF_DUMP(8);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 // ---- host ---------------------------------------------------------------------------------------
 // samples per CTA group: 8 when that still fits one cooperative wave (more SMs, half the exchange per CTA), else 16
 static int group_size(int N, int H) {
@@ -728,8 +998,29 @@ static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
   return ASR_OK;
 }
 
+template <int NB>
+static int32_t launch_bwd3(const asr_lstm_bwd_args* a, cudaStream_t st) {
+  const int G = a->N / NB;
+  const size_t smem = exclusive_smem(1024 + (size_t)2 * NM * 128 + 64);
+  const size_t xbytes = (size_t)2 * G * 2 * 16 * (NB / 2) * 16 * 32 * sizeof(uint2);
+  ASR_CUDA(cudaFuncSetAttribute(bwd3_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + xbytes, st));
+  ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));
+  asr_lstm_bwd_args args = *a;
+  int* flags = a->flags;
+  uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
+  void* kargs[] = {&args, &flags, &xbuf};
+  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd3_kernel<NB>, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
+  asr::count_launch();
+  return ASR_OK;
+}
+
+// ASR_LSTM_BWD=v2 pins the two-exchange 4 x 4 kernel (fp32 partials; the cross-check of the single-exchange one)
 int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
-  return group_size(a->N, a->H) == 8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
+  const char* e = getenv("ASR_LSTM_BWD");
+  const bool g8 = group_size(a->N, a->H) == 8;
+  if (e && strcmp(e, "v2") == 0) return g8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
+  return g8 ? launch_bwd3<8>(a, st) : launch_bwd3<16>(a, st);
 }
 
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st) {

@@ -255,7 +255,7 @@ def run_ours(args):
         # dominant kernel = the backward recurrence (largest share of the step, profiles/ncu_summary_*.md)
         ms_bwd = kern.get("lstm_bwd_ms", 0.0) / L
         ms_fwd = kern.get("lstm_fwd_ms", 0.0) / L
-        roof = {"bound": "tensor", "kernel": "lstmtc2::bwd_kernel (persistent BiLSTM BPTT, one launch per layer)",
+        roof = {"bound": "tensor", "kernel": "lstmtc2::bwd3_kernel (persistent BiLSTM BPTT, one launch per layer)",
                 "achieved": gf / ms_bwd if ms_bwd else None, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                 "frac": (gf / ms_bwd / pk["tf_burst"]) if ms_bwd else None,
                 "peak_source": pk["src"] + " bf16_tflops (burst; kernel timed alone with CUDA events)",
