@@ -57,6 +57,9 @@ class DatasetIterator(object):
 
     def _make_in(self, inputs):
         p = self.input_parser
+        if p is not None and any(isinstance(i, str) for i in inputs):      # file paths (audio.py:55-59)
+            from ..preprocessing.audio import load_audio
+            inputs = [load_audio(i, p.fs) if isinstance(i, str) else i for i in inputs]
         if p is not None and hasattr(p, "batch") and str(p) != "raw":
             import torch
             clips = [np.ascontiguousarray(np.asarray(c, dtype=np.float32).reshape(-1)) for c in inputs]

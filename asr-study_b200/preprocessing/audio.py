@@ -7,9 +7,10 @@ resolves here unchanged.  ``obj(audio)`` takes a 1-D ndarray/list and returns a
 fresh host ndarray [T, num_feats]; ``obj.batch(...)`` is the batched device entry
 the training loop uses (one kernel launch for the whole batch).
 
-File paths (librosa load + resample, audio.py:55-59) are out of scope: passing a
-string raises TypeError (the reference builds that TypeError without raising it,
-audio.py:63, and then fails on an unbound name).
+File paths (audio.py:55-59: librosa.load at its default 22 050 Hz, then librosa.resample
+to ``fs``) are served by ``load_audio`` below with scipy (RIFF/WAV only, polyphase resampling
+straight to ``fs``): librosa is not installable here, so samples differ from the reference's
+two-stage resampling at the filter-ripple level; ndarray / list inputs (the hot path) are exact.
 """
 from __future__ import annotations
 
@@ -20,6 +21,26 @@ import numpy as np
 from .._lib import AsrError, MfccConfig, cur_stream, lib, ptr
 
 _KIND = {"mfcc": 0, "logfbank": 1, "fbank": 2}
+
+
+def load_audio(path, fs):
+    """WAV file -> mono float32 in [-1, 1] at ``fs`` Hz (stands in for librosa.load + librosa.resample, audio.py:57-58)."""
+    from fractions import Fraction
+
+    import scipy.io.wavfile
+    import scipy.signal
+    sr, x = scipy.io.wavfile.read(path)
+    if x.dtype.kind == "i":
+        x = x.astype(np.float32) / float(np.iinfo(x.dtype).max + 1)
+    elif x.dtype.kind == "u":
+        x = (x.astype(np.float32) - 128.0) / 128.0
+    x = x.astype(np.float32)
+    if x.ndim > 1:
+        x = x.mean(axis=1)                      # librosa.load(mono=True)
+    if int(sr) != int(fs):
+        fr = Fraction(int(fs), int(sr)).limit_denominator(1000)
+        x = scipy.signal.resample_poly(x, fr.numerator, fr.denominator).astype(np.float32)
+    return x
 
 
 class Feature(object):
@@ -57,7 +78,7 @@ class Feature(object):
     # -- reference surface ----------------------------------------------------
     def __call__(self, audio):
         if isinstance(audio, str):
-            raise TypeError("audio type is not support (file loading/resampling is librosa's job)")
+            audio = load_audio(audio, self.fs)
         if type(audio) not in (np.ndarray, list) or len(audio) <= 1:
             raise TypeError("audio type is not support")
         pcm = np.ascontiguousarray(np.asarray(audio, dtype=np.float32).reshape(-1))

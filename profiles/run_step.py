@@ -1,4 +1,4 @@
-"""Two C2 training steps (MFCC -> 3xBiLSTM-512 -> CTC -> BPTT -> Adam) for ncu captures; no timing."""
+"""A few C2 training steps (MFCC -> 3xBiLSTM-512 -> CTC -> BPTT -> Adam, dropout 0.2) for ncu captures; no timing."""
 import os
 import sys
 
@@ -17,7 +17,7 @@ pcm = torch.from_numpy(pcm_np.reshape(-1)).to(dev)
 off = (torch.arange(33, dtype=torch.int64) * pcm_np.shape[1]).to(dev)
 flat, loff, mx = pack_labels(labels, dev)
 feat = audio.MFCC(num_cep=13, d=True, dd=False)
-eng = AcousticEngine(ModelSpec(26, 512, 3, 28, weight_decay=1e-4), device=dev)
+eng = AcousticEngine(ModelSpec(26, 512, 3, 28, weight_decay=1e-4, dropout=0.2), device=dev)
 for _ in range(steps):
     x, lens = feat.batch(pcm, off, t_max=999, time_major=True)
     loss = eng.train_step(x, lens, flat, loff, mx, lr=1e-3, clipnorm=400.0)

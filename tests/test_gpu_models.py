@@ -116,3 +116,46 @@ def test_train_and_eval_cli(tmp_path):
                        "dummy:num_speakers=2,num_utterances_per_speaker=4,max_duration=0.7,min_duration=0.4,"
                        "max_label_length=5,split=[.5,.25]", "--batch_size", "2", "--greedy"])
     assert len(m) == 4 and np.isfinite(m[1])
+
+
+def test_predict_cli_and_offline_featuriser(tmp_path):
+    """predict.py (reference predict.py:17-93) on a dataset subset and on a WAV file; extras.make_dataset
+    (extras/make_dataset.py:10-54) featurises in bulk with the same numbers as per-utterance calls."""
+    import scipy.io.wavfile
+    sys.path.insert(0, ROOT)
+    import predict as predict_cli
+    import train as train_cli
+    from asr_study_b200.extras import make_dataset
+    from asr_study_b200.preprocessing import audio
+    spec = ("dummy:num_speakers=2,num_utterances_per_speaker=4,max_duration=0.7,min_duration=0.4,max_label_length=5,"
+            "split=[.5,.25]")
+    out = str(tmp_path / "run")
+    train_cli.main(["--dataset", spec, "--input_parser", "mfcc", "--input_parser_params", "num_cep", "13", "dd", "False",
+                    "--model", "graves2006", "--model_params", "num_features", "26", "num_hiddens", "100",
+                    "--batch_size", "2", "--num_epochs", "1", "--save", out])
+    ckpt = os.path.join(out, "model.pkl")
+    res = predict_cli.main(["--model", ckpt, "--dataset", spec, "--subset", "test", "--save", str(tmp_path / "p.json")])
+    assert len(res) == 2 and all(isinstance(r["best"], str) for r in res) and os.path.exists(str(tmp_path / "p.json"))
+    rng = np.random.RandomState(0)
+    pcm = (0.1 * rng.randn(8000)).astype(np.float32)
+    wav = str(tmp_path / "clip.wav")
+    scipy.io.wavfile.write(wav, 16000, (pcm * 32767).astype(np.int16))
+    r1 = predict_cli.main(["--model", ckpt, "--file", wav])
+    assert len(r1) == 1 and isinstance(r1[0]["best"], str)
+    r2 = predict_cli.main(["--model", ckpt, "--file", wav, "--no_decoder", "--save", str(tmp_path / "post.npz")])
+    assert r2[0]["best"].shape[1] == 28
+    feat = audio.MFCC(num_cep=13, d=True, dd=False)
+    assert np.abs(feat(wav) - feat(audio.load_audio(wav, 16000))).max() == 0.0
+    # 8 kHz file is resampled to fs
+    scipy.io.wavfile.write(wav, 8000, (pcm[::2] * 32767).astype(np.int16))
+    assert abs(len(audio.load_audio(wav, 16000)) - 8000) <= 2
+    fn = make_dataset.main(["--parser", "dummy", "--parser_params", "num_speakers", "2", "num_utterances_per_speaker", "3",
+                            "max_duration", "0.6", "min_duration", "0.3", "split", "[.5,.25]", "--input_parser", "mfcc",
+                            "--input_parser_params", "num_cep", "13", "dd", "False", "--label_parser", "simple_char_parser",
+                            "--output_file", str(tmp_path / "d.npz")])
+    z = np.load(fn, allow_pickle=True)
+    assert int(z["num_feats"]) == 26 and len(z["train/inputs"]) == 3
+    from asr_study_b200.datasets.dummy import Dummy
+    dl = Dummy(num_speakers=2, num_utterances_per_speaker=3, max_duration=0.6, min_duration=0.3, split=[.5, .25]).to_dict_list()
+    first = [i for i, d in enumerate(dl["dataset"]) if d == "train"][0]
+    assert np.abs(z["train/inputs"][0] - feat(dl["input"][first])).max() < 1e-5
