@@ -75,6 +75,7 @@ SIGNATURES = {
     "asr_gemm_tn_ex": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I32, _P]),
     "asr_lstm_flags_bytes": (_SZ, []),
     "asr_lstm_fuses_masks": (_I32, [_I32, _I32, _I32]),
+    "asr_lstm_persistent_supported": (_I32, [_I32, _I32, _I32, _I32]),
     "asr_lstm_forward": (_I32, [C.POINTER(LstmFwdArgs), _P]),
     "asr_lstm_backward": (_I32, [C.POINTER(LstmBwdArgs), _P]),
     "asr_lstm_cell_forward": (_I32, [C.POINTER(LstmFwdArgs), C.POINTER(LstmVariant), _P, _P]),
@@ -124,7 +125,8 @@ class _Lib:
             raise AttributeError(name)
         fn = self.raw(name)
         res = SIGNATURES[name][0]
-        if res is not _I32 or name in ("asr_version", "asr_mfcc_num_feats", "asr_mfcc_num_frames", "asr_lstm_fuses_masks"):
+        if res is not _I32 or name in ("asr_version", "asr_mfcc_num_feats", "asr_mfcc_num_frames", "asr_lstm_fuses_masks",
+                                     "asr_lstm_persistent_supported"):
             return fn
 
         def checked(*a):

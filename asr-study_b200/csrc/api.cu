@@ -97,6 +97,17 @@ static int32_t check_common(int T, int N, int H) {
   return ASR_OK;
 }
 
+// 1 when one of the persistent engines (tensor-core or fp32) takes this shape; 0 = only the general-cell engine
+// (asr_lstm_cell_forward / backward: any N, H <= 1024) does, e.g. the 5 x BiLSTM-800 stack of BASELINE config 4
+extern "C" int32_t asr_lstm_persistent_supported(int32_t T, int32_t N, int32_t H, int32_t training) {
+  if (T < 1 || N < 1 || H < 1) return 0;
+  const bool fp32_ok = N <= 32 && 2 * ((H + 7) / 8) <= 148 &&
+                       ((size_t)H * 4 * 8 + (size_t)H * 32 + (size_t)8 * 32 * 4 * 8) * sizeof(float) <= 227 * 1024;
+  if (fp32_ok) return 1;
+  if (env_is("ASR_B200_LSTM", "fp32")) return 0;
+  return lstmtc2::shape_supported(T, N, H, false) && (!training || lstmtc2::shape_supported(T, N, H, true)) ? 1 : 0;
+}
+
 // the fused dropout fields are implemented by the default tensor-core engine (lstm_tc2.cu) only
 extern "C" int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H) {
   if (env_is("ASR_B200_LSTM", "fp32") || env_is("ASR_B200_LSTM", "tc1") || env_is("ASR_B200_LSTM", "tc3")) return 0;

@@ -297,7 +297,9 @@ class AcousticEngine:
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
         assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
-        if sp.general:
+        # the persistent engines cover the reference's shapes; anything else (e.g. H = 800) runs on the general cell
+        self._use_general = sp.general or not lib.asr_lstm_persistent_supported(T, N, sp.num_hiddens, int(training))
+        if self._use_general:
             return self._forward_general(feats_tm, training, masks, zmasks, input_mask)
         H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
         R = T * N
@@ -652,7 +654,7 @@ class AcousticEngine:
     def backward(self, dlogits: torch.Tensor):
         """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad."""
         sp, P, w = self.spec, self.params, self._w
-        if sp.general:
+        if self._use_general:
             return self._backward_general(dlogits)
         T, N = self._T, self._N
         H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes

@@ -169,6 +169,9 @@ typedef struct {
  * fields above (mask_next/hm16/hmT16/hT16u, dh2/mask_dh); 0 = the caller must mask with asr_mask_cast /
  * asr_mask_combine instead. */
 int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H);
+/* 1 when asr_lstm_forward/backward take this shape (a persistent engine exists for it); 0 = use the general-cell
+ * entry points below (any N, H <= 1024), e.g. H = 800 of BASELINE config 4. */
+int32_t asr_lstm_persistent_supported(int32_t T, int32_t N, int32_t H, int32_t training);
 
 size_t  asr_lstm_flags_bytes(void);
 int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream);

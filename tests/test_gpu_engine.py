@@ -189,3 +189,35 @@ def test_brsmv1_switches_train_step_parity(sw):
     p_after = {k: v.astype(np.float64) for k, v in eng.params.export("flat").items()}
     ref_eval, _ = om.forward_general(p_after, x, zoneout=spec.zoneout, residual=spec.residual)
     assert norm_err(logits_eval, ref_eval) < 1e-3
+
+
+def test_config4_stack_blstm800_logfbank40_on_general_cell():
+    """BASELINE config 4 recurrent stack (5 x BiLSTM-800 on 40 log-mel features; the DS2-style conv front end is not
+    in the reference) at a small T/N: no persistent engine takes H = 800, the engine routes to the general cell."""
+    from asr_study_b200._lib import lib
+    from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
+    N, T, F, H, L, C = 16, 12, 40, 800, 5, 28
+    assert lib.asr_lstm_persistent_supported(T, N, H, 1) == 0 and lib.asr_lstm_persistent_supported(999, 32, 512, 1) == 1
+    from oracle import lstm as ol
+    rng = np.random.RandomState(4)
+    params, D = {}, F                        # scaled-normal U instead of the orthogonal init: ten 800 x 3200 SVDs take minutes
+    for l in range(L):
+        for d in "fb":
+            params[f"l{l}.W{d}"] = ol.glorot_uniform(rng, (D, 4 * H))
+            params[f"l{l}.U{d}"] = (rng.randn(H, 4 * H) / np.sqrt(H)).astype(np.float32)
+            params[f"l{l}.b{d}"] = np.concatenate([np.zeros(H), np.ones(H), np.zeros(2 * H)]).astype(np.float32)
+        D = 2 * H
+    params["dense.W"], params["dense.b"] = ol.glorot_uniform(rng, (D, C)), np.zeros(C, np.float32)
+    x = rng.randn(N, T, F).astype(np.float32)
+    lens = np.full(N, T, np.int32)
+    labels = [rng.randint(0, C - 1, size=3).astype(np.int32) for _ in range(N)]
+    eng = AcousticEngine(ModelSpec(F, H, L, C), init_params=params)
+    flat, off, mx = pack_labels(labels, "cuda")
+    loss = eng.train_step(dev(np.ascontiguousarray(x.transpose(1, 0, 2))), dev(lens), flat, off, mx, lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    _, ctc, grads, ref_logits = om.loss_and_grads(params, x, lens, labels, dtype=np.float64)
+    assert norm_err(eng._w["logits"].cpu().numpy().transpose(1, 0, 2), ref_logits) < 1e-3
+    np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
+    got = eng.params.export("grad")
+    for k, g in grads.items():
+        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
