@@ -82,7 +82,8 @@ class CTCModel(object):
         raise ValueError("No such layer: %s" % name)
 
     def set_data_parallel(self, allreduce, world_size):
-        """allreduce(flat_grad_tensor) must SUM in place across ranks (one NCCL all-reduce per step)."""
+        """allreduce(grad_slice) must SUM in place across ranks; it is called on slices that tile the flat gradient
+        bucket exactly once per step, each as soon as it is complete, and may return a handle with .wait()."""
         self.allreduce, self.world_size = allreduce, int(world_size)
 
     # ---- batches ------------------------------------------------------------------

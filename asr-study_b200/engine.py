@@ -651,11 +651,26 @@ class AcousticEngine:
         return out, out_len
 
     # --------------------------------------------------------------- backward
-    def backward(self, dlogits: torch.Tensor):
-        """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad."""
+    def _layer_slice(self, l):
+        """flat-bucket range of layer l's parameters (Wf .. bb are contiguous per layer)."""
+        P, sp = self.params, self.spec
+        lo = P.offsets[f"l{l}.Wf"]
+        hi = P.offsets[f"l{l + 1}.Wf"] if l + 1 < sp.num_layers else P.offsets["dense.W"]
+        return lo, hi
+
+    def backward(self, dlogits: torch.Tensor, allreduce=None):
+        """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad.
+        allreduce (data parallel): called on slices of the flat gradient bucket as soon as they are complete — layer
+        l's slice right behind its dW/dU GEMMs, i.e. while the BPTT of layer l-1 runs — so the collective overlaps the
+        recurrences; the slices tile the bucket exactly once (still ONE logical all-reduce of the bucket per step).
+        Returns the handles (objects with .wait()) the callable returned, if any."""
         sp, P, w = self.spec, self.params, self._w
+        handles = []
         if self._use_general:
-            return self._backward_general(dlogits)
+            self._backward_general(dlogits)
+            if allreduce is not None:
+                handles.append(allreduce(P.grad))
+            return handles
         T, N = self._T, self._N
         H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
         R = T * N
@@ -723,6 +738,9 @@ class AcousticEngine:
                                            C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, bg, sst)
                     else:
                         P.g(f"l{l}.U{d}").zero_()
+                if allreduce is not None and l > 0:     # layer l's gradients are complete on this stream: reduce them now
+                    lo, hi = self._layer_slice(l)
+                    handles.append(allreduce(P.grad[lo:hi]))
             if l > 0 and masks is None:
                 # dX [R, 2H] = dz16 [R, 8H] . Wcat16 [2H, 8H]^T
                 self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w[f"dz16.{l}"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
@@ -744,6 +762,10 @@ class AcousticEngine:
                     dh, other = other, dh
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self._side)
+        if allreduce is not None:                       # layer 0 and the Dense layer: the two ends of the bucket
+            handles.append(allreduce(P.grad[:self._layer_slice(0)[1]]))
+            handles.append(allreduce(P.grad[P.offsets["dense.W"]:]))
+        return handles
 
     # -------------------------------------------------------------- optimiser
     def optimizer_step(self, lr=1e-3, clipnorm=400.0, beta1=0.9, beta2=0.999, eps=1e-8, opt="adam",
@@ -781,9 +803,9 @@ class AcousticEngine:
             logits = self.forward(feats_tm, training=True, masks=masks, zmasks=zmasks, input_mask=input_mask)
             loss, dlogits = self.ctc(logits, in_len, labels_flat, label_off, max_label_len,
                                      grad_scale=1.0 / float(global_batch or N))
-            self.backward(dlogits)
-            if allreduce is not None:
-                allreduce(self.params.grad)
+            for h in self.backward(dlogits, allreduce=allreduce):
+                if h is not None and hasattr(h, "wait"):
+                    h.wait()                            # async collectives: the current stream waits for them
             self.optimizer_step(**opt)
         if main is not caller:
             caller.wait_stream(main)

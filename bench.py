@@ -165,9 +165,9 @@ def run_ours(args):
     loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"k": 0, "last": None}
 
-    def allreduce(g):
+    def allreduce(g):                  # called on per-layer slices of the gradient bucket as they complete (engine.backward)
         if world > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            return dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
 
     # input pipeline: batch k+1's H2D copy + fused MFCC launch run on a side stream while batch k trains
     # (asr_study_b200/datasets/prefetch.py); every step still featurises its own batch inside the timed region

@@ -77,7 +77,8 @@ def main(argv=None):
                       metrics={"decoder": metrics.ler}, loss_weights=[1, 0])
     if world > 1:
         import torch.distributed as dist
-        model.set_data_parallel(lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM), world)
+        # called on per-layer slices of the flat gradient bucket as they complete (overlaps the BPTT recurrences)
+        model.set_data_parallel(lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True), world)
 
     output_dir = args.save or os.path.join("results", "%s_%s" % (args.model, datetime.datetime.now()))
     os.makedirs(output_dir, exist_ok=True)
