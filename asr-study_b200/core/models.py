@@ -230,9 +230,11 @@ def ctc_model(inputs, output, **kwargs):
     """core/models.py:31-52.  ``inputs`` = num_features, ``output`` = list of LSTM layer records followed by
     the number of classes: ``ctc_model(26, [LSTM(100), 28])`` is graves2006."""
     *layers, num_classes = output
-    hs = {l.output_dim for l in layers}
-    if not layers or len(hs) != 1 or not all(isinstance(l, LSTM) for l in layers):
-        raise NotImplementedError("the engine stacks identical-width BiLSTM layers")
+    input_dense = kwargs.pop("input_dense", None)
+    widths = [l.output_dim for l in layers]
+    hs = set(widths)
+    if not layers or not all(isinstance(l, LSTM) for l in layers):
+        raise NotImplementedError("the engine stacks BiLSTM layers")
     wd = kwargs.pop("weight_decay", 0.0)
     dps = {(l.dropout_W, l.dropout_U) for l in layers}
     if len(dps) != 1 or len(set(dps.pop())) != 1:
@@ -241,9 +243,10 @@ def ctc_model(inputs, output, **kwargs):
     if len(sw) != 1:
         raise NotImplementedError("zoneout / layer_norm / mi are tied across layers (core/models.py:260-271)")
     zo, ln, mi = sw.pop()
-    spec = ModelSpec(int(inputs), hs.pop(), len(layers), int(num_classes), float(wd), kwargs.pop("name", "ctc_model"),
+    spec = ModelSpec(int(inputs), widths[0], len(layers), int(num_classes), float(wd), kwargs.pop("name", "ctc_model"),
                      float(layers[0].dropout_W), zoneout=zo, layer_norm=ln, mi=mi, residual=kwargs.pop("residual", None),
-                     input_dropout=bool(kwargs.pop("input_dropout", False)))
+                     input_dropout=bool(kwargs.pop("input_dropout", False)),
+                     layer_hiddens=tuple(widths) if len(hs) > 1 else None, input_dense=input_dense)
     return CTCModel(spec, **kwargs)
 
 
@@ -256,8 +259,14 @@ def graves2006(num_features=26, num_hiddens=100, num_classes=28, std=.6, **kw):
 
 
 def eyben(num_features=39, num_hiddens=[78, 120, 27], num_classes=28, **kw):
-    """core/models.py:76-103 needs an input Dense and two different LSTM widths: not built."""
-    raise NotImplementedError("eyben: heterogeneous widths + input projection are not on the built path yet")
+    """core/models.py:76-103: TimeDistributed(Dense(n0)) -> Bidirectional(LSTM(n1)) -> Bidirectional(LSTM(n2)) ->
+    TimeDistributed(Dense(C)); a zero entry drops that layer (:90-99).  Heterogeneous widths run on the general-cell
+    engine (any H <= 1024)."""
+    assert len(num_hiddens) == 3
+    layers = [LSTM(n) for n in num_hiddens[1:] if n]
+    if not layers:
+        raise NotImplementedError("eyben without a recurrent layer is a plain Dense stack, outside the BiLSTM hot path")
+    return ctc_model(num_features, layers + [num_classes], name="eyben", input_dense=num_hiddens[0] or None, **kw)
 
 
 def maas(*a, **k):

@@ -45,10 +45,25 @@ class ModelSpec:
     residual: str | None = None      # merge mode; 'sum' is built (core/models.py:253-255, 273-274)
     input_dropout: bool = False      # element-wise Dropout(dropout) on the (projected) input (core/models.py:257-258)
 
+    # heterogeneous stacks (eyben, core/models.py:76-103): per-layer widths and a linear input projection
+    layer_hiddens: tuple | None = None   # overrides num_hiddens / num_layers when set
+    input_dense: int | None = None       # TimeDistributed(Dense(n)) in front of the first BiLSTM (no residual merges)
+
+    @property
+    def hs(self):
+        return tuple(self.layer_hiddens) if self.layer_hiddens else (self.num_hiddens,) * self.num_layers
+
+    @property
+    def proj_width(self):
+        """width of the input projection, or None: 2H for the residual stack (core/models.py:253-255), input_dense else."""
+        if self.residual is not None:
+            return 2 * self.hs[0]
+        return self.input_dense
+
     @property
     def general(self) -> bool:
         return bool(self.zoneout or self.layer_norm is not None or self.mi is not None or self.residual is not None
-                    or self.input_dropout)
+                    or self.input_dropout or self.input_dense or len(set(self.hs)) > 1)
 
 
 class ParamBucket:
@@ -60,13 +75,13 @@ class ParamBucket:
 
     def __init__(self, spec: ModelSpec, device):
         self.spec = spec
-        H, C = spec.num_hiddens, spec.num_classes
+        C = spec.num_classes
         shapes = []
         D = spec.num_features
-        if spec.residual is not None:
-            shapes += [("proj.W", (D, 2 * H)), ("proj.b", (2 * H,))]
-            D = 2 * H
-        for l in range(spec.num_layers):
+        if spec.proj_width:
+            shapes += [("proj.W", (D, spec.proj_width)), ("proj.b", (spec.proj_width,))]
+            D = spec.proj_width
+        for l, H in enumerate(spec.hs):
             shapes += [(f"l{l}.Wf", (D, 4 * H)), (f"l{l}.Wb", (D, 4 * H)),
                        (f"l{l}.Uf", (H, 4 * H)), (f"l{l}.Ub", (H, 4 * H)),
                        (f"l{l}.bf", (4 * H,)), (f"l{l}.bb", (4 * H,))]
@@ -147,15 +162,14 @@ class AcousticEngine:
         once per batch, constant over time, scaled by 1/(1-p) (K.dropout).  Returns {layer: {Wf,Wb,Uf,Ub}} plus the
         packed views W2 [2,N,D] / U2 [2,N,H] the kernels take.  One asr_dropout_mask launch fills all of them."""
         sp, p = self.spec, float(self.spec.dropout)
-        H = sp.num_hiddens
-        D0 = sp.num_features if sp.residual is None else 2 * H
-        widths = [(D0 if l == 0 else 2 * H) for l in range(sp.num_layers)]
-        total = sum(2 * N * (D + H) for D in widths)
+        hs = sp.hs
+        widths = [((sp.proj_width or sp.num_features) if l == 0 else 2 * hs[l - 1]) for l in range(len(hs))]
+        total = sum(2 * N * (D + H) for D, H in zip(widths, hs))
         flat = self._buf("dropout_masks", (total,), torch.float32)
         lib.asr_dropout_mask(ptr(flat), total, p, self._mask_seed, self._mask_offset, cur_stream())
         self._mask_offset += total
         out, o = {}, 0
-        for l, D in enumerate(widths):
+        for l, (D, H) in enumerate(zip(widths, hs)):
             W2 = flat[o:o + 2 * N * D].view(2, N, D); o += 2 * N * D
             U2 = flat[o:o + 2 * N * H].view(2, N, H); o += 2 * N * H
             out[l] = {"Wf": W2[0], "Wb": W2[1], "Uf": U2[0], "Ub": U2[1], "W2": W2, "U2": U2}
@@ -175,7 +189,7 @@ class AcousticEngine:
         """Keras-1.2.2 initialisers for LSTM(consume_less='gpu') and Dense:
         glorot_uniform W, orthogonal(1.1) U, zero b with forget slice = 1."""
         rng = np.random.RandomState(seed)
-        H, out = spec.num_hiddens, {}
+        out = {}
 
         def glorot(shape):
             lim = np.sqrt(6.0 / (shape[0] + shape[1]))
@@ -188,11 +202,11 @@ class AcousticEngine:
             return (1.1 * q.reshape(shape)).astype(np.float32)
 
         D = spec.num_features
-        if spec.residual is not None:
-            out["proj.W"] = glorot((D, 2 * H))
-            out["proj.b"] = np.zeros(2 * H, np.float32)
-            D = 2 * H
-        for l in range(spec.num_layers):
+        if spec.proj_width:
+            out["proj.W"] = glorot((D, spec.proj_width))
+            out["proj.b"] = np.zeros(spec.proj_width, np.float32)
+            D = spec.proj_width
+        for l, H in enumerate(spec.hs):
             for d in ("f", "b"):
                 out[f"l{l}.W{d}"] = glorot((D, 4 * H))
                 out[f"l{l}.U{d}"] = orth((H, 4 * H))
@@ -225,7 +239,7 @@ class AcousticEngine:
 
     def _alloc(self, T, N, training):
         sp = self.spec
-        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        H, L, Cc = sp.hs[0], len(sp.hs), sp.num_classes
         R = T * N
         w = {}
         D0 = _pad8(sp.num_features)
@@ -255,10 +269,10 @@ class AcousticEngine:
     def _prep_weights(self, training):
         """16-bit tensor-core operands derived from the fp32 masters (once per step)."""
         sp, P = self.spec, self.params
-        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        Cc = sp.num_classes
         st = cur_stream()
-        D = sp.num_features if sp.residual is None else 2 * H      # with the residual projection every layer sees 2H
-        for l in range(L):
+        D = sp.proj_width or sp.num_features                        # width the first BiLSTM sees
+        for l, H in enumerate(sp.hs):
             Dp = _pad8(D)
             wt = self._buf(f"WcatT16.{l}", (8 * H, Dp), torch.float16, zero=True)     # [8H, D]  fwd B operand
             for i, d in enumerate("fb"):
@@ -273,17 +287,17 @@ class AcousticEngine:
             if training:
                 ub = self._buf(f"Ub16.{l}", (2, H, 4 * H), torch.bfloat16)             # [2, H, 4H] U, BPTT recurrence
                 lib.asr_cast_rows(ptr(P.p(f"l{l}.Uf")), 4 * H, ptr(ub), 4 * H, 2 * H, 4 * H, BF16, st)
-            if training and (l > 0 or sp.residual is not None):
+            if training and (l > 0 or sp.proj_width):
                 wc = self._buf(f"Wcat16.{l}", (D, 8 * H), torch.bfloat16)              # [D, 8H]  dX B operand
                 for i, d in enumerate("fb"):
                     lib.asr_cast_rows(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wc[:, i * 4 * H:]), 8 * H, D, 4 * H, BF16, st)
             D = 2 * H
-        dp = _pad8(Cc)
-        wd = self._buf("WdT16", (Cc, 2 * H), torch.float16)                            # [C, 2H] logits B operand
-        lib.asr_cast_transpose(ptr(P.p("dense.W")), Cc, ptr(wd), 2 * H, 2 * H, Cc, F16, st)
+        dp, H2 = _pad8(Cc), 2 * sp.hs[-1]
+        wd = self._buf("WdT16", (Cc, _pad8(H2)), torch.float16, zero=True)             # [C, 2H (padded to 8)] logits B operand
+        lib.asr_cast_transpose(ptr(P.p("dense.W")), Cc, ptr(wd), _pad8(H2), H2, Cc, F16, st)
         if training:
-            wdb = self._buf("Wd16", (2 * H, dp), torch.bfloat16, zero=True)            # [2H, Cpad] dTop B operand
-            lib.asr_cast_rows(ptr(P.p("dense.W")), Cc, ptr(wdb), dp, 2 * H, Cc, BF16, st)
+            wdb = self._buf("Wd16", (H2, dp), torch.bfloat16, zero=True)               # [2H, Cpad] dTop B operand
+            lib.asr_cast_rows(ptr(P.p("dense.W")), Cc, ptr(wdb), dp, H2, Cc, BF16, st)
 
     def _gemm(self, din, dout, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, alpha=1.0, acc=0):
         lib.asr_gemm_tn(din, dout, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(Cm), ldc, ptr(bias), float(alpha), acc,
@@ -298,10 +312,10 @@ class AcousticEngine:
         T, N, Fd = feats_tm.shape
         assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
         # the persistent engines cover the reference's shapes; anything else (e.g. H = 800) runs on the general cell
-        self._use_general = sp.general or not lib.asr_lstm_persistent_supported(T, N, sp.num_hiddens, int(training))
+        self._use_general = sp.general or not lib.asr_lstm_persistent_supported(T, N, sp.hs[0], int(training))
         if self._use_general:
             return self._forward_general(feats_tm, training, masks, zmasks, input_mask)
-        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        H, L, Cc = sp.hs[0], len(sp.hs), sp.num_classes
         R = T * N
         w = self._alloc(T, N, training)
         self._w, self._T, self._N = w, T, N
@@ -378,8 +392,8 @@ class AcousticEngine:
         """One keep mask per (layer, direction, time step, unit), shared by the batch: K.dropout(h_diff, level,
         noise_shape=(output_dim,)) inside the step (core/layers_utils.py:34-42).  {layer: {h, c: f32 [2, T, H]}}."""
         sp = self.spec
-        return {l: {k: (torch.rand(2, T, sp.num_hiddens, device=self.device, generator=self._mask_rng) >= sp.zoneout).float()
-                    for k in ("h", "c")} for l in range(sp.num_layers)}
+        return {l: {k: (torch.rand(2, T, H, device=self.device, generator=self._mask_rng) >= sp.zoneout).float()
+                    for k in ("h", "c")} for l, H in enumerate(sp.hs)}
 
     def _variant(self, l, zm):
         sp, P = self.spec, self.params
@@ -434,17 +448,20 @@ class AcousticEngine:
     def _forward_general(self, feats_tm, training, masks, zmasks, input_mask):
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
-        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        hs, Cc = sp.hs, sp.num_classes
+        L, Hmax, PW = len(hs), max(hs), sp.proj_width
         R, st = T * N, cur_stream()
         if sp.residual not in (None, "sum"):
             raise NotImplementedError("residual merge mode %r: only 'sum' keeps the layer width (core/models.py:273-274)" % sp.residual)
+        if sp.residual is not None and len(set(hs)) > 1:
+            raise NotImplementedError("the residual merge needs equal layer widths")
         self._T, self._N = T, N
         if training and masks is None and sp.dropout > 0:
             masks = self.sample_masks(N)
         if training and zmasks is None and sp.zoneout > 0:
             zmasks = self.sample_zoneout_masks(T)
         if training and input_mask is None and sp.input_dropout and sp.dropout > 0:
-            Din = 2 * H if sp.residual is not None else Fd
+            Din = PW or Fd
             input_mask = (torch.rand(R, Din, device=self.device, generator=self._mask_rng) >= sp.dropout).float() / (1.0 - sp.dropout)
         if not training:
             masks = zmasks = input_mask = None
@@ -454,26 +471,26 @@ class AcousticEngine:
         x32 = feats_tm.contiguous().view(R, Fd)
         cur32, Dl = x32, Fd
         self._gen = dict(ops=[], x_ops=None)
-        if sp.residual is not None:
+        if PW:                                     # TimeDistributed(Dense(PW)): residual stack (2H) or eyben's input layer
             split = sp.layer_norm is not None      # everything that feeds a layer-normalised product runs split-precision
             self._gen["x_ops"] = self._operands("x", x32, Fd, None, training, split)[0]
             Fp = _pad8(Fd)
-            wp = self._buf("WpT16", (2 * H, Fp), torch.float16, zero=True)
-            lib.asr_cast_transpose(ptr(P.p("proj.W")), 2 * H, ptr(wp), Fp, Fd, 2 * H, F16, st)
-            cur32 = self._buf("res32.in", (R, 2 * H), torch.float32)
-            self._gemm(F16, OUT_F32, R, 2 * H, Fp, self._gen["x_ops"][0], Fp, wp, Fp, cur32, 2 * H, bias=P.p("proj.b"))
+            wp = self._buf("WpT16", (PW, Fp), torch.float16, zero=True)
+            lib.asr_cast_transpose(ptr(P.p("proj.W")), PW, ptr(wp), Fp, Fd, PW, F16, st)
+            cur32 = self._buf("res32.in", (R, PW), torch.float32)
+            self._gemm(F16, OUT_F32, R, PW, Fp, self._gen["x_ops"][0], Fp, wp, Fp, cur32, PW, bias=P.p("proj.b"))
             if split:
-                wpl = self._buf("WpT16lo", (2 * H, Fp), torch.float16, zero=True)
-                lib.asr_cast_transpose(ptr(P.p("proj.W")), 2 * H, ptr(wpl), Fp, Fd, 2 * H, F16_LO, st)
-                self._gemm(F16, OUT_F32, R, 2 * H, Fp, self._gen["x_ops"][0], Fp, wpl, Fp, cur32, 2 * H, acc=1)
-                self._gemm(F16, OUT_F32, R, 2 * H, Fp, self._gen["x_ops"][2], Fp, wp, Fp, cur32, 2 * H, acc=1)
-            Dl = 2 * H
+                wpl = self._buf("WpT16lo", (PW, Fp), torch.float16, zero=True)
+                lib.asr_cast_transpose(ptr(P.p("proj.W")), PW, ptr(wpl), Fp, Fd, PW, F16_LO, st)
+                self._gemm(F16, OUT_F32, R, PW, Fp, self._gen["x_ops"][0], Fp, wpl, Fp, cur32, PW, acc=1)
+                self._gemm(F16, OUT_F32, R, PW, Fp, self._gen["x_ops"][2], Fp, wp, Fp, cur32, PW, acc=1)
+            Dl = PW
         if input_mask is not None:
-            dst = cur32 if sp.residual is not None else self._buf("x32.masked", (R, Dl), torch.float32)
+            dst = cur32 if PW else self._buf("x32.masked", (R, Dl), torch.float32)
             lib.asr_add_mask(ptr(cur32), None, ptr(input_mask.contiguous()), R, ptr(dst), R, Dl, st)
             cur32 = dst
-        w["zx"] = self._buf("zx", (R, 8 * H), torch.float32)
-        for l in range(L):
+        for l, H in enumerate(hs):
+            w["zx"] = self._buf("zx", (R, 8 * H), torch.float32)
             mk = masks[l] if masks is not None else None
             # layer normalisation divides Wx by its row deviation, which amplifies the fp16 operand rounding of the
             # projection ~16x (measured 4.6e-3 on the logits, CPU emulation 4.56e-3): with LN on, the projection runs
@@ -523,10 +540,12 @@ class AcousticEngine:
             else:
                 cur32 = h32
             Dl = 2 * H
-        top = self._operands("top", cur32, 2 * H, None, training)[0]
+        H2 = 2 * hs[-1]
+        top = self._operands("top", cur32, H2, None, training)[0]
         self._gen["top"] = top
         w["logits"] = self._buf("logits", (T, N, Cc), torch.float32)
-        self._gemm(F16, OUT_F32, R, Cc, 2 * H, top[0], 2 * H, self._ws["WdT16"], 2 * H, w["logits"], Cc, bias=P.p("dense.b"))
+        self._gemm(F16, OUT_F32, R, Cc, _pad8(H2), top[0], _pad8(H2), self._views["WdT16"], _pad8(H2), w["logits"], Cc,
+                   bias=P.p("dense.b"))
         if training:
             w["dlogits"] = self._buf("dlogits", (T, N, Cc), torch.float32)
             w["loss"] = self._buf("loss", (N,), torch.float32)
@@ -535,7 +554,8 @@ class AcousticEngine:
     def _backward_general(self, dlogits):
         sp, P, w = self.spec, self.params, self._w
         T, N = self._T, self._N
-        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        hs, Cc = sp.hs, sp.num_classes
+        L, H2 = len(hs), 2 * hs[-1]
         R, st, cp = T * N, cur_stream(), _pad8(Cc)
         masks, zmasks = self._masks, self._zmasks
         dl16 = self._buf("dl16", (R, cp), torch.bfloat16, zero=True)
@@ -543,15 +563,16 @@ class AcousticEngine:
         lib.asr_cast_rows(ptr(dlogits), Cc, ptr(dl16), cp, R, Cc, BF16, st)
         lib.asr_cast_transpose(ptr(dlogits), Cc, ptr(dlT16), R, R, Cc, BF16, st)
         lib.asr_colsum(ptr(dlogits), Cc, R, Cc, ptr(P.g("dense.b")), st)
-        self._gemm(BF16, OUT_F32, 2 * H, Cc, R, self._gen["top"][1], R, dlT16, R, P.g("dense.W"), Cc)
-        dcur, dname = self._buf("dhA", (R, 2 * H), torch.float32), "dhA"
-        self._gemm(BF16, OUT_F32, R, 2 * H, cp, dl16, cp, self._ws["Wd16"], cp, dcur, 2 * H)
-        dwx = self._buf("dwx32", (R, 8 * H), torch.float32)
-        duh = self._buf("duh32", (R, 8 * H), torch.float32)
-        dwx16 = self._buf("dwx16", (R, 8 * H), torch.bfloat16)
-        dwxT16 = self._buf("dwxT16", (8 * H, R), torch.bfloat16)
-        duhT16 = self._buf("duhT16", (8 * H, R), torch.bfloat16)
+        self._gemm(BF16, OUT_F32, H2, Cc, R, self._gen["top"][1], R, dlT16, R, P.g("dense.W"), Cc)
+        dcur, dname = self._buf("dhA", (R, H2), torch.float32), "dhA"
+        self._gemm(BF16, OUT_F32, R, H2, cp, dl16, cp, self._views["Wd16"], cp, dcur, H2)
         for l in range(L - 1, -1, -1):
+            H = hs[l]
+            dwx = self._buf("dwx32", (R, 8 * H), torch.float32)
+            duh = self._buf("duh32", (R, 8 * H), torch.float32)
+            dwx16 = self._buf("dwx16", (R, 8 * H), torch.bfloat16)
+            dwxT16 = self._buf("dwxT16", (8 * H, R), torch.bfloat16)
+            duhT16 = self._buf("duhT16", (8 * H, R), torch.bfloat16)
             mk = masks[l] if masks is not None else None
             mask_u = self._views[f"maskU.{l}"] if mk is not None else None
             b = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dcur).value, gates=ptr(w[f"gates.{l}"]).value,
@@ -585,7 +606,7 @@ class AcousticEngine:
                                     ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, st)
                 else:
                     P.g(f"l{l}.U{d}").zero_()
-            need_dx = l > 0 or sp.residual is not None
+            need_dx = l > 0 or bool(sp.proj_width)
             if need_dx:
                 wc = self._views[f"Wcat16.{l}"]
                 res = sp.residual is not None
@@ -610,15 +631,16 @@ class AcousticEngine:
                         lib.asr_add_mask(ptr(dcur), ptr(comb), None, 1, ptr(dcur), R, Dl, st)
                     else:
                         dcur = comb
-        if sp.residual is not None:
+        PW = sp.proj_width
+        if PW:
             if self._input_mask is not None:
-                lib.asr_add_mask(ptr(dcur), None, ptr(self._input_mask.contiguous()), R, ptr(dcur), R, 2 * H, st)
-            dT = self._buf("dprojT16", (2 * H, R), torch.bfloat16)
-            lib.asr_cast_transpose(ptr(dcur), 2 * H, ptr(dT), R, R, 2 * H, BF16, st)
+                lib.asr_add_mask(ptr(dcur), None, ptr(self._input_mask.contiguous()), R, ptr(dcur), R, PW, st)
+            dT = self._buf("dprojT16", (PW, R), torch.bfloat16)
+            lib.asr_cast_transpose(ptr(dcur), PW, ptr(dT), R, R, PW, BF16, st)
             Fd = sp.num_features
-            lib.asr_gemm_tn(BF16, OUT_F32, Fd, 2 * H, R, ptr(self._gen["x_ops"][1]), R, ptr(dT), R, ptr(P.g("proj.W")), 2 * H,
+            lib.asr_gemm_tn(BF16, OUT_F32, Fd, PW, R, ptr(self._gen["x_ops"][1]), R, ptr(dT), R, ptr(P.g("proj.W")), PW,
                             None, 1.0, 0, st)
-            lib.asr_colsum(ptr(dcur), 2 * H, R, 2 * H, ptr(P.g("proj.b")), st)
+            lib.asr_colsum(ptr(dcur), PW, R, PW, ptr(P.g("proj.b")), st)
 
     # ------------------------------------------------------------------- CTC
     def ctc(self, logits, in_len, labels_flat, label_off, max_label_len, grad_scale=1.0, want_grad=True):
@@ -672,7 +694,7 @@ class AcousticEngine:
                 handles.append(allreduce(P.grad))
             return handles
         T, N = self._T, self._N
-        H, L, Cc = sp.num_hiddens, sp.num_layers, sp.num_classes
+        H, L, Cc = sp.hs[0], len(sp.hs), sp.num_classes
         R = T * N
         st = cur_stream()
         cp = _pad8(Cc)

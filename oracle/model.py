@@ -22,12 +22,18 @@ from . import ctc as octc
 from . import lstm as olstm
 
 
-def init_params(num_features, num_hiddens, num_layers, num_classes, seed=4321):
-    """Flat dict of fp32 parameters with Keras-1 initialisers."""
+def init_params(num_features, num_hiddens, num_layers, num_classes, seed=4321, input_dense=None):
+    """Flat dict of fp32 parameters with Keras-1 initialisers.  num_hiddens may be a per-layer sequence and
+    input_dense the width of a leading TimeDistributed(Dense) (eyben, core/models.py:76-103)."""
     rng = np.random.RandomState(seed)
     p = {}
     D = num_features
-    for l in range(num_layers):
+    hs = list(num_hiddens) if isinstance(num_hiddens, (list, tuple)) else [num_hiddens] * num_layers
+    if input_dense:
+        p["proj.W"] = olstm.glorot_uniform(rng, (D, input_dense))
+        p["proj.b"] = np.zeros(input_dense, dtype=np.float32)
+        D = input_dense
+    for l, num_hiddens in enumerate(hs):
         for d in ("f", "b"):
             W, U, b = olstm.init_lstm(rng, D, num_hiddens)
             p[f"l{l}.W{d}"], p[f"l{l}.U{d}"], p[f"l{l}.b{d}"] = W, U, b
@@ -182,13 +188,13 @@ def forward_general(params, x, masks=None, zoneout=0.0, zmasks=None, residual=No
     o = np.asarray(x, dtype=dtype)
     N, T, _ = o.shape
     ctx = dict(x=o, caches=[], ins=[])
-    if residual is not None:
-        assert residual == "sum"
-        o = (o.reshape(N * T, -1) @ params["proj.W"].astype(dtype)).reshape(N, T, -1) + params["proj.b"].astype(dtype)
+    assert residual in (None, "sum")
+    if "proj.W" in params:      # TimeDistributed(Dense): the residual stack's 2H projection (core/models.py:253-255) or
+        o = (o.reshape(N * T, -1) @ params["proj.W"].astype(dtype)).reshape(N, T, -1) + params["proj.b"].astype(dtype)   # eyben's input layer (:90-91)
     if input_mask is not None:
         o = o * input_mask
-    H = params["l0.Uf"].shape[0]
     for l in range(L):
+        H = params[f"l{l}.Uf"].shape[0]
         lm = (masks or {}).get(l, {})
         outs, cs = [], []
         for i, d in enumerate("fb"):
@@ -215,10 +221,10 @@ def loss_and_grads_general(params, x, x_len, labels, weight_decay=0.0, global_ba
     dlogits = (dlogits / gb).astype(dtype)
     top = ctx["top"]
     D = top.shape[2]
-    H = params["l0.Uf"].shape[0]
     grads = {"dense.W": top.reshape(N * T, D).T @ dlogits.reshape(N * T, C), "dense.b": dlogits.sum(axis=(0, 1))}
     do = (dlogits.reshape(N * T, C) @ params["dense.W"].T.astype(dtype)).reshape(N, T, D)
     for l in range(len(ctx["caches"]) - 1, -1, -1):
+        H = params[f"l{l}.Uf"].shape[0]
         dx = 0.0
         for i, d in enumerate("fb"):
             dxi, gp, _ = olstm.lstm_cell_backward(do[:, :, i * H:(i + 1) * H], ctx["caches"][l][i])
@@ -230,7 +236,7 @@ def loss_and_grads_general(params, x, x_len, labels, weight_decay=0.0, global_ba
         do = do + dx if ctx["residual"] is not None else dx
     if ctx["input_mask"] is not None:
         do = do * ctx["input_mask"]
-    if ctx["residual"] is not None:
+    if "proj.W" in params:
         F = ctx["x"].shape[2]
         grads["proj.W"] = ctx["x"].reshape(N * T, F).T @ do.reshape(N * T, -1)
         grads["proj.b"] = do.sum(axis=(0, 1))

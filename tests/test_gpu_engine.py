@@ -221,3 +221,33 @@ def test_config4_stack_blstm800_logfbank40_on_general_cell():
     got = eng.params.export("grad")
     for k, g in grads.items():
         assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+
+
+def test_eyben_heterogeneous_stack_parity():
+    """eyben (core/models.py:76-103): Dense(78) -> BiLSTM(120) -> BiLSTM(27) -> Dense(28), 39 features: whole train step
+    vs the fp64 oracle (logits 1e-3, loss 1e-3 rel, gradients 3e-2), widths that are not multiples of 8 included."""
+    from asr_study_b200.core import models
+    from asr_study_b200.engine import pack_labels
+    N, T, F, C = 16, 14, 39, 28
+    m = models.eyben(num_features=F)
+    assert m.spec.hs == (120, 27) and m.spec.input_dense == 78 and m.spec.general
+    eng = m.engine
+    rng = np.random.RandomState(2)
+    params = om.init_params(F, [120, 27], 2, C, seed=5, input_dense=78)
+    for k in params:
+        params[k] = (params[k] + 0.05 * rng.randn(*params[k].shape)).astype(np.float32)
+    assert set(params) == set(eng.params.shapes)
+    eng.params.load(params)
+    x = rng.randn(N, T, F).astype(np.float32)
+    lens = np.full(N, T, np.int32)
+    labels = [rng.randint(0, C - 1, size=3).astype(np.int32) for _ in range(N)]
+    flat, off, mx = pack_labels(labels, "cuda")
+    loss = eng.train_step(dev(np.ascontiguousarray(x.transpose(1, 0, 2))), dev(lens), flat, off, mx, lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    _, ctc, grads, ref_logits = om.loss_and_grads_general(p64, x, lens, labels)
+    assert norm_err(eng._w["logits"].cpu().numpy().transpose(1, 0, 2), ref_logits) < 1e-3
+    np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
+    got = eng.params.export("grad")
+    for k, g in grads.items():
+        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
