@@ -323,6 +323,7 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
 // lane; the previous frame's row lives in double-buffered shared memory, one 128-thread named barrier per frame.
 // Rows are stored un-normalised for ONE frame (the row maximum is published next to the row and subtracted by
 // the readers), and the running sum of maxima is the fp64 offset: alpha_t(s) = stored + offA[t].
+constexpr int PF = 4;         // emission prefetch distance of the multi-warp lattice (frames)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -384,15 +385,25 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
       if (lane == 0) mxA[warp] = wm;
       if (tid == 0) w_offA[0] = 0.0;
     }
-    float x = 0.0f, z = 0.0f;
-    if (len > 1) { x = logits[((size_t)1 * N + n) * C + lab]; z = w_lse[1]; }
+    // the emission x_t(lab) - lse_t of the next PF frames is prefetched into registers: one frame of lattice work
+    // (~400 cycles) does not cover an L2 round trip, and the load sits on the 999-step dependent chain otherwise
+    float xq[PF], zq[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int tt = 1 + j;
+      xq[j] = (tt < len) ? logits[((size_t)tt * N + n) * C + lab] : 0.0f;
+      zq[j] = (tt < len) ? w_lse[tt] : 0.0f;
+    }
     named_bar_sync(1, 128);
     for (int t = 1; t < len; ++t) {
       const float* prev = rowA + ((t - 1) & 1) * 132 + 2;
       const float* pm = mxA + ((t - 1) & 1) * 4;
       const float M = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
-      float xn = 0.0f, zn = 0.0f;
-      if (t + 1 < len) { xn = logits[((size_t)(t + 1) * N + n) * C + lab]; zn = w_lse[t + 1]; }
+      const float x = xq[0], z = zq[0];
+#pragma unroll
+      for (int j = 0; j + 1 < PF; ++j) { xq[j] = xq[j + 1]; zq[j] = zq[j + 1]; }
+      xq[PF - 1] = zq[PF - 1] = 0.0f;
+      if (t + PF < len) { xq[PF - 1] = logits[((size_t)(t + PF) * N + n) * C + lab]; zq[PF - 1] = w_lse[t + PF]; }
       const float p0 = prev[s], p1 = prev[s - 1], p2 = skip ? prev[s - 2] : NEG;
       float v = lse3(p0, p1, p2);
       v = (v > NEG && M > NEG) ? v - M + (x - z) : NEG;
@@ -403,7 +414,6 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
       const float wm = asr::warp_max(a);
       if (lane == 0) mxA[(t & 1) * 4 + warp] = wm;
       if (tid == 0) w_offA[t] = off;
-      x = xn; z = zn;
       named_bar_sync(1, 128);
     }
     if (tid == 0) {
@@ -425,15 +435,23 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
       if (lane == 0) mxB[((len - 1) & 1) * 4 + w4] = wm;
       if (tid == 128) w_offB[len - 1] = 0.0;
     }
-    float x = 0.0f, z = 0.0f;
-    if (len > 1) { x = logits[((size_t)(len - 2) * N + n) * C + lab]; z = w_lse[len - 2]; }
+    float xq[PF], zq[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int tt = len - 2 - j;
+      xq[j] = (tt >= 0) ? logits[((size_t)tt * N + n) * C + lab] : 0.0f;
+      zq[j] = (tt >= 0) ? w_lse[tt] : 0.0f;
+    }
     named_bar_sync(2, 128);
     for (int t = len - 2; t >= 0; --t) {
       const float* nxt = rowB + ((t + 1) & 1) * 132;
       const float* pm = mxB + ((t + 1) & 1) * 4;
       const float M = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
-      float xn = 0.0f, zn = 0.0f;
-      if (t > 0) { xn = logits[((size_t)(t - 1) * N + n) * C + lab]; zn = w_lse[t - 1]; }
+      const float x = xq[0], z = zq[0];
+#pragma unroll
+      for (int j = 0; j + 1 < PF; ++j) { xq[j] = xq[j + 1]; zq[j] = zq[j + 1]; }
+      xq[PF - 1] = zq[PF - 1] = 0.0f;
+      if (t - PF >= 0) { xq[PF - 1] = logits[((size_t)(t - PF) * N + n) * C + lab]; zq[PF - 1] = w_lse[t - PF]; }
       const float p0 = nxt[s], p1 = nxt[s + 1], p2 = skip ? nxt[s + 2] : NEG;
       float v = lse3(p0, p1, p2);
       v = (v > NEG && M > NEG) ? v - M + (x - z) : NEG;
@@ -444,7 +462,6 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
       const float wm = asr::warp_max(b);
       if (lane == 0) mxB[(t & 1) * 4 + w4] = wm;
       if (tid == 128) w_offB[t] = off;
-      x = xn; z = zn;
       named_bar_sync(2, 128);
     }
   }
