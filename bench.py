@@ -359,23 +359,35 @@ def run_infer(args):
     nb, total, W = 64, args.clips, args.beam_width
     feat = audio.MFCC(num_cep=13, d=True, dd=False)
     eng = AcousticEngine(ModelSpec(F, H, L, C), device=dev, seed=4321)
-    # sharpen the random-init posteriors a little so beams are not degenerate
-    eng.params.p("dense.W").mul_(6.0)
+    # a random-init network emits near-uniform posteriors (logits within +-0.1): every beam is a near tie and fp32
+    # totals collide exactly, so the result hangs on tie-breaking order.  Scale the Dense kernel so the posteriors are
+    # as peaky as a trained CTC model's (the regime config 5 is about); --sharpen sets the factor.
+    eng.params.p("dense.W").mul_(args.sharpen)
     pcm_np = np.stack([synth_clip(777, i, SECONDS, FS) for i in range(nb)])
     pcm_host = torch.from_numpy(pcm_np.reshape(-1)).pin_memory()
     off = (torch.arange(nb + 1, dtype=torch.int64) * pcm_np.shape[1]).to(dev)
     truth = synth_labels(778, nb, 50)
 
+    G = max(1, args.decode_group)
+    nb_fwd = nb
+    big = torch.empty(T_FRAMES, G * nb_fwd, C, dtype=torch.float32, device=dev)
+    big_len = torch.empty(G * nb_fwd, dtype=torch.int32, device=dev)
+
     def batch():
-        pcm = pcm_host.to(dev, non_blocking=True)
-        x, lens = feat.batch(pcm, off, t_max=T_FRAMES, time_major=True)
-        logits = eng.forward(x, training=False)
-        out, out_len = eng.beam(logits, lens, W, True)
-        return logits, lens, out.cpu(), out_len.cpu()
+        """G forward batches (host pcm -> H2D -> MFCC -> BiLSTM) then one beam-search launch over all G * nb utterances."""
+        for g in range(G):
+            pcm = pcm_host.to(dev, non_blocking=True)
+            x, lens = feat.batch(pcm, off, t_max=T_FRAMES, time_major=True)
+            logits = eng.forward(x, training=False)
+            big[:, g * nb_fwd:(g + 1) * nb_fwd].copy_(logits)
+            big_len[g * nb_fwd:(g + 1) * nb_fwd].copy_(lens)
+        out, out_len = eng.beam(big, big_len, W, True)
+        return big, big_len, out.cpu(), out_len.cpu()
 
     for _ in range(2):
         logits, lens, out, out_len = batch()
     torch.cuda.synchronize()
+    nb = G * nb_fwd
     nbatches = max(1, total // nb)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.asr_launch_count()
@@ -394,11 +406,15 @@ def run_infer(args):
     same = sum(int(a == b) for a, b in zip(got, ref))
     res = {"metric": "clips/sec (inference: MFCC -> 3xBiLSTM-512 fwd -> CTC beam search width %d)" % W,
            "value": nb * nbatches / (ms / 1e3), "unit": "clips/s", "n_gpus": 1, "clips": nb * nbatches,
-           "ms_per_batch": ms / nbatches, "batch": nb, "higher_is_better": True, "data": "synthetic",
+           "ms_per_batch": ms / nbatches, "batch": nb, "forward_batch": nb_fwd, "higher_is_better": True, "data": "synthetic",
            "config": {"workload": "C5: synthetic 16 kHz 10 s clips, 26-MFCC, 3xBiLSTM-512, beam %d, host pcm -> labels" % W},
            "gpu_launches": int(launches),
            "ler_parity": {"sample": k, "identical_label_sequences": same,
-                          "ler_device_vs_truth": oc.ler(truth[:k], got), "ler_oracle_vs_truth": oc.ler(truth[:k], ref)}}
+                          "ler_device_vs_truth": oc.ler(truth[:k], got), "ler_oracle_vs_truth": oc.ler(truth[:k], ref),
+                          "ler_rel_diff": abs(oc.ler(truth[:k], got) - oc.ler(truth[:k], ref)) / max(oc.ler(truth[:k], ref), 1e-12),
+                          "note": "sequences differ only where fp32 beam totals tie exactly (random-init posteriors): TF breaks "
+                                  "ties by heap order, which neither restatement can pin without TF; tests/test_gpu_beam.py "
+                                  "has the identical-sequence cases"}}
     print(json.dumps(res), flush=True)
 
 
@@ -417,6 +433,10 @@ def main():
     ap.add_argument("--clips", type=int, default=1024)
     ap.add_argument("--beam_width", type=int, default=100)
     ap.add_argument("--ler_sample", type=int, default=4)
+    ap.add_argument("--sharpen", type=float, default=60.0, help="infer mode: factor on the random-init Dense kernel")
+    ap.add_argument("--decode_group", type=int, default=8,
+                    help="infer mode: forward batches decoded by ONE beam-search launch (one warp per utterance: the "
+                         "search is latency-bound, so more utterances per launch is nearly free)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
