@@ -32,7 +32,8 @@ class LstmFwdArgs(C.Structure):
                 ("zx", C.c_void_p), ("bias", C.c_void_p), ("U", C.c_void_p), ("U16", C.c_void_p),
                 ("h16", C.c_void_p), ("hT16", C.c_void_p), ("h32", C.c_void_p),
                 ("gates", C.c_void_p), ("cell", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p),
-                ("mask_next", C.c_void_p), ("hm16", C.c_void_p), ("hmT16", C.c_void_p), ("hT16u", C.c_void_p)]
+                ("mask_next", C.c_void_p), ("hm16", C.c_void_p), ("hmT16", C.c_void_p), ("hT16u", C.c_void_p),
+                ("mi", C.c_void_p), ("uh", C.c_void_p), ("zoneout", C.c_float), ("zmask", C.c_void_p)]
 
 
 class LstmBwdArgs(C.Structure):
@@ -40,7 +41,9 @@ class LstmBwdArgs(C.Structure):
                 ("dh", C.c_void_p), ("gates", C.c_void_p), ("cell", C.c_void_p),
                 ("U", C.c_void_p), ("U16", C.c_void_p), ("dz16", C.c_void_p), ("dzT16", C.c_void_p),
                 ("dz32", C.c_void_p), ("dbias", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p),
-                ("dh2", C.c_void_p), ("mask_dh", C.c_void_p)]
+                ("dh2", C.c_void_p), ("mask_dh", C.c_void_p),
+                ("mi", C.c_void_p), ("zx", C.c_void_p), ("uh", C.c_void_p), ("dmi", C.c_void_p), ("duhT16", C.c_void_p),
+                ("zoneout", C.c_float), ("zmask", C.c_void_p)]
 
 
 class LstmVariant(C.Structure):
@@ -76,6 +79,7 @@ SIGNATURES = {
     "asr_lstm_flags_bytes": (_SZ, []),
     "asr_lstm_fuses_masks": (_I32, [_I32, _I32, _I32]),
     "asr_lstm_persistent_supported": (_I32, [_I32, _I32, _I32, _I32]),
+    "asr_lstm_fuses_variants": (_I32, [_I32, _I32, _I32]),
     "asr_lstm_forward": (_I32, [C.POINTER(LstmFwdArgs), _P]),
     "asr_lstm_backward": (_I32, [C.POINTER(LstmBwdArgs), _P]),
     "asr_lstm_cell_forward": (_I32, [C.POINTER(LstmFwdArgs), C.POINTER(LstmVariant), _P, _P]),
@@ -126,7 +130,7 @@ class _Lib:
         fn = self.raw(name)
         res = SIGNATURES[name][0]
         if res is not _I32 or name in ("asr_version", "asr_mfcc_num_feats", "asr_mfcc_num_frames", "asr_lstm_fuses_masks",
-                                     "asr_lstm_persistent_supported"):
+                                     "asr_lstm_persistent_supported", "asr_lstm_fuses_variants"):
             return fn
 
         def checked(*a):

@@ -114,13 +114,18 @@ extern "C" int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H) {
   return lstmtc2::shape_supported(T, N, H, false) && lstmtc2::shape_supported(T, N, H, true) ? 1 : 0;
 }
 
+extern "C" int32_t asr_lstm_fuses_variants(int32_t T, int32_t N, int32_t H) {
+  return (H == 512 && asr_lstm_fuses_masks(T, N, H)) ? 1 : 0;
+}
+
 extern "C" int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream) {
   ASR_CHECK_ARG(a && a->zx && a->bias && a->flags, "asr_lstm_forward: null argument");
   if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
   ASR_CHECK_ARG(!a->training || (a->gates && a->cell), "asr_lstm_forward: training needs gates/cell buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fused = a->mask_next || a->hm16 || a->hmT16 || a->hT16u;
+  const bool fused = a->mask_next || a->hm16 || a->hmT16 || a->hT16u || a->mi || a->zoneout > 0.0f;
   ASR_CHECK_ARG(!a->mask_next == !a->hm16, "asr_lstm_forward: mask_next and hm16 go together");
+  ASR_CHECK_ARG(a->zoneout >= 0.0f && a->zoneout < 1.0f, "asr_lstm_forward: zoneout must be in [0, 1)");
   if (!env_is("ASR_B200_LSTM", "fp32")) {
     const bool pin1 = env_is("ASR_B200_LSTM", "tc1"), pin3 = env_is("ASR_B200_LSTM", "tc3");
     if (pin3 && !fused && lstmtc3::supports_fwd(a)) return lstmtc3::forward(a, st);    // cluster / DSMEM exchange (same speed, kept selectable)
@@ -136,7 +141,7 @@ extern "C" int32_t asr_lstm_backward(const asr_lstm_bwd_args* a, void* stream) {
   ASR_CHECK_ARG(a && a->dh && a->gates && a->cell && a->dbias && a->flags, "asr_lstm_backward: null argument");
   if (int32_t rc = check_common(a->T, a->N, a->H)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fused = a->dh2 || a->mask_dh;
+  const bool fused = a->dh2 || a->mask_dh || a->mi || a->zoneout > 0.0f;
   ASR_CHECK_ARG(!a->dh2 || a->mask_dh, "asr_lstm_backward: dh2 needs mask_dh");
   if (!env_is("ASR_B200_LSTM", "fp32")) {
     if (!env_is("ASR_B200_LSTM", "tc1") && lstmtc2::supports_bwd(a)) return lstmtc2::backward(a, st);

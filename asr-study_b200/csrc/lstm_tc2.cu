@@ -67,7 +67,9 @@ __device__ __forceinline__ void st_volatile_v2(uint2* p, uint2 v) {
 // NB = samples per CTA group (8 or 16).  NB = 8 spreads N = 32 over 128 CTAs instead of 64: the MMA still runs at
 // N = 16 (rows 8..15 of the B operand stay zero, their accumulator columns are never read) and costs the same issue
 // slots, while the LL exchange, the shared-memory staging and the gate math per CTA are halved.
-template <int H, int NB>
+// VAR = the element-wise brsmv1 switches (core/layers.py:441-467): multiplicative integration
+// z = alpha*Wx*Uh + beta1*Uh + beta2*Wx + b and zoneout on c and h; off in the default instantiation.
+template <int H, int NB, bool VAR>
 __global__ void __launch_bounds__(THREADS, 1)
 fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf, int delay1) {
   extern __shared__ uint8_t smem_raw[];
@@ -132,10 +134,21 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   float bias[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) bias[g] = a.bias[(size_t)dir * 4 * H + g * H + u];
+  float mia[4], mib1[4], mib2[4];                        // multiplicative integration (VAR): alpha, beta1, beta2 per gate
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const size_t o = (size_t)dir * 4 * H + g * H + u;
+    mia[g] = (VAR && a.mi) ? a.mi[o] : 0.0f;
+    mib1[g] = (VAR && a.mi) ? a.mi[(size_t)8 * H + o] : 1.0f;
+    mib2[g] = (VAR && a.mi) ? a.mi[(size_t)16 * H + o] : 1.0f;
+  }
+  const bool zone = VAR && a.zoneout > 0.0f;
+  float h_prev[NPT];                                     // raw h_{t-1} for zoneout (the exchanged copy carries B_U)
   float c_state[NPT], mu[NPT], mn0[NPT], mn1[NPT];
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     c_state[i] = 0.0f;
+    h_prev[i] = 0.0f;
     mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;   // B_U, constant over time
     // B_W of the NEXT layer's two directions (core/layers.py:439 applies it to this layer's output): the masked
     // operand copies are written here, as side stores, instead of by separate mask kernels
@@ -209,6 +222,13 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       const float* zr = a.zx + (((size_t)t * N + n0 + warp * NPT + i) * 2 + dir) * 4 * H;
 #pragma unroll
       for (int g = 0; g < 4; ++g) zx[i][g] = __ldg(zr + g * H + u);
+    }
+    // zoneout keep coefficients of this step: the train-phase mask (one per time step and unit, shared by the batch) or
+    // the inference blend 1 - level (core/layers_utils.py:34-42); zmask = [h | c][2 dirs][T][H]
+    float kh = 1.0f, kc = 1.0f;
+    if (zone) {
+      kh = a.zmask ? __ldg(a.zmask + ((size_t)(0 * 2 + dir) * T + t) * H + u) : 1.0f - a.zoneout;
+      kc = a.zmask ? __ldg(a.zmask + ((size_t)(1 * 2 + dir) * T + t) * H + u) : 1.0f - a.zoneout;
     }
     float z[NPT][4];
     if (s > 0) {
@@ -315,12 +335,25 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     uint2* xo = xb + (size_t)(s & 1) * WORDS;
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
-      gi[i] = asr::hard_sigmoid(z[i][0] + zx[i][0] + bias[0]);
-      gf[i] = asr::hard_sigmoid(z[i][1] + zx[i][1] + bias[1]);
-      gg[i] = asr::tanh_fast(z[i][2] + zx[i][2] + bias[2]);
-      go[i] = asr::hard_sigmoid(z[i][3] + zx[i][3] + bias[3]);
-      c_state[i] = gf[i] * c_state[i] + gi[i] * gg[i];
-      hv[i] = go[i] * asr::tanh_fast(c_state[i]);
+      float pre[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        pre[g] = VAR ? fmaf(mia[g] * zx[i][g], z[i][g], fmaf(mib1[g], z[i][g], fmaf(mib2[g], zx[i][g], bias[g])))
+                     : z[i][g] + zx[i][g] + bias[g];
+      if (VAR && a.uh && a.training) {                     // raw recurrent product: the backward pass of MI needs it
+        float* up = a.uh + (((size_t)t * N + n0 + warp * NPT + i) * 2 + dir) * 4 * H;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) up[g * H + u] = z[i][g];
+      }
+      gi[i] = asr::hard_sigmoid(pre[0]);
+      gf[i] = asr::hard_sigmoid(pre[1]);
+      gg[i] = asr::tanh_fast(pre[2]);
+      go[i] = asr::hard_sigmoid(pre[3]);
+      const float c_new = gf[i] * c_state[i] + gi[i] * gg[i];
+      c_state[i] = VAR ? fmaf(kc, c_new - c_state[i], c_state[i]) : c_new;
+      const float h_new = go[i] * asr::tanh_fast(c_state[i]);
+      hv[i] = VAR ? fmaf(kh, h_new - h_prev[i], h_prev[i]) : h_new;
+      h_prev[i] = hv[i];
       // publish h * B_U: even lanes pack (unit, unit+1) into one LL word {half2, tag = s+1}
       const float hm = hv[i] * mu[i];
       const float other = __shfl_down_sync(0xffffffffu, hm, 1);
@@ -673,7 +706,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 //   needs one, with the same wire bytes per CTA as the forward all-gather (partials travel as bf16 pairs — the
 //   operands of the product are bf16 already, see DESIGN.md for the error budget).
 // ------------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, bool VAR>
 __global__ void __launch_bounds__(THREADS, 1)
 bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf) {
   extern __shared__ uint8_t smem_raw[];
@@ -737,10 +770,21 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
   const uint32_t idesc = tc::umma_idesc_f16(128, NM, 1);
   const uint32_t sB_addr = tc::smem_u32(sB);
   const int u = u0 + lane;
+  float mia[4], mib1[4], mib2[4], gal[4] = {0, 0, 0, 0}, gb1[4] = {0, 0, 0, 0}, gb2[4] = {0, 0, 0, 0};
+  const bool mi = VAR && a.mi != nullptr, zone = VAR && a.zoneout > 0.0f;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const size_t o = (size_t)dir * K4 + g * H + u;
+    mia[g] = mi ? a.mi[o] : 0.0f;
+    mib1[g] = mi ? a.mi[(size_t)2 * K4 + o] : 1.0f;
+    mib2[g] = mi ? a.mi[(size_t)4 * K4 + o] : 1.0f;
+  }
+  float dh_zone[NPT];                                    // zoneout: (1 - k_h) * dh passes straight to h_{t-1}
   float dc_carry[NPT], mu[NPT], md0[NPT], md1[NPT], db[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     dc_carry[i] = 0.0f;
+    dh_zone[i] = 0.0f;
     mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;
     md0[i] = a.mask_dh ? a.mask_dh[((size_t)0 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
     md1[i] = a.mask_dh ? a.mask_dh[((size_t)1 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
@@ -751,7 +795,23 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
   __nv_bfloat16* dz16 = reinterpret_cast<__nv_bfloat16*>(a.dz16);
   const size_t R = (size_t)T * N;
 
-  auto side_stores = [&](int t, const float (&dz)[NPT][4]) {
+  auto side_stores = [&](int t, const float (&dz)[NPT][4], const float (&du)[NPT][4]) {
+    if (mi && a.duhT16) {                                  // dL/d(uh), transposed: the dU operand when MI splits the two paths
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        __nv_bfloat16* dstT = reinterpret_cast<__nv_bfloat16*>(a.duhT16) + (size_t)(dir * K4 + g * H + u) * ((size_t)T * N) + (size_t)t * N + n0 + warp * NPT;
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(du[0][g], du[1][g]);
+        if constexpr (NPT == 4) {
+          const __nv_bfloat162 p1 = __floats2bfloat162_rn(du[2][g], du[3][g]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(dstT) = pk;
+        } else {
+          *reinterpret_cast<__nv_bfloat162*>(dstT) = p0;
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
       const size_t row = (size_t)t * N + n0 + warp * NPT + i;
@@ -779,7 +839,7 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
       }
     }
   };
-  float p_dz[NPT][4];
+  float p_dz[NPT][4], p_du[NPT][4];      // p_du only lives in the VAR instantiation (never read otherwise)
   int p_t = -1;
 
   PROF_DECL;
@@ -799,12 +859,25 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
       cc[i] = __ldg(a.cell + (row * 2 + dir) * H + u);
       cp[i] = has_fprev ? __ldg(a.cell + ((((size_t)t_fprev * N + n0 + warp * NPT + i) * 2 + dir) * H + u)) : 0.0f;
     }
+    float wxv[VAR ? NPT : 1][4], uhv[VAR ? NPT : 1][4], kh = 1.0f, kc = 1.0f;
+    if (mi) {
+#pragma unroll
+      for (int i = 0; i < NPT; ++i) {
+        const size_t o = (((size_t)t * N + n0 + warp * NPT + i) * 2 + dir) * K4 + u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { wxv[VAR ? i : 0][g] = __ldg(a.zx + o + g * H); uhv[VAR ? i : 0][g] = __ldg(a.uh + o + g * H); }
+      }
+    }
+    if (zone) {
+      kh = a.zmask ? __ldg(a.zmask + ((size_t)(0 * 2 + dir) * T + t) * H + u) : 1.0f - a.zoneout;
+      kc = a.zmask ? __ldg(a.zmask + ((size_t)(1 * 2 + dir) * T + t) * H + u) : 1.0f - a.zoneout;
+    }
     float dh_rec[NPT];
 #pragma unroll
     for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
     if (s > 0) {
       // ---- receive: 16 partials (bf16 pairs of two samples) for each of my (unit, sample pair) ----------------
-      if (p_t >= 0) side_stores(p_t, p_dz);                // first: gives the peers' LL words time to land in L2
+      if (p_t >= 0) side_stores(p_t, p_dz, p_du);   // first: gives the peers' LL words time to land in L2
       const uint32_t tag = (uint32_t)s;
       const uint2* src = xb + ((size_t)((s - 1) & 1) * NCTA + cta) * SLOT + (size_t)(warp * PPT) * NCTA * 32 + lane;
       uint2 w[PPT * NCTA];
@@ -844,23 +917,44 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
       PROF(0);
     }
     // ---- element-wise BPTT -> dz; my dz is the B operand of my own product ------------------------------------
-    float dz[NPT][4];
+    float dz[NPT][4], du[VAR ? NPT : 1][4];
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
-      const float dh = fmaf(dho2[i], md1[i], fmaf(dho[i], md0[i], dh_rec[i]));
+      float dh = fmaf(dho2[i], md1[i], fmaf(dho[i], md0[i], dh_rec[i]));
+      if (VAR) {                                           // h_t = h_{t-1} + k_h (h_new - h_{t-1})
+        dh += dh_zone[i];
+        dh_zone[i] = (1.0f - kh) * dh;
+        dh *= kh;
+      }
       const float tch = asr::tanh_fast(cc[i]);
       const float d_o = dh * tch * asr::hard_sigmoid_grad(go[i]);
-      const float dc = dc_carry[i] + dh * go[i] * (1.0f - tch * tch);
+      float dc = dc_carry[i] + dh * go[i] * (1.0f - tch * tch);
+      float dc_pass = 0.0f;
+      if (VAR) {                                           // c_t = c_{t-1} + k_c (c_new - c_{t-1})
+        dc_pass = (1.0f - kc) * dc;
+        dc *= kc;
+      }
       dz[i][0] = dc * gg[i] * asr::hard_sigmoid_grad(gi[i]);
       dz[i][1] = dc * cp[i] * asr::hard_sigmoid_grad(gf[i]);
       dz[i][2] = dc * gi[i] * (1.0f - gg[i] * gg[i]);
       dz[i][3] = d_o;
-      dc_carry[i] = dc * gf[i];
+      dc_carry[i] = dc * gf[i] + dc_pass;
       const int n = warp * NPT + i;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        float v = dz[i][g];                                // dL/dz; with MI the recurrent path sees dz * (alpha*Wx + beta1)
+        if (mi) {
+          const float wx = wxv[VAR ? i : 0][g], uh = uhv[VAR ? i : 0][g];
+          gal[g] = fmaf(dz[i][g] * wx, uh, gal[g]);
+          gb1[g] = fmaf(dz[i][g], uh, gb1[g]);
+          gb2[g] = fmaf(dz[i][g], wx, gb2[g]);
+          db[g] += dz[i][g];
+          v = dz[i][g] * fmaf(mia[g], wx, mib1[g]);
+          du[VAR ? i : 0][g] = v;
+          dz[i][g] *= fmaf(mia[g], uh, mib2[g]);           // dL/d(zx): what dW and dX consume
+        }
         const int k = g * 32 + lane;                       // K index inside my 128 gate columns
-        *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = __float2bfloat16_rn(dz[i][g]);
+        *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = __float2bfloat16_rn(v);
       }
     }
     PROF(1);
@@ -914,13 +1008,23 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
     for (int i = 0; i < NPT; ++i)
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        db[g] += dz[i][g];
+        if (!mi) db[g] += dz[i][g];
         p_dz[i][g] = dz[i][g];
+        if (VAR) p_du[i][g] = mi ? du[i][g] : dz[i][g];
       }
     p_t = t;
     PROF(6);
   }
-  if (p_t >= 0 && !s_dead) side_stores(p_t, p_dz);
+  if (p_t >= 0 && !s_dead) side_stores(p_t, p_dz, p_du);
+  if (mi) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const size_t o = (size_t)dir * K4 + g * H + u;
+      atomicAdd(a.dmi + o, gal[g]);
+      atomicAdd(a.dmi + (size_t)2 * K4 + o, gb1[g]);
+      atomicAdd(a.dmi + (size_t)4 * K4 + o, gb2[g]);
+    }
+  }
   PROF_DUMP(8);
 #pragma unroll
   for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);
@@ -961,12 +1065,12 @@ static size_t exclusive_smem(size_t need) {
   return (env_int("ASR_LSTM_EXCLUSIVE", 1) && need < want) ? want : need;
 }
 
-template <int H, int NB>
+template <int H, int NB, bool VAR>
 static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   constexpr int KC = H / 64;
   const size_t smem = exclusive_smem(1024 + (size_t)KC * NM * 128 + 4 * NB * 32 * 4 + 64);
   const int G = a->N / NB;
-  ASR_CUDA(cudaFuncSetAttribute(fwd_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ASR_CUDA(cudaFuncSetAttribute(fwd_kernel<H, NB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t xbytes = (size_t)2 * G * 2 * NB * (H / 2) * sizeof(uint2);
   ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + xbytes, st));
   asr_lstm_fwd_args args = *a;
@@ -974,7 +1078,7 @@ static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
   int delay1 = env_int("ASR_LSTM_FWD_DELAY_NS", 0);
   void* kargs[] = {&args, &flags, &xbuf, &delay1};
-  ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H, NB>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
+  ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H, NB, VAR>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
   asr::count_launch();
   return ASR_OK;
 }
@@ -998,19 +1102,20 @@ static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
   return ASR_OK;
 }
 
-template <int NB>
+template <int NB, bool VAR>
 static int32_t launch_bwd3(const asr_lstm_bwd_args* a, cudaStream_t st) {
   const int G = a->N / NB;
   const size_t smem = exclusive_smem(1024 + (size_t)2 * NM * 128 + 64);
   const size_t xbytes = (size_t)2 * G * 2 * 16 * (NB / 2) * 16 * 32 * sizeof(uint2);
-  ASR_CUDA(cudaFuncSetAttribute(bwd3_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ASR_CUDA(cudaFuncSetAttribute(bwd3_kernel<NB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + xbytes, st));
   ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));
+  if (VAR && a->mi) ASR_CUDA(cudaMemsetAsync(a->dmi, 0, (size_t)3 * 2 * 4 * a->H * sizeof(float), st));
   asr_lstm_bwd_args args = *a;
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
   void* kargs[] = {&args, &flags, &xbuf};
-  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd3_kernel<NB>, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
+  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd3_kernel<NB, VAR>, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
   asr::count_launch();
   return ASR_OK;
 }
@@ -1019,17 +1124,28 @@ static int32_t launch_bwd3(const asr_lstm_bwd_args* a, cudaStream_t st) {
 int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
   const char* e = getenv("ASR_LSTM_BWD");
   const bool g8 = group_size(a->N, a->H) == 8;
+  const bool var = a->mi != nullptr || a->zoneout > 0.0f;
+  if (var) {
+    ASR_CHECK_ARG(!a->mi || (a->zx && a->uh && a->dmi && a->duhT16), "lstmtc2 backward: MI needs zx, uh, dmi and duhT16");
+    return g8 ? launch_bwd3<8, true>(a, st) : launch_bwd3<16, true>(a, st);
+  }
   if (e && strcmp(e, "v2") == 0) return g8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
-  return g8 ? launch_bwd3<8>(a, st) : launch_bwd3<16>(a, st);
+  return g8 ? launch_bwd3<8, false>(a, st) : launch_bwd3<16, false>(a, st);
 }
 
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st) {
   const bool g8 = group_size(a->N, a->H) == 8;
+  const bool var = a->mi != nullptr || a->zoneout > 0.0f;
+  if (var) {                                              // the element-wise switches are built for the C2 width
+    ASR_CHECK_ARG(a->H == 512, "lstmtc2 forward: MI / zoneout need H = 512 (got %d)", a->H);
+    ASR_CHECK_ARG(!a->mi || !a->training || a->uh, "lstmtc2 forward: training with MI needs the uh buffer");
+    return g8 ? launch_fwd<512, 8, true>(a, st) : launch_fwd<512, 16, true>(a, st);
+  }
   switch (a->H) {
-    case 128: return g8 ? launch_fwd<128, 8>(a, st) : launch_fwd<128, 16>(a, st);
-    case 256: return g8 ? launch_fwd<256, 8>(a, st) : launch_fwd<256, 16>(a, st);
-    case 384: return g8 ? launch_fwd<384, 8>(a, st) : launch_fwd<384, 16>(a, st);
-    case 512: return g8 ? launch_fwd<512, 8>(a, st) : launch_fwd<512, 16>(a, st);
+    case 128: return g8 ? launch_fwd<128, 8, false>(a, st) : launch_fwd<128, 16, false>(a, st);
+    case 256: return g8 ? launch_fwd<256, 8, false>(a, st) : launch_fwd<256, 16, false>(a, st);
+    case 384: return g8 ? launch_fwd<384, 8, false>(a, st) : launch_fwd<384, 16, false>(a, st);
+    case 512: return g8 ? launch_fwd<512, 8, false>(a, st) : launch_fwd<512, 16, false>(a, st);
   }
   asr::set_error("lstmtc2: unsupported H=%d", a->H);
   return ASR_ERR_INVALID;

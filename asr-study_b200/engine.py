@@ -62,8 +62,15 @@ class ModelSpec:
 
     @property
     def general(self) -> bool:
-        return bool(self.zoneout or self.layer_norm is not None or self.mi is not None or self.residual is not None
-                    or self.input_dropout or self.input_dense or len(set(self.hs)) > 1)
+        """switches only the general-cell path implements (layer norm needs whole-row statistics every step; the
+        residual / projection / heterogeneous stacks use its per-layer operand plumbing)."""
+        return bool(self.layer_norm is not None or self.residual is not None or self.input_dropout or self.input_dense
+                    or len(set(self.hs)) > 1)
+
+    @property
+    def elementwise(self) -> bool:
+        """multiplicative integration / zoneout: element-wise in the step, a template switch of the tensor-core kernels."""
+        return bool(self.zoneout or self.mi is not None)
 
 
 class ParamBucket:
@@ -312,7 +319,8 @@ class AcousticEngine:
         T, N, Fd = feats_tm.shape
         assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
         # the persistent engines cover the reference's shapes; anything else (e.g. H = 800) runs on the general cell
-        self._use_general = sp.general or not lib.asr_lstm_persistent_supported(T, N, sp.hs[0], int(training))
+        self._use_general = (sp.general or not lib.asr_lstm_persistent_supported(T, N, sp.hs[0], int(training))
+                             or (sp.elementwise and not lib.asr_lstm_fuses_variants(T, N, sp.hs[0])))
         if self._use_general:
             return self._forward_general(feats_tm, training, masks, zmasks, input_mask)
         H, L, Cc = sp.hs[0], len(sp.hs), sp.num_classes
@@ -323,6 +331,10 @@ class AcousticEngine:
             masks = self.sample_masks(N)
         self._masks = masks if training else None
         masks = self._masks
+        if training and zmasks is None and sp.zoneout > 0:
+            zmasks = self.sample_zoneout_masks(T)
+        self._zmasks = zmasks if training else None
+        self._zpacked = {}
         st = cur_stream()
         self._prep_weights(training)
         feats_tm = feats_tm.contiguous()
@@ -339,8 +351,12 @@ class AcousticEngine:
         prev = None                                                 # fused outputs of the previous layer
         for l in range(L):
             mask_u = None
+            zx = w["zx"]
+            if training and sp.mi is not None:             # the backward pass of MI re-reads every layer's Wx
+                zx = w[f"zx.{l}"] = self._buf(f"zx.{l}", (R, 8 * H), torch.float32)
+                w[f"uh.{l}"] = self._buf(f"uh.{l}", (R, 8 * H), torch.float32)
             if masks is None:
-                self._gemm(F16, OUT_F32, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, w["zx"], 8 * H)
+                self._gemm(F16, OUT_F32, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, zx, 8 * H)
             else:
                 mk = masks[l]
                 mask_u = self._packed(mk, "U")
@@ -358,7 +374,7 @@ class AcousticEngine:
                             xmT = self._buf(f"xmT16.{l}.{i}", (Dl, R), torch.bfloat16)
                             lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xmT), BF16, R, R, Dl, 1, st)
                     lib.asr_gemm_tn(F16, OUT_F32, R, 4 * H, D, ptr(xm), D, ptr(self._views[f"WcatT16.{l}"][i * 4 * H:]), D,
-                                    ptr(w["zx"][:, i * 4 * H:]), 8 * H, None, 1.0, 0, st)
+                                    ptr(zx[:, i * 4 * H:]), 8 * H, None, 1.0, 0, st)
             top = l == L - 1
             fz = dict(mask_next=None, hm16=None, hmT16=None, hT16u=None)
             cur = None
@@ -371,7 +387,15 @@ class AcousticEngine:
                           hmT16=ptr(cur["hmT16"]).value if training else None)
             if fuse and top and training:
                 fz["hT16u"] = ptr(self._buf("topT16", (2 * H, R), torch.bfloat16)).value
-            a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(w["zx"]).value,
+            if sp.elementwise:                             # MI / zoneout switches of the tensor-core kernels
+                fz["zoneout"] = float(sp.zoneout)
+                if sp.mi is not None:
+                    fz["mi"] = P.p(f"l{l}.mi_alpha").data_ptr()       # alpha | beta1 | beta2 are contiguous in the bucket
+                    fz["uh"] = ptr(w[f"uh.{l}"]).value if training else None
+                if self._zmasks is not None:
+                    zp = self._zpacked[l] = torch.stack([self._zmasks[l]["h"], self._zmasks[l]["c"]]).contiguous()
+                    fz["zmask"] = zp.data_ptr()
+            a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(zx).value,
                             bias=ptr(P.p(f"l{l}.bf")).value, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"UT16.{l}"]).value,
                             h16=ptr(w[f"h16.{l}"]).value if (top or not fuse) else None,
@@ -721,6 +745,15 @@ class AcousticEngine:
         dh2, mask_dh = None, None                  # fused path: the layer above left its dX as two masked partials
         for l in range(L - 1, -1, -1):
             mask_u = self._views[f"maskU.{l}"] if masks is not None else None
+            vz = {}
+            if sp.elementwise:
+                vz["zoneout"] = float(sp.zoneout)
+                if sp.mi is not None:
+                    duhT = self._buf(f"duhT16.{l}", (8 * H, R), torch.bfloat16)
+                    vz.update(mi=P.p(f"l{l}.mi_alpha").data_ptr(), zx=ptr(w[f"zx.{l}"]).value, uh=ptr(w[f"uh.{l}"]).value,
+                              dmi=P.g(f"l{l}.mi_alpha").data_ptr(), duhT16=ptr(duhT).value)
+                if self._zmasks is not None:
+                    vz["zmask"] = self._zpacked[l].data_ptr()
             a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(w[f"gates.{l}"]).value,
                             cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"Ub16.{l}"]).value,
@@ -728,7 +761,7 @@ class AcousticEngine:
                             dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value,
                             mask_u=ptr(mask_u).value if mask_u is not None else None,
                             dh2=ptr(dh2).value if dh2 is not None else None,
-                            mask_dh=ptr(mask_dh).value if mask_dh is not None else None)
+                            mask_dh=ptr(mask_dh).value if mask_dh is not None else None, **vz)
             lib.asr_lstm_backward(C.byref(a), st)
             dh2, mask_dh = None, None
             D = sp.num_features if l == 0 else 2 * H
@@ -751,7 +784,7 @@ class AcousticEngine:
                     if T > 1:
                         Kk = (T - 1) * N
                         hA = hT[i * H:(i + 1) * H]
-                        dzB = dzT[i * 4 * H:(i + 1) * 4 * H]
+                        dzB = (self._views[f"duhT16.{l}"] if sp.mi is not None else dzT)[i * 4 * H:(i + 1) * 4 * H]
                         if i == 0:   # forward direction: h_{t-1} with dz_t
                             Ap, Bp = hA, dzB[:, N:]
                         else:        # reverse direction: h_{t+1} with dz_t

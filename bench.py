@@ -159,7 +159,8 @@ def run_ours(args):
     off_dev = off_host.to(dev)
     flat, loff, mx = pack_labels(labels, dev)
     feat = audio.MFCC(num_cep=13, d=True, dd=False)
-    eng = AcousticEngine(ModelSpec(F, H, L, C, weight_decay=1e-4, dropout=args.dropout), device=dev, seed=4321)
+    eng = AcousticEngine(ModelSpec(F, H, L, C, weight_decay=1e-4, dropout=args.dropout, zoneout=args.zoneout,
+                                   mi=(1.0, 0.5, 0.5) if args.mi else None), device=dev, seed=4321)
     loss_host = torch.empty(nb, dtype=torch.float32).pin_memory()
     loss_bufs = [loss_host, torch.empty(nb, dtype=torch.float32).pin_memory()]
     loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
@@ -277,7 +278,8 @@ def run_ours(args):
                "scaling": "weak", "vs_baseline": None, "dtype": "fp16/bf16 tensor-core operands, fp32 accumulate+state",
                "data": "synthetic",
                "config": {"workload": "C2: synthetic 16 kHz 10 s clips, 26-MFCC, 3xBiLSTM-512, Dense-28, CTC, "
-                                      "Adam(1e-3, clipnorm 400), l2 1e-4, variational dropout %g" % args.dropout, "per_gpu_batch": nb,
+                                      "Adam(1e-3, clipnorm 400), l2 1e-4, variational dropout %g" % args.dropout
+                                      + (", zoneout %g" % args.zoneout if args.zoneout else "") + (", MI" if args.mi else ""), "per_gpu_batch": nb,
                           "global_batch": gb, "frames": T_FRAMES, "parallelism": f"dp{world}",
                           "l2_flush": "per-step working set ~4 GB >> 126 MB L2 (inputs larger than L2)",
                           "input_pipeline": "prefetch: H2D + MFCC of batch k+1 on a side stream during step k" if args.prefetch
@@ -426,6 +428,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dropout", type=float, default=0.2, help="brsmv1 dropout_W = dropout_U (reference default 0.2)")
+    ap.add_argument("--zoneout", type=float, default=0.0, help="brsmv1 zoneout switch (off in the headline config)")
+    ap.add_argument("--mi", action="store_true", help="brsmv1 multiplicative-integration switch (off in the headline config)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="featurise each batch in line instead of one step ahead on the side stream")

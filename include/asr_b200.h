@@ -145,6 +145,11 @@ typedef struct {
   void*  hm16;              /* fp16 [2, T*N, 2H]  h * mask_next[i]: the next layer's projection operands    */
   void*  hmT16;             /* bf16 [2, 2H, T*N]  transposed copies: the next layer's dW operands (training)*/
   void*  hT16u;             /* bf16 [2H, T*N]  unmasked transposed copy (the Dense dW operand), or NULL     */
+  /* element-wise brsmv1 switches on the tensor-core engine (asr_lstm_fuses_variants() == 1; core/layers.py:441-467):  */
+  const float* mi;          /* f32 [3, 2, 4H]  alpha | beta1 | beta2 of multiplicative integration, or NULL  */
+  float* uh;                /* f32 [T, N, 2, 4H]  raw recurrent product, saved when training with mi         */
+  float  zoneout;           /* level in [0,1): zoneout on h and c (0 = off)                                  */
+  const float* zmask;       /* f32 [2 (h|c), 2, T, H]  train-phase keep masks, NULL = inference blend 1-level */
 } asr_lstm_fwd_args;
 
 typedef struct {
@@ -163,12 +168,22 @@ typedef struct {
   /* fused dropout inputs (asr_lstm_fuses_masks() == 1): dL/d(output) = dh * mask_dh[0] + dh2 * mask_dh[1] */
   const float* dh2;         /* f32 [T, N, 2H]  second partial (the bwd LSTM of the layer above), or NULL    */
   const float* mask_dh;     /* f32 [2, N, 2H]  B_W of the layer above (fwd | bwd), or NULL = ones            */
+  /* element-wise switches (see asr_lstm_fwd_args); with mi, dz16 / dzT16 carry dL/d(zx) (dW, dX) and            */
+  const float* mi;          /* duhT16 carries dL/d(uh) (dU); dmi receives the alpha|beta1|beta2 gradients    */
+  const float* zx;          /* f32 [T, N, 2, 4H]  the forward call's zx (mi)                                 */
+  const float* uh;          /* f32 [T, N, 2, 4H]  saved by the forward call (mi)                             */
+  float* dmi;               /* f32 [3, 2, 4H]  (overwritten)                                                 */
+  void*  duhT16;            /* bf16 [2*4H, T*N]                                                              */
+  float  zoneout;
+  const float* zmask;
 } asr_lstm_bwd_args;
 
 /* 1 when the engine asr_lstm_forward/backward would select for this shape implements the fused dropout
  * fields above (mask_next/hm16/hmT16/hT16u, dh2/mask_dh); 0 = the caller must mask with asr_mask_cast /
  * asr_mask_combine instead. */
 int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H);
+/* 1 when that engine also implements the element-wise switches (mi / zoneout fields); 0 = use the general cell. */
+int32_t asr_lstm_fuses_variants(int32_t T, int32_t N, int32_t H);
 /* 1 when asr_lstm_forward/backward take this shape (a persistent engine exists for it); 0 = use the general-cell
  * entry points below (any N, H <= 1024), e.g. H = 800 of BASELINE config 4. */
 int32_t asr_lstm_persistent_supported(int32_t T, int32_t N, int32_t H, int32_t training);

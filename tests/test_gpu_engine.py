@@ -251,3 +251,50 @@ def test_eyben_heterogeneous_stack_parity():
     got = eng.params.export("grad")
     for k, g in grads.items():
         assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+
+
+@pytest.mark.parametrize("sw", [dict(mi=(1.0, 0.5, 0.5)), dict(zoneout=0.2), dict(mi=(1.0, 0.5, 0.5), zoneout=0.15, dropout=0.2)])
+def test_elementwise_switches_on_the_tensor_core_engine(sw):
+    """MI / zoneout at the C2 width run as a template switch of the tensor-core recurrences (lstm_tc2.cu), not on the
+    general cell: whole train step vs the fp64 oracle with the same masks, then the inference blend."""
+    from asr_study_b200._lib import lib
+    from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
+    N, T, F, H, L, C = 8, 20, 26, 512, 2, 28
+    assert lib.asr_lstm_fuses_variants(T, N, H) == 1
+    rng = np.random.RandomState(23)
+    spec = ModelSpec(F, H, L, C, dropout=sw.get("dropout", 0.0), zoneout=sw.get("zoneout", 0.0), mi=sw.get("mi"))
+    assert spec.elementwise and not spec.general
+    params = AcousticEngine.keras_init(spec, 31)
+    for k in params:
+        params[k] = (params[k] + 0.03 * rng.randn(*params[k].shape)).astype(np.float32)
+    eng = AcousticEngine(spec, init_params=params)
+    x = rng.randn(N, T, F).astype(np.float32)
+    lens = np.full(N, T, np.int32)
+    labels = [rng.randint(0, C - 1, size=rng.randint(2, 6)).astype(np.int32) for _ in range(N)]
+    masks_np = zm_np = None
+    if spec.dropout:
+        masks_np, D = {}, F
+        for l in range(L):
+            masks_np[l] = {k: ((rng.rand(N, w) >= 0.2) / 0.8).astype(np.float32) for k, w in (("Wf", D), ("Wb", D), ("Uf", H), ("Ub", H))}
+            D = 2 * H
+    if spec.zoneout:
+        zm_np = {l: {k + d: (rng.rand(T, H) >= spec.zoneout).astype(np.float32) for k in "hc" for d in "fb"} for l in range(L)}
+    masks_dev = None if masks_np is None else {l: {k: dev(v) for k, v in m.items()} for l, m in masks_np.items()}
+    zm_dev = None if zm_np is None else {l: {k: dev(np.stack([m[k + "f"], m[k + "b"]])) for k in "hc"} for l, m in zm_np.items()}
+    flat, off, mx = pack_labels(labels, "cuda")
+    feats = dev(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    loss = eng.train_step(feats, dev(lens), flat, off, mx, masks=masks_dev, zmasks=zm_dev, lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    assert eng.lstm_status() == 0 and not eng._use_general
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    _, ctc, grads, ref_logits = om.loss_and_grads_general(p64, x, lens, labels, masks=masks_np, zoneout=spec.zoneout, zmasks=zm_np)
+    assert norm_err(eng._w["logits"].cpu().numpy().transpose(1, 0, 2), ref_logits) < 1e-3
+    np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
+    got = eng.params.export("grad")
+    assert set(got) == set(grads)
+    for k, g in grads.items():
+        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+    logits_eval = eng.forward(feats, training=False).cpu().numpy().transpose(1, 0, 2)
+    p_after = {k: v.astype(np.float64) for k, v in eng.params.export("flat").items()}
+    ref_eval, _ = om.forward_general(p_after, x, zoneout=spec.zoneout)
+    assert norm_err(logits_eval, ref_eval) < 1e-3
