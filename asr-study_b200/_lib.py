@@ -72,6 +72,7 @@ SIGNATURES = {
     "asr_mfcc_num_feats": (_I32, [_P]),
     "asr_mfcc_num_frames": (_I32, [_P, _I64]),
     "asr_mfcc_workspace_bytes": (_SZ, [_P, _I32]),
+    "asr_mfcc_workspace_bytes_ex": (_SZ, [_P, _I32, _I32]),
     "asr_mfcc_forward": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _I32, _P, _P]),
     "asr_mfcc_forward_host": (_I32, [_P, _P, _I64, _P]),
     "asr_gemm_tn": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _P]),

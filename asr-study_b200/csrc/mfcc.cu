@@ -324,6 +324,44 @@ mfcc_kernel(Params p, const float* __restrict__ pcm, const int64_t* __restrict__
   }
 }
 
+// ---- +-num_context frames (Feature._postprocessing, audio.py:88-150) + CMVN over the widened matrix ------------
+// raw: un-normalised (strided) features [N, t_max, F] from the fused kernel.  Output column j = (k, f) with
+// k = j / F - ctx is column f shifted by k frames, zeros outside [0, len) ("empty_mfcc", audio.py:97-98); every
+// output column is then standardised on its own over the utterance's len rows (audio.py:70-75 runs after
+// _postprocessing, audio.py:65).  One CTA per (utterance, output column): two-pass mean / deviation in fp64.
+__global__ void __launch_bounds__(256)
+mfcc_context_kernel(const float* __restrict__ raw, const int* __restrict__ out_len, int n_utt, int t_max, int F, int ctx,
+                    int mean_norm, int var_norm, float eps, float* __restrict__ out, int time_major) {
+  const int n = blockIdx.y, j = blockIdx.x, tid = threadIdx.x;
+  const int Fx = F * (1 + 2 * ctx), k = j / F - ctx, f = j % F;
+  const int len = min(out_len[n], t_max);
+  const float* col = raw + (size_t)n * t_max * F + f;
+  auto at = [&](int t) -> float { const int ts = t + k; return (ts >= 0 && ts < len) ? col[(size_t)ts * F] : 0.0f; };
+  __shared__ double red[256];
+  auto block_sum = [&](double v) -> double {
+    red[tid] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) red[tid] += red[tid + o];
+      __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+  };
+  double s = 0.0;
+  for (int t = tid; t < len; t += 256) s += (double)at(t);
+  const double mean = len > 0 ? block_sum(s) / len : 0.0;
+  double ss = 0.0;
+  for (int t = tid; t < len; t += 256) { const double d = (double)at(t) - mean; ss += d * d; }
+  const double var = len > 0 ? block_sum(ss) / len : 0.0;
+  const double m = mean_norm ? mean : 0.0, inv = var_norm ? 1.0 / (sqrt(var) + (double)eps) : 1.0;
+  for (int t = tid; t < t_max; t += 256) {
+    float* q = time_major ? out + ((size_t)t * n_utt + n) * Fx + j : out + ((size_t)n * t_max + t) * Fx + j;
+    *q = (t < len) ? (float)(((double)at(t) - m) * inv) : 0.0f;
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -341,10 +379,7 @@ static int round_half_up(double x) { return (int)floor(x + 0.5); }  // audio_uti
 extern "C" int32_t asr_mfcc_plan_create(const asr_mfcc_config* cfg, asr_mfcc_plan** out) {
   ASR_CHECK_ARG(cfg && out, "asr_mfcc_plan_create: null argument");
   ASR_CHECK_ARG(cfg->nfft == NFFT, "mfcc: only nfft=512 is built (got %d)", cfg->nfft);
-  if (cfg->num_context != 0) {
-    asr::set_error("mfcc: num_context=%d not built yet (audio.py:88-150)", cfg->num_context);
-    return ASR_ERR_UNSUPPORTED;
-  }
+  ASR_CHECK_ARG(cfg->num_context >= 0 && cfg->num_context <= 64, "mfcc: num_context out of range");
   ASR_CHECK_ARG(cfg->high_freq <= cfg->fs / 2, "high_freq must be less or equal than fs/2");  // audio.py:186
   ASR_CHECK_ARG(cfg->num_filt >= 1 && cfg->num_filt <= MAX_FILT, "mfcc: num_filt out of range");
   ASR_CHECK_ARG(cfg->kind >= 0 && cfg->kind <= 2, "mfcc: kind must be 0..2");
@@ -478,7 +513,9 @@ extern "C" void asr_mfcc_plan_destroy(asr_mfcc_plan* plan) {
   delete plan;
 }
 
-extern "C" int32_t asr_mfcc_num_feats(const asr_mfcc_plan* plan) { return plan ? plan->p.feat_dim : ASR_ERR_INVALID; }
+extern "C" int32_t asr_mfcc_num_feats(const asr_mfcc_plan* plan) {
+  return plan ? plan->p.feat_dim * (1 + 2 * plan->cfg.num_context) : ASR_ERR_INVALID;   // audio.py:146
+}
 
 extern "C" int32_t asr_mfcc_num_frames(const asr_mfcc_plan* plan, int64_t num_samples) {
   if (!plan) return ASR_ERR_INVALID;
@@ -488,9 +525,19 @@ extern "C" int32_t asr_mfcc_num_frames(const asr_mfcc_plan* plan, int64_t num_sa
   return (int32_t)((nf + plan->p.stride - 1) / plan->p.stride);
 }
 
+static size_t stats_bytes(const asr_mfcc_plan* plan, int32_t n) {
+  return (size_t)n * 2 * plan->p.feat_dim * sizeof(double) + (((size_t)n * sizeof(int) + 15) & ~(size_t)15);
+}
 extern "C" size_t asr_mfcc_workspace_bytes(const asr_mfcc_plan* plan, int32_t n) {
   if (!plan || n <= 0) return 0;
-  return (size_t)n * 2 * plan->p.feat_dim * sizeof(double) + (((size_t)n * sizeof(int) + 15) & ~(size_t)15);
+  return stats_bytes(plan, n);
+}
+// with num_context > 0 the fused kernel's un-normalised [n, t_max, F] features are staged in the workspace too
+extern "C" size_t asr_mfcc_workspace_bytes_ex(const asr_mfcc_plan* plan, int32_t n, int32_t t_max) {
+  if (!plan || n <= 0 || t_max <= 0) return 0;
+  size_t b = (stats_bytes(plan, n) + 255) & ~(size_t)255;
+  if (plan->cfg.num_context > 0) b += (size_t)n * t_max * plan->p.feat_dim * sizeof(float);
+  return b;
 }
 
 extern "C" int32_t asr_mfcc_forward(const asr_mfcc_plan* plan, const float* pcm, const int64_t* offsets, int32_t n,
@@ -502,8 +549,25 @@ extern "C" int32_t asr_mfcc_forward(const asr_mfcc_plan* plan, const float* pcm,
   int* counters = (int*)((char*)ws + (size_t)n * 2 * plan->p.feat_dim * sizeof(double));
   const int raw = t_max * plan->p.stride;
   dim3 grid((raw + CHUNK - 1) / CHUNK, n);
-  mfcc_kernel<<<grid, THREADS, plan->smem_bytes, (cudaStream_t)stream>>>(plan->p, pcm, offsets, n, t_max, out, out_len,
-                                                                          time_major, counters, stats);
+  const int ctx = plan->cfg.num_context;
+  if (ctx == 0) {
+    mfcc_kernel<<<grid, THREADS, plan->smem_bytes, (cudaStream_t)stream>>>(plan->p, pcm, offsets, n, t_max, out, out_len,
+                                                                            time_major, counters, stats);
+    ASR_LAUNCH_CHECK();
+    return ASR_OK;
+  }
+  // num_context > 0 (audio.py:88-150): un-normalised features into the workspace (sized by
+  // asr_mfcc_workspace_bytes_ex), then the context gather + CMVN kernel
+  float* rawf = (float*)((char*)ws + ((stats_bytes(plan, n) + 255) & ~(size_t)255));
+  Params p = plan->p;
+  p.mean_norm = p.var_norm = 0;
+  mfcc_kernel<<<grid, THREADS, plan->smem_bytes, (cudaStream_t)stream>>>(p, pcm, offsets, n, t_max, rawf, out_len, 0, counters,
+                                                                          stats);
+  ASR_LAUNCH_CHECK();
+  const int Fx = plan->p.feat_dim * (1 + 2 * ctx);
+  mfcc_context_kernel<<<dim3(Fx, n), 256, 0, (cudaStream_t)stream>>>(rawf, out_len, n, t_max, plan->p.feat_dim, ctx,
+                                                                      plan->p.mean_norm, plan->p.var_norm, plan->p.eps, out,
+                                                                      time_major);
   ASR_LAUNCH_CHECK();
   return ASR_OK;
 }
@@ -511,8 +575,8 @@ extern "C" int32_t asr_mfcc_forward(const asr_mfcc_plan* plan, const float* pcm,
 extern "C" int32_t asr_mfcc_forward_host(const asr_mfcc_plan* plan, const float* pcm_host, int64_t num_samples,
                                          float* out_host) {
   ASR_CHECK_ARG(plan && pcm_host && out_host && num_samples > 1, "asr_mfcc_forward_host: bad argument");
-  const int T = asr_mfcc_num_frames(plan, num_samples), F = plan->p.feat_dim;
-  const size_t wsb = asr_mfcc_workspace_bytes(plan, 1);
+  const int T = asr_mfcc_num_frames(plan, num_samples), F = asr_mfcc_num_feats(plan);
+  const size_t wsb = asr_mfcc_workspace_bytes_ex(plan, 1, T);
   char* dev = nullptr;
   const size_t o_off = ((size_t)num_samples * 4 + 255) & ~(size_t)255, o_out = o_off + 256,
                o_len = o_out + (((size_t)T * F * 4 + 255) & ~(size_t)255), o_ws = o_len + 256, total = o_ws + wsb;

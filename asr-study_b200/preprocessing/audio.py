@@ -106,10 +106,10 @@ class Feature(object):
         if out is None:
             out = torch.empty(shape, dtype=torch.float32, device=pcm.device)
         out_len = torch.empty(n, dtype=torch.int32, device=pcm.device)
-        key = (n, pcm.device)
+        key = (n, int(t_max), pcm.device)
         ws = self._ws.get(key)
         if ws is None:
-            ws = torch.zeros(lib.asr_mfcc_workspace_bytes(plan, n) // 8 + 1, dtype=torch.float64, device=pcm.device)
+            ws = torch.zeros(lib.asr_mfcc_workspace_bytes_ex(plan, n, int(t_max)) // 8 + 1, dtype=torch.float64, device=pcm.device)
             self._ws[key] = ws
         lib.asr_mfcc_forward(plan, ptr(pcm), ptr(offsets), n, t_max, ptr(out), ptr(out_len), int(time_major),
                              ptr(ws), cur_stream())
@@ -120,7 +120,10 @@ class Feature(object):
 
     @property
     def num_feats(self):
-        return self._num_feats
+        # width of what __call__ returns: the base features widened by +-num_context frames (audio.py:146 — the
+        # reference only updates _num_feats inside the first _postprocessing call; the final value is returned here)
+        base = self._num_feats
+        return base if base is None else base * (1 + 2 * int(self.num_context))
 
 
 class FBank(Feature):

@@ -77,6 +77,9 @@ int32_t asr_mfcc_num_feats(const asr_mfcc_plan* plan);
 int32_t asr_mfcc_num_frames(const asr_mfcc_plan* plan, int64_t num_samples);
 /* bytes of zero-initialised device scratch for a batch of n utterances */
 size_t  asr_mfcc_workspace_bytes(const asr_mfcc_plan* plan, int32_t n);
+/* same, for plans with num_context > 0 (they stage the un-normalised [n, t_max, F] features in the workspace);
+ * equals asr_mfcc_workspace_bytes (rounded up) when num_context == 0 */
+size_t  asr_mfcc_workspace_bytes_ex(const asr_mfcc_plan* plan, int32_t n, int32_t t_max);
 /*
  * pcm      f32 [sum samples], utterance i = pcm[offsets[i] .. offsets[i+1])
  * offsets  i64 [n+1] (device)

@@ -160,6 +160,8 @@ class Feature:
         out = np.zeros((T, F * (2 * c + 1)), dtype=feats.dtype)
         for off in range(-c, c + 1):
             lo, hi = max(0, -off), min(T, T - off)
+            if hi <= lo:                       # utterance shorter than the offset: the whole block stays "empty_mfcc"
+                continue
             out[lo:hi, (off + c) * F:(off + c + 1) * F] = feats[lo + off:hi + off]
         return out
 

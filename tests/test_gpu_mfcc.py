@@ -101,7 +101,34 @@ def test_errors_are_loud():
     from asr_study_b200 import AsrError
     with pytest.raises(ValueError):
         audio.MFCC(high_freq=9000)                      # audio.py:186-187
+    with pytest.raises((FileNotFoundError, OSError)):
+        audio.MFCC()("some.wav")                       # paths are loaded (WAV); a missing file is an OS error
     with pytest.raises(TypeError):
-        audio.MFCC()("some.wav")
+        audio.MFCC()(3.0)
     with pytest.raises(AsrError):
-        audio.MFCC(num_context=2)(np.zeros(1000, np.float32))
+        audio.MFCC(num_context=200)(np.zeros(1000, np.float32))
+
+
+@pytest.mark.parametrize("ctx,stride", [(2, 1), (9, 2), (3, 3)])
+def test_context_window_and_stride(ctx, stride):
+    """Feature._postprocessing (audio.py:77-150): every stride-th frame, then +-num_context frames with zero frames
+    outside the utterance, THEN per-column CMVN of the widened matrix (audio.py:65) — vs the oracle, single clip and
+    ragged batch (time-major and batch-major), incl. a clip shorter than the context."""
+    from asr_study_b200.preprocessing import audio
+    f = audio.MFCC(num_cep=13, d=True, dd=False, num_context=ctx, stride=stride)
+    o = om.MFCC(num_cep=13, d=True, dd=False, num_context=ctx, stride=stride)
+    assert f.num_feats == 26 * (1 + 2 * ctx)
+    clips = [_clip(21, 0.9), _clip(22, 0.31), _clip(23, 0.05)]
+    refs = [o(c) for c in clips]
+    for c, r in zip(clips, refs):
+        got = f(c)
+        assert got.shape == r.shape and np.abs(got - r).max() <= TOL
+    off = dev(np.concatenate([[0], np.cumsum([len(c) for c in clips])]).astype(np.int64))
+    pcm = dev(np.concatenate(clips))
+    for tm in (True, False):
+        feats, lens = f.batch(pcm, off, time_major=tm)
+        feats = feats.cpu().numpy()
+        for n, r in enumerate(refs):
+            assert int(lens[n]) == r.shape[0]
+            g = feats[:, n] if tm else feats[n]
+            assert np.abs(g[:r.shape[0]] - r).max() <= TOL and np.all(g[r.shape[0]:] == 0)

@@ -67,6 +67,16 @@ def test_context_window_matches_reference_loop():
             if 0 <= t + off < T:
                 exp[t, (off + 2) * F:(off + 3) * F] = xs[t + off]
     assert np.array_equal(got, exp)
+    # utterance shorter than the context (the reference pads with "empty_mfcc" on both sides, audio.py:108-131)
+    f9 = om.Feature(num_context=9, stride=1)
+    y = np.random.RandomState(2).randn(2, 3)
+    g9 = f9._postprocessing(y)
+    e9 = np.zeros((2, 3 * 19))
+    for t in range(2):
+        for off in range(-9, 10):
+            if 0 <= t + off < 2:
+                e9[t, (off + 9) * 3:(off + 10) * 3] = y[t + off]
+    assert np.array_equal(g9, e9)
 
 
 def test_pad_batch_contract():
