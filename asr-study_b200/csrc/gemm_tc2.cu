@@ -9,8 +9,8 @@
 //     accumulators: the epilogue of item i (TMEM -> registers -> smem transpose -> coalesced 128-byte stores) runs
 //     under the main loop of item i+1 instead of needing a second resident CTA.
 //   * 4-stage TMA ring of 48 KB stages (A 16 KB + B 32 KB, SWIZZLE_128B).
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane),
-// warps 2..5 = epilogue, one TMEM lane quarter each (warp % 4).
+// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane),
+// warps 2..9 = epilogue: TMEM lane quarter warp % 4, two warps per quarter split the 256 columns.
 // Split-K (fp32 C, red.global.add into a zeroed C) for the short-M/N, long-K gradient GEMMs.
 #include "common.cuh"
 #include "tc.cuh"
@@ -19,10 +19,11 @@
 
 namespace gemm_tc2 {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, THREADS = 192;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int EPI_WARPS = 8, THREADS = 64 + 32 * EPI_WARPS;        // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KB
-constexpr int STG_FLOATS = 32 * 36;                                                              // per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int STG_LD = 20, STG_FLOATS = 32 * STG_LD;               // per epilogue warp: [32 rows][16 cols + 4 pad]
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
 
 struct Params {
   int M, N, K;
@@ -39,7 +40,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(stg_base + 4 * STG_FLOATS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_FLOATS);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
@@ -57,7 +58,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(tmem_full + b, 1);
-      tc::mbar_init(tmem_empty + b, 4);      // one arrival per epilogue warp
+      tc::mbar_init(tmem_empty + b, EPI_WARPS);      // one arrival per epilogue warp
     }
     tc::fence_mbar_init();
   }
@@ -121,9 +122,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    const int q = warp & 3;
-    float* stg = stg_base + q * STG_FLOATS;
-    const int sub = lane >> 3, l8 = lane & 7;
+    // 8 epilogue warps: TMEM lane quarter q = warp % 4 (the hardware restriction), column half = the two warps of a
+    // quarter split the 256 accumulator columns, so the drain of an accumulator (the limiter of the K = 1024
+    // projection: 128 KB of fp32 per 16 k-blocks) runs twice as wide.  16-column chunks: TMEM -> registers -> smem
+    // transpose -> 64-byte row segments (4 lanes x 16 B per row, 8 rows per store instruction).
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* stg = stg_base + (warp - 2) * STG_FLOATS;
+    const int sub = lane >> 2, l4 = lane & 3;
     const bool split = p.split > 1;
     int w = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++w) {
@@ -134,22 +139,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc::tcgen05_fence_after();
       const bool add_bias = p.bias != nullptr && kb0 == 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0), r);
+      for (int cc = 0; cc < BN / 2; cc += 16) {
+        const int c0 = half * (BN / 2) + cc;
+        uint32_t r[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0), r);
         tc::tmem_ld_wait();
-        if (c0 + 32 == BN) {                       // last read of this accumulator: hand it back to the MMA warp
+        if (cc + 16 == BN / 2) {                     // last read of this accumulator half: hand it back to the MMA warp
           tc::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(tmem_empty + b);
         }
         if (n0 + c0 >= p.N) continue;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * 36 + j) =
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + j) =
               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         __syncwarp();
-        const int col = n0 + c0 + l8 * 4;
+        const int col = n0 + c0 + l4 * 4;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (add_bias) {
           if (col < p.N) bv.x = __ldg(p.bias + col);
@@ -158,10 +164,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
         }
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {
-          const int rl = pass * 4 + sub;
+        for (int pass = 0; pass < 4; ++pass) {
+          const int rl = pass * 8 + sub;
           const int row = m0 + q * 32 + rl;
-          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 36 + l8 * 4);
+          const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + l4 * 4);
           float v[4] = {p.alpha * a.x + bv.x, p.alpha * a.y + bv.y, p.alpha * a.z + bv.z, p.alpha * a.w + bv.w};
           if (row >= p.M || col >= p.N) continue;
           const int64_t o = (int64_t)row * p.ldc + col;
