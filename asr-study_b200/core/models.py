@@ -123,7 +123,7 @@ class CTCModel(object):
         else:
             kw.update(momentum=o.momentum)
         loss = self.engine.train_step(xt, lens, flat, off, mx, global_batch=gb, allreduce=self.allreduce, **kw)
-        dec = self._decode(self.engine._w["logits"], lens)[:N]
+        dec = self._decode(self.engine.last_logits, lens)[:N]
         ctc = float(loss[:N].mean().item())
         reg = self._reg()
         return [ctc + reg, ctc, 0.0, metrics.ler(_label_rows(labels), dec)]

@@ -115,7 +115,7 @@ extern "C" int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H) {
 }
 
 extern "C" int32_t asr_lstm_fuses_variants(int32_t T, int32_t N, int32_t H) {
-  return (H == 512 && asr_lstm_fuses_masks(T, N, H)) ? 1 : 0;
+  return asr_lstm_fuses_masks(T, N, H);
 }
 
 extern "C" int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream) {

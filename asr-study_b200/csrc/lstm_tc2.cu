@@ -694,10 +694,11 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward through time (v3): ONE exchange per step.  H = 512, 16 CTAs per (direction, batch group).
+// backward through time (v3): ONE exchange per step.  H in {128, 256, 384, 512}: H / 32 CTAs per (direction,
+//   batch group); the figures below are for H = 512 (16 CTAs, 4 blocks).
 //   CTA j owns the 32 hidden units [32j, 32j + 32) for the element-wise BPTT step, i.e. the 128 gate columns
-//   {g*H + 32j + i}, and keeps the [512 units x 128 own gate columns] slice of U (bf16) in TMEM as four
-//   M = 128 blocks.  Its own dz_t is the B operand — written to shared memory locally, no gather — and
+//   {g*H + 32j + i}, and keeps the [H units x 128 own gate columns] slice of U (bf16) in TMEM as H / 128
+//   M = 128 blocks (warps >= H / 128 issue no MMA; every warp still sends its lane quarter of every block).  Its own dz_t is the B operand — written to shared memory locally, no gather — and
 //       P_j[u][n] = sum_{k in own columns} U[u][k] * dz_t[n][k]            (4 blocks x 8 TS-mode tcgen05.mma)
 //   is its partial contribution to dh_rec of ALL 512 units.  Warp w of CTA j holds, for block b, the rows of the
 //   units owned by CTA 4b + w and sends them there (reduce-scatter through the LL ring); every CTA sums the 16
@@ -706,12 +707,14 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 //   needs one, with the same wire bytes per CTA as the forward all-gather (partials travel as bf16 pairs — the
 //   operands of the product are bf16 already, see DESIGN.md for the error budget).
 // ------------------------------------------------------------------------------------------------
-template <int NB, bool VAR>
+template <int H, int NB, bool VAR>
 __global__ void __launch_bounds__(THREADS, 1)
 bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int H = 512, K4 = 4 * H, NCTA = H / UPC;
+  constexpr int K4 = 4 * H, NCTA = H / UPC;
+  constexpr int NBLK = H / 128;                          // M = 128 blocks of the U slice = issuing warps
+  static_assert(H % 128 == 0 && NBLK >= 1 && NBLK <= 4, "one M = 128 block of units per issuing warp");
   constexpr int B_CHUNK = NM * 128;                      // one 64-wide K chunk of the B operand
   constexpr int NPT = NB / 4;                            // samples per thread
   constexpr int PPT = NPT / 2;                           // sample pairs per thread
@@ -728,7 +731,7 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
   __shared__ int s_dead;
 
   if (tid == 0) {
-    tc::mbar_init(mma_bar, 4);
+    tc::mbar_init(mma_bar, NBLK);                          // one tcgen05.commit per issuing warp
     tc::fence_mbar_init();
     s_dead = 0;
   }
@@ -743,7 +746,7 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
   // one-time: U slice -> TMEM.  block b, lane m <-> unit 128b + m; K index k = g*32 + i <-> gate column g*H + u0 + i
   {
 #pragma unroll 1
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < NBLK; ++b) {
       const __nv_bfloat16* Ub = reinterpret_cast<const __nv_bfloat16*>(a.U16) + (size_t)dir * H * K4 +
                                 (size_t)(128 * b + tid) * K4 + u0;
 #pragma unroll 1
@@ -876,7 +879,7 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
 #pragma unroll
     for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
     if (s > 0) {
-      // ---- receive: 16 partials (bf16 pairs of two samples) for each of my (unit, sample pair) ----------------
+      // ---- receive: NCTA partials (bf16 pairs of two samples) for each of my (unit, sample pair) --------------
       if (p_t >= 0) side_stores(p_t, p_dz, p_du);   // first: gives the peers' LL words time to land in L2
       const uint32_t tag = (uint32_t)s;
       const uint2* src = xb + ((size_t)((s - 1) & 1) * NCTA + cta) * SLOT + (size_t)(warp * PPT) * NCTA * 32 + lane;
@@ -962,7 +965,7 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
       tc::fence_proxy_async_smem();
       __syncthreads();                                     // the whole B operand (all samples) is staged
       if (s_dead) break;
-      if (tc::elect_one_sync()) {                          // warp w issues M block w (units 128w .. 128w + 127)
+      if (warp < NBLK && tc::elect_one_sync()) {           // warp w issues M block w (units 128w .. 128w + 127)
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {
@@ -979,25 +982,20 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
       PROF(2);
       // ---- send: my warp's rows of block b belong to CTA 4b + warp ----------------------------------------------
       {
-        uint32_t r0[NB], r1[NB], r2[NB], r3[NB];
+        uint32_t rb[NBLK][NB];
         const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
-        tc::tmem_ldn(tq, r0);
-        tc::tmem_ldn(tq + NM, r1);
-        tc::tmem_ldn(tq + 2 * NM, r2);
-        tc::tmem_ldn(tq + 3 * NM, r3);
+#pragma unroll
+        for (int b = 0; b < NBLK; ++b) tc::tmem_ldn(tq + b * NM, rb[b]);
         tc::tmem_ld_wait();
         const uint32_t tg = (uint32_t)(s + 1);
         uint2* out = xb + (size_t)(s & 1) * NCTA * SLOT + (size_t)cta * 32 + lane;      // + dst*SLOT + pair*NCTA*32
 #pragma unroll
         for (int np = 0; np < NP; ++np) {
-          const __nv_bfloat162 q0 = __floats2bfloat162_rn(__uint_as_float(r0[2 * np]), __uint_as_float(r0[2 * np + 1]));
-          const __nv_bfloat162 q1 = __floats2bfloat162_rn(__uint_as_float(r1[2 * np]), __uint_as_float(r1[2 * np + 1]));
-          const __nv_bfloat162 q2 = __floats2bfloat162_rn(__uint_as_float(r2[2 * np]), __uint_as_float(r2[2 * np + 1]));
-          const __nv_bfloat162 q3 = __floats2bfloat162_rn(__uint_as_float(r3[2 * np]), __uint_as_float(r3[2 * np + 1]));
-          st_volatile_v2(out + (size_t)(0 * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q0), tg));
-          st_volatile_v2(out + (size_t)(1 * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q1), tg));
-          st_volatile_v2(out + (size_t)(2 * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q2), tg));
-          st_volatile_v2(out + (size_t)(3 * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q3), tg));
+#pragma unroll
+          for (int b = 0; b < NBLK; ++b) {
+            const __nv_bfloat162 q = __floats2bfloat162_rn(__uint_as_float(rb[b][2 * np]), __uint_as_float(rb[b][2 * np + 1]));
+            st_volatile_v2(out + (size_t)(b * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q), tg));
+          }
         }
       }
       tc::tcgen05_fence_before();
@@ -1045,9 +1043,9 @@ static int group_size(int N, int H) {
 static bool shape_ok(int T, int N, int H) {
   return T >= 1 && (H == 128 || H == 256 || H == 384 || H == 512) && N >= 8 && group_size(N, H) != 0;
 }
-bool shape_supported(int T, int N, int H, bool bwd) { return shape_ok(T, N, H) && (!bwd || H == 512); }
+bool shape_supported(int T, int N, int H, bool) { return shape_ok(T, N, H); }
 bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && (a->h16 || a->hm16) && shape_ok(a->T, a->N, a->H); }
-bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && a->H == 512 && shape_ok(a->T, a->N, a->H); }
+bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && shape_ok(a->T, a->N, a->H); }
 static size_t x1_bytes_per_dg(int NB) { return (size_t)4 * 2 * NB * 256 * sizeof(uint2); }           // hop 1 per (dir, grp)
 static size_t x2_bytes_per_dg(int NB) { return (size_t)4 * 4 * 4 * 2 * NB * 32 * sizeof(uint2); }    // hop 2 per (dir, grp)
 size_t scratch_bytes(int) { return HEADER_BYTES + (size_t)2 * 8 * (x1_bytes_per_dg(16) + x2_bytes_per_dg(16)); }
@@ -1102,12 +1100,13 @@ static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
   return ASR_OK;
 }
 
-template <int NB, bool VAR>
+template <int H, int NB, bool VAR>
 static int32_t launch_bwd3(const asr_lstm_bwd_args* a, cudaStream_t st) {
+  constexpr int NCTA = H / UPC;
   const int G = a->N / NB;
   const size_t smem = exclusive_smem(1024 + (size_t)2 * NM * 128 + 64);
-  const size_t xbytes = (size_t)2 * G * 2 * 16 * (NB / 2) * 16 * 32 * sizeof(uint2);
-  ASR_CUDA(cudaFuncSetAttribute(bwd3_kernel<NB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t xbytes = (size_t)2 * G * 2 * NCTA * (NB / 2) * NCTA * 32 * sizeof(uint2);   // [(dir,grp)][parity][dst][pair][src][unit]
+  ASR_CUDA(cudaFuncSetAttribute(bwd3_kernel<H, NB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + xbytes, st));
   ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));
   if (VAR && a->mi) ASR_CUDA(cudaMemsetAsync(a->dmi, 0, (size_t)3 * 2 * 4 * a->H * sizeof(float), st));
@@ -1115,7 +1114,7 @@ static int32_t launch_bwd3(const asr_lstm_bwd_args* a, cudaStream_t st) {
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
   void* kargs[] = {&args, &flags, &xbuf};
-  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd3_kernel<NB, VAR>, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
+  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd3_kernel<H, NB, VAR>, dim3(NCTA, 2, G), dim3(THREADS), kargs, smem, st));
   asr::count_launch();
   return ASR_OK;
 }
@@ -1125,28 +1124,38 @@ int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
   const char* e = getenv("ASR_LSTM_BWD");
   const bool g8 = group_size(a->N, a->H) == 8;
   const bool var = a->mi != nullptr || a->zoneout > 0.0f;
-  if (var) {
-    ASR_CHECK_ARG(!a->mi || (a->zx && a->uh && a->dmi && a->duhT16), "lstmtc2 backward: MI needs zx, uh, dmi and duhT16");
-    return g8 ? launch_bwd3<8, true>(a, st) : launch_bwd3<16, true>(a, st);
+  if (var) ASR_CHECK_ARG(!a->mi || (a->zx && a->uh && a->dmi && a->duhT16), "lstmtc2 backward: MI needs zx, uh, dmi and duhT16");
+  if (!var && a->H == 512 && e && strcmp(e, "v2") == 0) return g8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
+#define ASR_BWD3_CASE(HH)                                                                             \
+  case HH:                                                                                            \
+    if (var) return g8 ? launch_bwd3<HH, 8, true>(a, st) : launch_bwd3<HH, 16, true>(a, st);          \
+    return g8 ? launch_bwd3<HH, 8, false>(a, st) : launch_bwd3<HH, 16, false>(a, st);
+  switch (a->H) {
+    ASR_BWD3_CASE(128)
+    ASR_BWD3_CASE(256)
+    ASR_BWD3_CASE(384)
+    ASR_BWD3_CASE(512)
   }
-  if (e && strcmp(e, "v2") == 0) return g8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
-  return g8 ? launch_bwd3<8, false>(a, st) : launch_bwd3<16, false>(a, st);
+#undef ASR_BWD3_CASE
+  asr::set_error("lstmtc2: unsupported H=%d", a->H);
+  return ASR_ERR_INVALID;
 }
 
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st) {
   const bool g8 = group_size(a->N, a->H) == 8;
   const bool var = a->mi != nullptr || a->zoneout > 0.0f;
-  if (var) {                                              // the element-wise switches are built for the C2 width
-    ASR_CHECK_ARG(a->H == 512, "lstmtc2 forward: MI / zoneout need H = 512 (got %d)", a->H);
-    ASR_CHECK_ARG(!a->mi || !a->training || a->uh, "lstmtc2 forward: training with MI needs the uh buffer");
-    return g8 ? launch_fwd<512, 8, true>(a, st) : launch_fwd<512, 16, true>(a, st);
-  }
+  if (var) ASR_CHECK_ARG(!a->mi || !a->training || a->uh, "lstmtc2 forward: training with MI needs the uh buffer");
+#define ASR_FWD_CASE(HH)                                                                              \
+  case HH:                                                                                            \
+    if (var) return g8 ? launch_fwd<HH, 8, true>(a, st) : launch_fwd<HH, 16, true>(a, st);            \
+    return g8 ? launch_fwd<HH, 8, false>(a, st) : launch_fwd<HH, 16, false>(a, st);
   switch (a->H) {
-    case 128: return g8 ? launch_fwd<128, 8, false>(a, st) : launch_fwd<128, 16, false>(a, st);
-    case 256: return g8 ? launch_fwd<256, 8, false>(a, st) : launch_fwd<256, 16, false>(a, st);
-    case 384: return g8 ? launch_fwd<384, 8, false>(a, st) : launch_fwd<384, 16, false>(a, st);
-    case 512: return g8 ? launch_fwd<512, 8, false>(a, st) : launch_fwd<512, 16, false>(a, st);
+    ASR_FWD_CASE(128)
+    ASR_FWD_CASE(256)
+    ASR_FWD_CASE(384)
+    ASR_FWD_CASE(512)
   }
+#undef ASR_FWD_CASE
   asr::set_error("lstmtc2: unsupported H=%d", a->H);
   return ASR_ERR_INVALID;
 }

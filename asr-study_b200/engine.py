@@ -318,6 +318,38 @@ class AcousticEngine:
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
         assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
+        # ragged batches (the last batch of an epoch, predict.py's batch of 1): the tensor-core recurrences work on
+        # groups of 8 / 16 samples, so the batch is padded with zero utterances up to the next group boundary.  Utterances
+        # are independent (no batch statistics anywhere on the path) and backward() pads dlogits with zero rows, so
+        # the padding contributes nothing to any gradient; callers only ever see the first N samples.
+        Np = self._padded_batch(T, N)
+        self._pad = (N, Np) if Np != N else None
+        if self._pad:
+            fp = self._buf("feats_pad", (T, Np, Fd), torch.float32)
+            fp[:, :N].copy_(feats_tm)
+            fp[:, N:].zero_()
+            if masks is not None:
+                masks = {l: {k: torch.cat([v, torch.ones(Np - N, v.shape[1], dtype=v.dtype, device=v.device)])
+                             for k, v in m.items()} for l, m in masks.items()}
+            self.last_logits = self._forward(fp, training, masks, zmasks, input_mask)[:, :N].contiguous()
+        else:
+            self.last_logits = self._forward(feats_tm, training, masks, zmasks, input_mask)
+        return self.last_logits
+
+    def _padded_batch(self, T, N):
+        """N itself when the tensor-core engine takes it (or cannot take the model at all); else the next group boundary."""
+        sp = self.spec
+        H = sp.hs[0]
+        if sp.general or lib.asr_lstm_fuses_masks(T, N, H):
+            return N
+        for Np in (_pad8(N), (N + 15) // 16 * 16):
+            if Np != N and lib.asr_lstm_fuses_masks(T, Np, H):
+                return Np
+        return N
+
+    def _forward(self, feats_tm, training, masks, zmasks, input_mask):
+        sp, P = self.spec, self.params
+        T, N, Fd = feats_tm.shape
         # the persistent engines cover the reference's shapes; anything else (e.g. H = 800) runs on the general cell
         self._use_general = (sp.general or not lib.asr_lstm_persistent_supported(T, N, sp.hs[0], int(training))
                              or (sp.elementwise and not lib.asr_lstm_fuses_variants(T, N, sp.hs[0])))
@@ -672,8 +704,8 @@ class AcousticEngine:
         w = self._w
         wsb = lib.asr_ctc_workspace_bytes(T, N, max_label_len)
         ws = self._buf("ctc_ws", (wsb // 4 + 1,), torch.float32)
-        loss = w.get("loss") if "loss" in w else self._buf("loss", (N,), torch.float32)
-        grad = w["dlogits"] if want_grad else self._buf("dlogits", (T, N, Cc), torch.float32)
+        loss = self._buf("loss", (N,), torch.float32)      # shaped by the logits handed in (forward() may have padded)
+        grad = self._buf("dlogits", (T, N, Cc), torch.float32)
         lib.asr_ctc_loss_grad(ptr(logits), T, N, Cc, ptr(in_len), ptr(labels_flat), ptr(label_off), max_label_len,
                               Cc - 1, float(grad_scale), ptr(loss), ptr(grad), ptr(ws), cur_stream())
         return loss, grad
@@ -712,6 +744,12 @@ class AcousticEngine:
         Returns the handles (objects with .wait()) the callable returned, if any."""
         sp, P, w = self.spec, self.params, self._w
         handles = []
+        if getattr(self, "_pad", None):                 # forward() padded the batch: zero gradient rows for the padding
+            n, npad = self._pad
+            dl = self._buf("dlogits_pad", (dlogits.shape[0], npad, dlogits.shape[2]), torch.float32)
+            dl[:, :n].copy_(dlogits)
+            dl[:, n:].zero_()
+            dlogits = dl
         if self._use_general:
             self._backward_general(dlogits)
             if allreduce is not None:

@@ -70,6 +70,44 @@ def test_train_step_gradients_and_adam_parity(N, T, F, H, L):
         np.testing.assert_allclose(newp[k], p0[k], atol=2e-6)
 
 
+@pytest.mark.parametrize("N,T,F,H,L,dropout", [(13, 18, 26, 256, 2, True), (5, 12, 26, 512, 1, False), (40, 10, 26, 512, 1, False)])
+def test_ragged_batch_is_padded_onto_the_tensor_core_engine(N, T, F, H, L, dropout):
+    """A batch that is not a whole number of 8 / 16-sample groups (the last batch of an epoch) is padded with zero
+    utterances inside the engine and still runs on the tensor-core recurrences; loss, logits, decode and every
+    gradient are those of the N real utterances (the padding contributes exactly nothing)."""
+    from asr_study_b200._lib import lib
+    C = 28
+    eng, params, x, lens, labels, pack = _setup(N, T, F, H, L, C, seed=3 * N + T)
+    assert lib.asr_lstm_fuses_masks(T, N, H) == 0 and eng._padded_batch(T, N) > N
+    masks_np = masks_dev = None
+    if dropout:
+        rng = np.random.RandomState(9)
+        masks_np, D = {}, F
+        for l in range(L):
+            masks_np[l] = {k: ((rng.rand(N, w) >= 0.2) / 0.8).astype(np.float32) for k, w in (("Wf", D), ("Wb", D), ("Uf", H), ("Ub", H))}
+            D = 2 * H
+        masks_dev = {l: {k: dev(v) for k, v in m.items()} for l, m in masks_np.items()}
+    flat, off, mx = pack(labels, "cuda")
+    feats = dev(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    loss = eng.train_step(feats, dev(lens), flat, off, mx, masks=masks_dev, lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    assert eng.lstm_status() == 0 and not eng._use_general and eng._pad == (N, eng._padded_batch(T, N))
+    assert loss.shape == (N,) and eng.last_logits.shape == (T, N, C)
+    _, ctc, grads, ref_logits = om.loss_and_grads(params, x, lens, labels, masks=masks_np, weight_decay=0.0, dtype=np.float64)
+    assert norm_err(eng.last_logits.cpu().numpy().transpose(1, 0, 2), ref_logits) < 1e-3
+    np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
+    got = eng.params.export("grad")
+    for k, g in grads.items():
+        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+    logits = eng.forward(feats, training=False)
+    assert logits.shape == (T, N, C) and logits.is_contiguous()
+    out, out_len = eng.greedy(logits, dev(lens))
+    ref_dec = oc.greedy_decode(logits.cpu().numpy().transpose(1, 0, 2), lens)
+    out, out_len = out.cpu().numpy(), out_len.cpu().numpy()
+    for n in range(N):
+        assert out[n, :out_len[n]].tolist() == ref_dec[n]
+
+
 def test_clipnorm_engages():
     C = 28
     eng, params, x, lens, labels, pack = _setup(8, 20, 26, 64, 1, C, seed=3, wd=0.0)
@@ -84,7 +122,8 @@ def test_clipnorm_engages():
         np.testing.assert_allclose(newp[k], p0[k], atol=2e-6)
 
 
-@pytest.mark.parametrize("N,T,F,H,L", [(8, 20, 26, 64, 2), (16, 24, 26, 512, 2)])
+@pytest.mark.parametrize("N,T,F,H,L", [(8, 20, 26, 64, 2), (16, 24, 26, 512, 2), (24, 18, 26, 256, 3), (8, 21, 26, 384, 2),
+                                       (16, 16, 26, 128, 2)])
 def test_variational_dropout_forward_backward_parity(N, T, F, H, L):
     """dropout_W / dropout_U masks (per sample, constant over time; core/layers.py:438-439, core/models.py:265-266)
     with the SAME masks on both sides: logits, loss and every parameter gradient vs the oracle."""
@@ -253,13 +292,15 @@ def test_eyben_heterogeneous_stack_parity():
         assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
 
 
+@pytest.mark.parametrize("H", [512, 256, 384, 128])
 @pytest.mark.parametrize("sw", [dict(mi=(1.0, 0.5, 0.5)), dict(zoneout=0.2), dict(mi=(1.0, 0.5, 0.5), zoneout=0.15, dropout=0.2)])
-def test_elementwise_switches_on_the_tensor_core_engine(sw):
-    """MI / zoneout at the C2 width run as a template switch of the tensor-core recurrences (lstm_tc2.cu), not on the
-    general cell: whole train step vs the fp64 oracle with the same masks, then the inference blend."""
+def test_elementwise_switches_on_the_tensor_core_engine(sw, H):
+    """MI / zoneout at the tensor-core widths (H in 128..512) run as a template switch of the tensor-core recurrences
+    (lstm_tc2.cu), not on the general cell: whole train step vs the fp64 oracle with the same masks, then the
+    inference blend."""
     from asr_study_b200._lib import lib
     from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
-    N, T, F, H, L, C = 8, 20, 26, 512, 2, 28
+    N, T, F, L, C = 8, 20, 26, 2, 28
     assert lib.asr_lstm_fuses_variants(T, N, H) == 1
     rng = np.random.RandomState(23)
     spec = ModelSpec(F, H, L, C, dropout=sw.get("dropout", 0.0), zoneout=sw.get("zoneout", 0.0), mi=sw.get("mi"))

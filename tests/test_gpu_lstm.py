@@ -154,7 +154,8 @@ def test_full_length_sequence_T999_stability():
     assert norm_err(h, ref) < 1e-4
 
 
-TC_SHAPES = [(16, 12, 26, 64), (16, 25, 20, 256), (32, 40, 26, 512), (48, 7, 26, 128)]
+TC_SHAPES = [(16, 12, 26, 64), (16, 25, 20, 256), (32, 40, 26, 512), (48, 7, 26, 128), (24, 15, 26, 384), (64, 9, 26, 256),
+             (96, 6, 26, 128)]
 
 
 @pytest.mark.parametrize("N,T,D,H", TC_SHAPES)
