@@ -213,8 +213,7 @@ class CTCModel(object):
         P = m.engine.params
         P.load(blob["params"])
         for name in ("m", "v"):
-            for k, val in blob[name].items():
-                P._view(getattr(P, name), k).copy_(torch.as_tensor(val))
+            P.load(blob[name], which=name)
         m.engine.step_count = blob["step"]
         o = blob["optimizer"]
         m.optimizer = Adam(o["lr"], o["beta_1"], o["beta_2"], o["epsilon"], o["clipnorm"]) if o["kind"] == "adam" \

@@ -694,8 +694,10 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward through time (v3): ONE exchange per step.  H in {128, 256, 384, 512}: H / 32 CTAs per (direction,
-//   batch group); the figures below are for H = 512 (16 CTAs, 4 blocks).
+// backward through time (v3): ONE exchange per step.  H a multiple of 64 up to 896: H / 32 CTAs per (direction,
+//   batch group); the figures below are for H = 512 (16 CTAs, 4 blocks).  Wider layers (5 to 7 blocks: the U slice
+//   fills 448 of the 512 TMEM columns, which leaves room for four accumulators) run the product in two rounds of
+//   at most four blocks; the rows of a last half block (H = 832) beyond H are zero and are never sent.
 //   CTA j owns the 32 hidden units [32j, 32j + 32) for the element-wise BPTT step, i.e. the 128 gate columns
 //   {g*H + 32j + i}, and keeps the [H units x 128 own gate columns] slice of U (bf16) in TMEM as H / 128
 //   M = 128 blocks (warps >= H / 128 issue no MMA; every warp still sends its lane quarter of every block).  Its own dz_t is the B operand — written to shared memory locally, no gather — and
@@ -713,8 +715,9 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int K4 = 4 * H, NCTA = H / UPC;
-  constexpr int NBLK = H / 128;                          // M = 128 blocks of the U slice = issuing warps
-  static_assert(H % 128 == 0 && NBLK >= 1 && NBLK <= 4, "one M = 128 block of units per issuing warp");
+  constexpr int NBLK = (H + 127) / 128;                  // M = 128 blocks of the U slice
+  constexpr int NR = (NBLK + 3) / 4;                     // rounds of <= 4 blocks (one issuing warp, one accumulator each)
+  static_assert(H % 64 == 0 && NBLK >= 1 && NBLK <= 7, "U slice: NBLK x 64 TMEM columns beside four accumulators");
   constexpr int B_CHUNK = NM * 128;                      // one 64-wide K chunk of the B operand
   constexpr int NPT = NB / 4;                            // samples per thread
   constexpr int PPT = NPT / 2;                           // sample pairs per thread
@@ -726,12 +729,13 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
   const int u0 = cta * UPC, n0 = grp * NB;
 
   uint8_t* sB = smem;                                    // 2 chunks of [NM rows x 128 B]: K = 128 own gate columns
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sB + 2 * B_CHUNK);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sB + 2 * B_CHUNK);      // one per round
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 2);
   __shared__ int s_dead;
 
   if (tid == 0) {
-    tc::mbar_init(mma_bar, NBLK);                          // one tcgen05.commit per issuing warp
+    tc::mbar_init(mma_bar, NBLK < 4 ? NBLK : 4);           // one tcgen05.commit per issuing warp
+    if constexpr (NR > 1) tc::mbar_init(mma_bar + 1, (uint32_t)(NBLK - 4));
     tc::fence_mbar_init();
     s_dead = 0;
   }
@@ -747,8 +751,9 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
   {
 #pragma unroll 1
     for (int b = 0; b < NBLK; ++b) {
+      const bool row_ok = 128 * b + tid < H;             // a last half block: the rows beyond H are zero
       const __nv_bfloat16* Ub = reinterpret_cast<const __nv_bfloat16*>(a.U16) + (size_t)dir * H * K4 +
-                                (size_t)(128 * b + tid) * K4 + u0;
+                                (size_t)(row_ok ? 128 * b + tid : 0) * K4 + u0;
 #pragma unroll 1
       for (int hs = 0; hs < 2; ++hs) {                   // two gates (64 K elements = 32 columns) per tcgen05.st
         uint32_t rr[32];
@@ -757,7 +762,7 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
           const uint4* src = reinterpret_cast<const uint4*>(Ub + (2 * hs + gg) * H);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 v = __ldg(src + q);
+            const uint4 v = row_ok ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
             rr[gg * 16 + 4 * q] = v.x; rr[gg * 16 + 4 * q + 1] = v.y; rr[gg * 16 + 4 * q + 2] = v.z; rr[gg * 16 + 4 * q + 3] = v.w;
           }
         }
@@ -965,36 +970,46 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
       tc::fence_proxy_async_smem();
       __syncthreads();                                     // the whole B operand (all samples) is staged
       if (s_dead) break;
-      if (warp < NBLK && tc::elect_one_sync()) {           // warp w issues M block w (units 128w .. 128w + 127)
-        tc::tcgen05_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {
-          const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-          tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL + warp * 64 + kb * 8, bd, idesc, kb > 0);
+      for (int r = 0; r < NR; ++r) {
+        constexpr int B0[2] = {0, 4};
+        const int b0 = B0[r], cnt = (NBLK - b0 < 4) ? NBLK - b0 : 4;       // blocks b0 .. b0 + cnt - 1 in this round
+        if (r > 0) {                                         // every warp has read the accumulators of the previous round
+          tc::tcgen05_fence_before();
+          __syncthreads();
         }
-        tc::umma_commit(mma_bar);
-      }
-      if (!tc::mbar_wait(mma_bar, (uint32_t)(s & 1), WATCHDOG_CYCLES)) {
-        atomicExch(status, 1);
-        s_dead = 1;
-      }
-      tc::tcgen05_fence_after();
-      PROF(2);
-      // ---- send: my warp's rows of block b belong to CTA 4b + warp ----------------------------------------------
-      {
-        uint32_t rb[NBLK][NB];
+        if (warp < cnt && tc::elect_one_sync()) {            // warp w issues M block b0 + w (units 128 (b0 + w) ..)
+          tc::tcgen05_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
+            tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL + (b0 + warp) * 64 + kb * 8, bd, idesc, kb > 0);
+          }
+          tc::umma_commit(mma_bar + r);
+        }
+        if (!tc::mbar_wait(mma_bar + r, (uint32_t)(s & 1), WATCHDOG_CYCLES)) {
+          atomicExch(status, 1);
+          s_dead = 1;
+        }
+        tc::tcgen05_fence_after();
+        if (r == 0) PROF(2);
+        // ---- send: my warp's rows of block b belong to CTA 4b + warp --------------------------------------------
+        uint32_t rb[4][NB];
         const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
 #pragma unroll
-        for (int b = 0; b < NBLK; ++b) tc::tmem_ldn(tq + b * NM, rb[b]);
+        for (int b = 0; b < 4; ++b)
+          if (b < cnt) tc::tmem_ldn(tq + b * NM, rb[b]);
         tc::tmem_ld_wait();
         const uint32_t tg = (uint32_t)(s + 1);
         uint2* out = xb + (size_t)(s & 1) * NCTA * SLOT + (size_t)cta * 32 + lane;      // + dst*SLOT + pair*NCTA*32
 #pragma unroll
         for (int np = 0; np < NP; ++np) {
 #pragma unroll
-          for (int b = 0; b < NBLK; ++b) {
-            const __nv_bfloat162 q = __floats2bfloat162_rn(__uint_as_float(rb[b][2 * np]), __uint_as_float(rb[b][2 * np + 1]));
-            st_volatile_v2(out + (size_t)(b * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q), tg));
+          for (int b = 0; b < 4; ++b) {
+            if (b < cnt && (H % 128 == 0 || (b0 + b) * 4 + warp < NCTA)) {     // a last half block has two destinations
+              const __nv_bfloat162 q = __floats2bfloat162_rn(__uint_as_float(rb[b][2 * np]), __uint_as_float(rb[b][2 * np + 1]));
+              st_volatile_v2(out + (size_t)((b0 + b) * 4 + warp) * SLOT + (size_t)np * NCTA * 32, make_uint2(*reinterpret_cast<const uint32_t*>(&q), tg));
+            }
           }
         }
       }
@@ -1040,15 +1055,23 @@ static int group_size(int N, int H) {
   if (N % 16 == 0 && N / 16 <= 8 && (H / UPC) * 2 * (N / 16) <= 148) return 16;
   return 0;
 }
-static bool shape_ok(int T, int N, int H) {
-  return T >= 1 && (H == 128 || H == 256 || H == 384 || H == 512) && N >= 8 && group_size(N, H) != 0;
+// widths with an instantiation: the U^T slice of the forward kernel needs H / 2 TMEM columns beside 64 of accumulators
+// (H <= 896), the U slice of the BPTT kernel ceil(H / 128) x 64 columns (<= 448).  Other widths are zero-padded up to
+// the next of these by the host engine (engine.py: padded units stay exactly zero in both passes).
+static bool width_ok(int H) {
+  return H == 128 || H == 256 || H == 384 || H == 512 || H == 640 || H == 768 || H == 832 || H == 896;
 }
+static bool shape_ok(int T, int N, int H) { return T >= 1 && width_ok(H) && N >= 8 && group_size(N, H) != 0; }
 bool shape_supported(int T, int N, int H, bool) { return shape_ok(T, N, H); }
 bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && (a->h16 || a->hm16) && shape_ok(a->T, a->N, a->H); }
 bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && shape_ok(a->T, a->N, a->H); }
 static size_t x1_bytes_per_dg(int NB) { return (size_t)4 * 2 * NB * 256 * sizeof(uint2); }           // hop 1 per (dir, grp)
 static size_t x2_bytes_per_dg(int NB) { return (size_t)4 * 4 * 4 * 2 * NB * 32 * sizeof(uint2); }    // hop 2 per (dir, grp)
-size_t scratch_bytes(int) { return HEADER_BYTES + (size_t)2 * 8 * (x1_bytes_per_dg(16) + x2_bytes_per_dg(16)); }
+size_t scratch_bytes(int) {                              // the largest ring any launch clears: bwd3 at H = 896, NB = 16, G = 2
+  const size_t v2 = (size_t)2 * 8 * (x1_bytes_per_dg(16) + x2_bytes_per_dg(16));
+  const size_t v3 = (size_t)2 * 2 * 2 * 28 * 8 * 28 * 32 * sizeof(uint2);
+  return HEADER_BYTES + (v2 > v3 ? v2 : v3);
+}
 
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -1135,6 +1158,10 @@ int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
     ASR_BWD3_CASE(256)
     ASR_BWD3_CASE(384)
     ASR_BWD3_CASE(512)
+    ASR_BWD3_CASE(640)
+    ASR_BWD3_CASE(768)
+    ASR_BWD3_CASE(832)
+    ASR_BWD3_CASE(896)
   }
 #undef ASR_BWD3_CASE
   asr::set_error("lstmtc2: unsupported H=%d", a->H);
@@ -1154,6 +1181,10 @@ int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st) {
     ASR_FWD_CASE(256)
     ASR_FWD_CASE(384)
     ASR_FWD_CASE(512)
+    ASR_FWD_CASE(640)
+    ASR_FWD_CASE(768)
+    ASR_FWD_CASE(832)
+    ASR_FWD_CASE(896)
   }
 #undef ASR_FWD_CASE
   asr::set_error("lstmtc2: unsupported H=%d", a->H);

@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import dataclasses
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -27,6 +28,38 @@ OUT_F32, OUT_F16, OUT_BF16 = 0, 1, 2
 
 def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
+
+
+TC_WIDTHS = (128, 256, 384, 512, 640, 768, 832, 896)     # widths the tensor-core recurrences are instantiated for
+
+
+def tc_width(H: int) -> int:
+    """The width the tensor-core recurrences run a layer of H units at: H itself when instantiated, else the next
+    instantiated width (the extra units are zero-padded: see ParamBucket).  Narrow layers (H <= 128, e.g. the
+    BiLSTM-100 of graves2006) and layers wider than 896 are left alone (fp32 persistent / general-cell engines)."""
+    if H <= 128 or H > TC_WIDTHS[-1] or H in TC_WIDTHS:
+        return H
+    return next(w for w in TC_WIDTHS if w >= H)
+
+
+def _pad_blocks(a: np.ndarray, axis: int, blocks: int, H: int, Hp: int) -> np.ndarray:
+    """axis = `blocks` consecutive blocks of H -> blocks of Hp, zero-filled behind each block."""
+    shp = list(a.shape)
+    assert shp[axis] == blocks * H
+    out = np.zeros(shp[:axis] + [blocks, Hp] + shp[axis + 1:], a.dtype)
+    idx = [slice(None)] * out.ndim
+    idx[axis + 1] = slice(0, H)
+    out[tuple(idx)] = a.reshape(shp[:axis] + [blocks, H] + shp[axis + 1:])
+    return out.reshape(shp[:axis] + [blocks * Hp] + shp[axis + 1:])
+
+
+def _unpad_blocks(a: np.ndarray, axis: int, blocks: int, H: int, Hp: int) -> np.ndarray:
+    shp = list(a.shape)
+    assert shp[axis] == blocks * Hp
+    idx = [slice(None)] * (a.ndim + 1)
+    idx[axis + 1] = slice(0, H)
+    v = a.reshape(shp[:axis] + [blocks, Hp] + shp[axis + 1:])[tuple(idx)]
+    return np.ascontiguousarray(v).reshape(shp[:axis] + [blocks * H] + shp[axis + 1:])
 
 
 @dataclass
@@ -78,10 +111,16 @@ class ParamBucket:
 
     Per layer the order is Wf, Wb, Uf, Ub, bf, bb so that [Uf|Ub] is a contiguous
     [2,H,4H] block and [bf|bb] a contiguous [2,4H] block (what the kernels take).
+
+    `logical_h` (optional): the model's own width when `spec` is the zero-padded device spec (tc_width): load() pads
+    every tensor per gate / per direction block, export() cuts the padding off again.  A padded unit has W = U = b = 0,
+    so z = 0, i = f = o = 0.5, g = 0, c = h = 0 at every step, its dz is 0 in BPTT and every gradient, Adam moment and
+    l2 term that touches it stays exactly 0: the padded model IS the logical model.
     """
 
-    def __init__(self, spec: ModelSpec, device):
+    def __init__(self, spec: ModelSpec, device, logical_h: int | None = None):
         self.spec = spec
+        self.logical_h = logical_h if (logical_h and logical_h != spec.num_hiddens) else None
         C = spec.num_classes
         shapes = []
         D = spec.num_features
@@ -125,26 +164,59 @@ class ParamBucket:
     def g(self, k):
         return self._view(self.grad, k)
 
-    def load(self, params: dict):
+    def _blocks(self, k):
+        """(axis, number of H-wide blocks) pairs of tensor k that carry the hidden width."""
+        if k == "dense.W":
+            return [(0, 2)]
+        if not k.startswith("l") or "." not in k:
+            return []
+        l, n = k.split(".", 1)
+        if n in ("Wf", "Wb"):
+            return [(1, 4)] + ([(0, 2)] if int(l[1:]) > 0 else [])
+        if n in ("Uf", "Ub"):
+            return [(0, 1), (1, 4)]
+        if n in ("bf", "bb"):
+            return [(0, 4)]
+        if n.startswith("mi_"):
+            return [(1, 4)]
+        raise KeyError(k)
+
+    def load(self, params: dict, which="flat"):
         for k, v in params.items():
-            self.p(k).copy_(torch.as_tensor(np.asarray(v, dtype=np.float32)))
+            v = np.asarray(v, dtype=np.float32)
+            if self.logical_h:
+                for axis, blocks in self._blocks(k):
+                    v = _pad_blocks(v, axis, blocks, self.logical_h, self.spec.num_hiddens)
+            self._view(getattr(self, which), k).copy_(torch.as_tensor(v))
 
     def export(self, which="flat") -> dict:
         src = getattr(self, which)
-        return {k: self._view(src, k).detach().cpu().numpy().copy() for k in self.shapes}
+        out = {k: self._view(src, k).detach().cpu().numpy().copy() for k in self.shapes}
+        if self.logical_h:
+            for k in out:
+                for axis, blocks in self._blocks(k):
+                    out[k] = _unpad_blocks(out[k], axis, blocks, self.logical_h, self.spec.num_hiddens)
+        return out
 
 
 class AcousticEngine:
     """Forward / backward / optimiser step for one rank."""
 
     def __init__(self, spec: ModelSpec, device="cuda:0", seed=4321, init_params: dict | None = None):
+        # widths without a tensor-core instantiation (e.g. the BiLSTM-800 of BASELINE config 4) run zero-padded at the
+        # next instantiated width; self.spec is the device spec, self.user_spec the model's own
+        self.user_spec = spec
+        Hl = spec.num_hiddens
+        if not spec.general and not spec.layer_hiddens and tc_width(Hl) != Hl and os.environ.get("ASR_B200_PAD_WIDTH", "1") != "0":
+            spec = dataclasses.replace(spec, num_hiddens=tc_width(Hl))
         self.spec = spec
+        self.logical_h = Hl if spec.num_hiddens != Hl else None
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         lib.load()
-        self.params = ParamBucket(spec, self.device)
+        self.params = ParamBucket(spec, self.device, logical_h=self.logical_h)
         if init_params is None:
-            init_params = self.keras_init(spec, seed)
+            init_params = self.keras_init(self.user_spec, seed)
         self.params.load(init_params)
         self.step_count = 0
         self._ws = {}
@@ -322,6 +394,8 @@ class AcousticEngine:
         # groups of 8 / 16 samples, so the batch is padded with zero utterances up to the next group boundary.  Utterances
         # are independent (no batch statistics anywhere on the path) and backward() pads dlogits with zero rows, so
         # the padding contributes nothing to any gradient; callers only ever see the first N samples.
+        if self.logical_h:                              # zero-padded width: widen caller-supplied masks (values irrelevant)
+            masks, zmasks = self._widen_masks(masks, zmasks)
         Np = self._padded_batch(T, N)
         self._pad = (N, Np) if Np != N else None
         if self._pad:
@@ -335,6 +409,24 @@ class AcousticEngine:
         else:
             self.last_logits = self._forward(feats_tm, training, masks, zmasks, input_mask)
         return self.last_logits
+
+    def _widen_masks(self, masks, zmasks):
+        H, Hp = self.logical_h, self.spec.num_hiddens
+
+        def widen(v, axis, blocks):
+            if v.shape[axis] != blocks * H:
+                return v                                # layer-0 input masks [N, F], or already device-width
+            shp = list(v.shape)
+            out = torch.ones(shp[:axis] + [blocks, Hp] + shp[axis + 1:], dtype=v.dtype, device=v.device)
+            out.narrow(axis + 1, 0, H).copy_(v.reshape(shp[:axis] + [blocks, H] + shp[axis + 1:]))
+            return out.reshape(shp[:axis] + [blocks * Hp] + shp[axis + 1:])
+
+        if masks is not None:
+            masks = {l: {k: (widen(v, 1, 1) if k in ("Uf", "Ub") else widen(v, 1, 2) if (k in ("Wf", "Wb") and l > 0) else v)
+                         for k, v in m.items() if k in ("Wf", "Wb", "Uf", "Ub")} for l, m in masks.items()}
+        if zmasks is not None:
+            zmasks = {l: {k: widen(v, v.dim() - 1, 1) for k, v in m.items()} for l, m in zmasks.items()}
+        return masks, zmasks
 
     def _padded_batch(self, T, N):
         """N itself when the tensor-core engine takes it (or cannot take the model at all); else the next group boundary."""

@@ -230,13 +230,19 @@ def test_brsmv1_switches_train_step_parity(sw):
     assert norm_err(logits_eval, ref_eval) < 1e-3
 
 
-def test_config4_stack_blstm800_logfbank40_on_general_cell():
+@pytest.mark.parametrize("pad_width", [True, False])
+def test_config4_stack_blstm800_logfbank40(pad_width, monkeypatch):
     """BASELINE config 4 recurrent stack (5 x BiLSTM-800 on 40 log-mel features; the DS2-style conv front end is not
-    in the reference) at a small T/N: no persistent engine takes H = 800, the engine routes to the general cell."""
+    in the reference) at a small T/N.  No kernel is instantiated for H = 800: the engine zero-pads the layers to 832
+    units (26 CTAs per chain, seven U blocks in two MMA rounds) and runs the tensor-core recurrences; with
+    ASR_B200_PAD_WIDTH=0 it routes to the general cell instead.  Same parity bars either way, and the exported
+    parameters / gradients have the model's own shapes."""
     from asr_study_b200._lib import lib
     from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
+    monkeypatch.setenv("ASR_B200_PAD_WIDTH", "1" if pad_width else "0")
     N, T, F, H, L, C = 16, 12, 40, 800, 5, 28
     assert lib.asr_lstm_persistent_supported(T, N, H, 1) == 0 and lib.asr_lstm_persistent_supported(999, 32, 512, 1) == 1
+    assert lib.asr_lstm_fuses_masks(T, N, 832) == 1
     from oracle import lstm as ol
     rng = np.random.RandomState(4)
     params, D = {}, F                        # scaled-normal U instead of the orthogonal init: ten 800 x 3200 SVDs take minutes
@@ -254,11 +260,72 @@ def test_config4_stack_blstm800_logfbank40_on_general_cell():
     flat, off, mx = pack_labels(labels, "cuda")
     loss = eng.train_step(dev(np.ascontiguousarray(x.transpose(1, 0, 2))), dev(lens), flat, off, mx, lr=1e-3, clipnorm=400.0)
     torch.cuda.synchronize()
+    assert eng.lstm_status() == 0 and eng._use_general == (not pad_width) and eng.spec.num_hiddens == (832 if pad_width else 800)
     _, ctc, grads, ref_logits = om.loss_and_grads(params, x, lens, labels, dtype=np.float64)
     assert norm_err(eng._w["logits"].cpu().numpy().transpose(1, 0, 2), ref_logits) < 1e-3
     np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
     got = eng.params.export("grad")
     for k, g in grads.items():
+        assert got[k].shape == g.shape
+        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+    if pad_width:                                    # the padding stays exactly zero through the optimiser step
+        P = eng.params
+        for k in ("l1.Wf", "l0.Uf", "l2.bb", "dense.W"):
+            full, cut = P.p(k).cpu().numpy(), P.export("flat")[k]
+            assert abs(np.abs(full).sum() - np.abs(cut).sum()) <= 1e-6 * np.abs(cut).sum()
+
+
+@pytest.mark.parametrize("H,N,T,L,sw", [(200, 8, 14, 2, dict(dropout=0.2)), (320, 16, 10, 2, dict(mi=(1.0, 0.5, 0.5), zoneout=0.1)),
+                                        (640, 8, 9, 1, dict(dropout=0.2)), (800, 32, 8, 1, dict(dropout=0.2, zoneout=0.1)),
+                                        (896, 8, 8, 1, dict())])
+def test_zero_padded_widths_on_the_tensor_core_engine(H, N, T, L, sw):
+    """Widths without an instantiation (200 -> 256, 320 -> 384, 800 -> 832) and the wide instantiations (640: five U
+    blocks, 896: seven) incl. the 16-sample groups (N = 32 at 26 CTAs per chain), with the brsmv1 switches and
+    caller-supplied masks of the MODEL's width: whole train step vs the fp64 oracle."""
+    from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels, tc_width
+    F, C = 26, 28
+    rng = np.random.RandomState(H + N)
+    spec = ModelSpec(F, H, L, C, dropout=sw.get("dropout", 0.0), zoneout=sw.get("zoneout", 0.0), mi=sw.get("mi"))
+    from oracle import lstm as ol
+    params, D = {}, F
+    for l in range(L):
+        for d in "fb":
+            params[f"l{l}.W{d}"] = ol.glorot_uniform(rng, (D, 4 * H))
+            params[f"l{l}.U{d}"] = (rng.randn(H, 4 * H) / np.sqrt(H)).astype(np.float32)
+            params[f"l{l}.b{d}"] = (np.concatenate([np.zeros(H), np.ones(H), np.zeros(2 * H)]) + 0.05 * rng.randn(4 * H)).astype(np.float32)
+        if spec.mi is not None:
+            for n, k in zip(("mi_alpha", "mi_beta1", "mi_beta2"), spec.mi):
+                params[f"l{l}.{n}"] = (k + 0.05 * rng.randn(2, 4 * H)).astype(np.float32)
+        D = 2 * H
+    params["dense.W"], params["dense.b"] = ol.glorot_uniform(rng, (D, C)), np.zeros(C, np.float32)
+    eng = AcousticEngine(spec, init_params=params)
+    assert eng.spec.num_hiddens == tc_width(H) and set(eng.params.shapes) == set(params)
+    x = rng.randn(N, T, F).astype(np.float32)
+    lens = np.full(N, T, np.int32)
+    labels = [rng.randint(0, C - 1, size=rng.randint(2, 4)).astype(np.int32) for _ in range(N)]
+    masks_np = zm_np = None
+    if spec.dropout:
+        masks_np, D = {}, F
+        for l in range(L):
+            masks_np[l] = {k: ((rng.rand(N, w) >= 0.2) / 0.8).astype(np.float32) for k, w in (("Wf", D), ("Wb", D), ("Uf", H), ("Ub", H))}
+            D = 2 * H
+    if spec.zoneout:
+        zm_np = {l: {k + d: (rng.rand(T, H) >= spec.zoneout).astype(np.float32) for k in "hc" for d in "fb"} for l in range(L)}
+    masks_dev = None if masks_np is None else {l: {k: dev(v) for k, v in m.items()} for l, m in masks_np.items()}
+    zm_dev = None if zm_np is None else {l: {k: dev(np.stack([m[k + "f"], m[k + "b"]])) for k in "hc"} for l, m in zm_np.items()}
+    flat, off, mx = pack_labels(labels, "cuda")
+    feats = dev(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    loss = eng.train_step(feats, dev(lens), flat, off, mx, masks=masks_dev, zmasks=zm_dev, lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    assert eng.lstm_status() == 0 and not eng._use_general
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    _, ctc, grads, ref_logits = om.loss_and_grads_general(p64, x, lens, labels, masks=masks_np, zoneout=spec.zoneout, zmasks=zm_np)
+    assert norm_err(eng.last_logits.cpu().numpy().transpose(1, 0, 2), ref_logits) < 1e-3
+    np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
+    got = eng.params.export("grad")
+    assert set(got) == set(grads)
+    for k, g in grads.items():
+        assert got[k].shape == g.shape
         assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
 
 
