@@ -71,7 +71,7 @@ __device__ __forceinline__ void st_volatile_v2(uint2* p, uint2 v) {
 // z = alpha*Wx*Uh + beta1*Uh + beta2*Wx + b and zoneout on c and h; off in the default instantiation.
 template <int H, int NB, bool VAR>
 __global__ void __launch_bounds__(THREADS, 1)
-fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf, int delay1) {
+fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf, int delay1, int grp0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int KC = H / 64;
@@ -82,7 +82,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   const int T = a.T, N = a.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
-  const int u0 = cta * UPC, n0 = grp * NB;
+  const int u0 = cta * UPC, n0 = (grp0 + grp) * NB;      // grp0: first batch group of this launch (large batches: several launches)
 
   uint8_t* sB = smem;                                    // KC chunks of [NM rows x 128 B], SW128 K-major
   float* sZ = reinterpret_cast<float*>(sB + KC * B_CHUNK);   // [4 gates][NB][32 units]
@@ -711,7 +711,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 // ------------------------------------------------------------------------------------------------
 template <int H, int NB, bool VAR>
 __global__ void __launch_bounds__(THREADS, 1)
-bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf) {
+bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf, int grp0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int K4 = 4 * H, NCTA = H / UPC;
@@ -726,7 +726,7 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
   const int T = a.T, N = a.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
-  const int u0 = cta * UPC, n0 = grp * NB;
+  const int u0 = cta * UPC, n0 = (grp0 + grp) * NB;
 
   uint8_t* sB = smem;                                    // 2 chunks of [NM rows x 128 B]: K = 128 own gate columns
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sB + 2 * B_CHUNK);      // one per round
@@ -1047,13 +1047,16 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
 }
 
 // ---- host ---------------------------------------------------------------------------------------
-// samples per CTA group: 8 when that still fits one cooperative wave (more SMs, half the exchange per CTA), else 16
+// batch groups one cooperative launch holds: every CTA owns its SM
+static int max_groups(int H) { return 148 / (2 * (H / UPC)); }
+// samples per CTA group: 8 when the batch then still fits one cooperative wave (more SMs, half the exchange per CTA),
+// else 16; a batch of more than max_groups() groups runs as several launches over consecutive groups (grp0)
 static int group_size(int N, int H) {
   const char* e = getenv("ASR_LSTM_GROUP");
   if (e && atoi(e) == 16) return (N % 16 == 0) ? 16 : 0;
-  if (N % 8 == 0 && N / 8 <= 8 && (H / UPC) * 2 * (N / 8) <= 148) return 8;
-  if (N % 16 == 0 && N / 16 <= 8 && (H / UPC) * 2 * (N / 16) <= 148) return 16;
-  return 0;
+  if (N % 8 == 0 && N / 8 <= max_groups(H)) return 8;
+  if (N % 16 == 0) return 16;
+  return (N % 8 == 0) ? 8 : 0;
 }
 // widths with an instantiation: the U^T slice of the forward kernel needs H / 2 TMEM columns beside 64 of accumulators
 // (H <= 896), the U slice of the BPTT kernel ceil(H / 128) x 64 columns (<= 448).  Other widths are zero-padded up to
@@ -1067,10 +1070,23 @@ bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && (a->h16 || a->h
 bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && shape_ok(a->T, a->N, a->H); }
 static size_t x1_bytes_per_dg(int NB) { return (size_t)4 * 2 * NB * 256 * sizeof(uint2); }           // hop 1 per (dir, grp)
 static size_t x2_bytes_per_dg(int NB) { return (size_t)4 * 4 * 4 * 2 * NB * 32 * sizeof(uint2); }    // hop 2 per (dir, grp)
-size_t scratch_bytes(int) {                              // the largest ring any launch clears: bwd3 at H = 896, NB = 16, G = 2
-  const size_t v2 = (size_t)2 * 8 * (x1_bytes_per_dg(16) + x2_bytes_per_dg(16));
-  const size_t v3 = (size_t)2 * 2 * 2 * 28 * 8 * 28 * 32 * sizeof(uint2);
-  return HEADER_BYTES + (v2 > v3 ? v2 : v3);
+static size_t fwd_ring_bytes(int H, int NB, int G) { return (size_t)2 * G * 2 * NB * (H / 2) * sizeof(uint2); }
+// [(dir, grp)][parity][dst][pair][src][unit]
+static size_t bwd3_ring_bytes(int H, int NB, int G) {
+  const size_t nc = H / UPC;
+  return (size_t)2 * G * 2 * nc * (NB / 2) * nc * 32 * sizeof(uint2);
+}
+size_t scratch_bytes(int) {                              // the largest ring any launch clears
+  size_t m = (size_t)2 * 8 * (x1_bytes_per_dg(16) + x2_bytes_per_dg(16));
+  for (int H = 128; H <= 896; H += 64) {
+    if (!width_ok(H)) continue;
+    for (int NB = 8; NB <= 16; NB += 8) {
+      const size_t f = fwd_ring_bytes(H, NB, max_groups(H)), b = bwd3_ring_bytes(H, NB, max_groups(H));
+      m = f > m ? f : m;
+      m = b > m ? b : m;
+    }
+  }
+  return HEADER_BYTES + m;
 }
 
 static int env_int(const char* name, int dflt) {
@@ -1090,17 +1106,19 @@ template <int H, int NB, bool VAR>
 static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   constexpr int KC = H / 64;
   const size_t smem = exclusive_smem(1024 + (size_t)KC * NM * 128 + 4 * NB * 32 * 4 + 64);
-  const int G = a->N / NB;
+  const int Gall = a->N / NB, gm = max_groups(H);
   ASR_CUDA(cudaFuncSetAttribute(fwd_kernel<H, NB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const size_t xbytes = (size_t)2 * G * 2 * NB * (H / 2) * sizeof(uint2);
-  ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + xbytes, st));
   asr_lstm_fwd_args args = *a;
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
   int delay1 = env_int("ASR_LSTM_FWD_DELAY_NS", 0);
-  void* kargs[] = {&args, &flags, &xbuf, &delay1};
-  ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H, NB, VAR>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
-  asr::count_launch();
+  for (int grp0 = 0; grp0 < Gall; grp0 += gm) {          // one launch per max_groups() batch groups (C2: a single launch)
+    const int G = Gall - grp0 < gm ? Gall - grp0 : gm;
+    ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + fwd_ring_bytes(H, NB, G), st));
+    void* kargs[] = {&args, &flags, &xbuf, &delay1, &grp0};
+    ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H, NB, VAR>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
+    asr::count_launch();
+  }
   return ASR_OK;
 }
 
@@ -1126,19 +1144,21 @@ static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
 template <int H, int NB, bool VAR>
 static int32_t launch_bwd3(const asr_lstm_bwd_args* a, cudaStream_t st) {
   constexpr int NCTA = H / UPC;
-  const int G = a->N / NB;
+  const int Gall = a->N / NB, gm = max_groups(H);
   const size_t smem = exclusive_smem(1024 + (size_t)2 * NM * 128 + 64);
-  const size_t xbytes = (size_t)2 * G * 2 * NCTA * (NB / 2) * NCTA * 32 * sizeof(uint2);   // [(dir,grp)][parity][dst][pair][src][unit]
   ASR_CUDA(cudaFuncSetAttribute(bwd3_kernel<H, NB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + xbytes, st));
-  ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));
+  ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));      // accumulated over all groups
   if (VAR && a->mi) ASR_CUDA(cudaMemsetAsync(a->dmi, 0, (size_t)3 * 2 * 4 * a->H * sizeof(float), st));
   asr_lstm_bwd_args args = *a;
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
-  void* kargs[] = {&args, &flags, &xbuf};
-  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd3_kernel<H, NB, VAR>, dim3(NCTA, 2, G), dim3(THREADS), kargs, smem, st));
-  asr::count_launch();
+  for (int grp0 = 0; grp0 < Gall; grp0 += gm) {
+    const int G = Gall - grp0 < gm ? Gall - grp0 : gm;
+    ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + bwd3_ring_bytes(H, NB, G), st));
+    void* kargs[] = {&args, &flags, &xbuf, &grp0};
+    ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd3_kernel<H, NB, VAR>, dim3(NCTA, 2, G), dim3(THREADS), kargs, smem, st));
+    asr::count_launch();
+  }
   return ASR_OK;
 }
 
@@ -1148,7 +1168,8 @@ int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
   const bool g8 = group_size(a->N, a->H) == 8;
   const bool var = a->mi != nullptr || a->zoneout > 0.0f;
   if (var) ASR_CHECK_ARG(!a->mi || (a->zx && a->uh && a->dmi && a->duhT16), "lstmtc2 backward: MI needs zx, uh, dmi and duhT16");
-  if (!var && a->H == 512 && e && strcmp(e, "v2") == 0) return g8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
+  if (!var && a->H == 512 && e && strcmp(e, "v2") == 0 && a->N / (g8 ? 8 : 16) <= max_groups(512))
+    return g8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
 #define ASR_BWD3_CASE(HH)                                                                             \
   case HH:                                                                                            \
     if (var) return g8 ? launch_bwd3<HH, 8, true>(a, st) : launch_bwd3<HH, 16, true>(a, st);          \

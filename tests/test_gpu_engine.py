@@ -43,7 +43,8 @@ def test_forward_loss_decode_parity(N, T, F, H, L):
         assert out[n, :out_len[n]].tolist() == ref_dec[n]
 
 
-@pytest.mark.parametrize("N,T,F,H,L", [(8, 20, 26, 64, 2), (8, 40, 26, 128, 3), (16, 30, 26, 128, 2)])
+@pytest.mark.parametrize("N,T,F,H,L", [(8, 20, 26, 64, 2), (8, 40, 26, 128, 3), (16, 30, 26, 128, 2),
+                                       (72, 8, 26, 512, 1)])       # 72 = nine 8-sample groups: three launches per recurrence
 def test_train_step_gradients_and_adam_parity(N, T, F, H, L):
     C = 28
     eng, params, x, lens, labels, pack = _setup(N, T, F, H, L, C, seed=7 * N + T)
@@ -70,7 +71,7 @@ def test_train_step_gradients_and_adam_parity(N, T, F, H, L):
         np.testing.assert_allclose(newp[k], p0[k], atol=2e-6)
 
 
-@pytest.mark.parametrize("N,T,F,H,L,dropout", [(13, 18, 26, 256, 2, True), (5, 12, 26, 512, 1, False), (40, 10, 26, 512, 1, False)])
+@pytest.mark.parametrize("N,T,F,H,L,dropout", [(13, 18, 26, 256, 2, True), (5, 12, 26, 512, 1, False), (43, 10, 26, 512, 1, False)])
 def test_ragged_batch_is_padded_onto_the_tensor_core_engine(N, T, F, H, L, dropout):
     """A batch that is not a whole number of 8 / 16-sample groups (the last batch of an epoch) is padded with zero
     utterances inside the engine and still runs on the tensor-core recurrences; loss, logits, decode and every

@@ -155,7 +155,7 @@ def test_full_length_sequence_T999_stability():
 
 
 TC_SHAPES = [(16, 12, 26, 64), (16, 25, 20, 256), (32, 40, 26, 512), (48, 7, 26, 128), (24, 15, 26, 384), (64, 9, 26, 256),
-             (96, 6, 26, 128)]
+             (96, 6, 26, 128), (128, 6, 26, 512), (160, 5, 26, 256)]     # the last two: several launches over batch groups
 
 
 @pytest.mark.parametrize("N,T,D,H", TC_SHAPES)
