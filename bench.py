@@ -158,7 +158,7 @@ def run_ours(args):
     pcm_dev = pcm_host.to(dev)
     off_dev = off_host.to(dev)
     flat, loff, mx = pack_labels(labels, dev)
-    feat = audio.MFCC(num_cep=13, d=True, dd=False)
+    feat = audio.MFCC(num_cep=13, d=True, dd=(F == 39))
     eng = AcousticEngine(ModelSpec(F, H, L, C, weight_decay=1e-4, dropout=args.dropout, zoneout=args.zoneout,
                                    mi=(1.0, 0.5, 0.5) if args.mi else None), device=dev, seed=4321)
     loss_host = torch.empty(nb, dtype=torch.float32).pin_memory()
@@ -277,7 +277,8 @@ def run_ours(args):
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "fp16/bf16 tensor-core operands, fp32 accumulate+state",
                "data": "synthetic",
-               "config": {"workload": "C2: synthetic 16 kHz 10 s clips, 26-MFCC, 3xBiLSTM-512, Dense-28, CTC, "
+               "config": {"workload": ("C2" if (F, H, L) == (26, 512, 3) else "custom (not the BASELINE config)") +
+                                      ": synthetic 16 kHz 10 s clips, %d-MFCC, %dxBiLSTM-%d, Dense-28, CTC, " % (F, L, H) +
                                       "Adam(1e-3, clipnorm 400), l2 1e-4, variational dropout %g" % args.dropout
                                       + (", zoneout %g" % args.zoneout if args.zoneout else "") + (", MI" if args.mi else ""), "per_gpu_batch": nb,
                           "global_batch": gb, "frames": T_FRAMES, "parallelism": f"dp{world}",
@@ -441,7 +442,15 @@ def main():
     ap.add_argument("--decode_group", type=int, default=8,
                     help="infer mode: forward batches decoded by ONE beam-search launch (one warp per utterance: the "
                          "search is latency-bound, so more utterances per launch is nearly free)")
+    ap.add_argument("--hidden", type=int, default=512, help="BiLSTM width (BASELINE config: 512; brsmv1's own default: 256)")
+    ap.add_argument("--layers", type=int, default=3, help="BiLSTM layers (BASELINE config: 3; brsmv1's own default: 5)")
+    ap.add_argument("--dd", action="store_true", help="39-dim MFCC (13 + delta + delta-delta: brsmv1's own default) instead of 26")
     args = ap.parse_args()
+    global F, H, L, GFLOP_TRAIN_PER_UTT
+    F, H, L = (39 if args.dd else 26), args.hidden, args.layers
+    # fwd + dX + dW of the LSTM GEMMs and the Dense layer (88.80 GFLOP/utt for the BASELINE config)
+    GFLOP_TRAIN_PER_UTT = 3 * (sum(2 * T_FRAMES * 2 * ((F if l == 0 else 2 * H) + H) * 4 * H for l in range(L))
+                               + 2 * T_FRAMES * 2 * H * C) / 1e9
     if args.impl == "reference":
         run_reference(args)
     elif args.mode == "infer":

@@ -188,7 +188,12 @@ int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H);
 /* 1 when that engine also implements the element-wise switches (mi / zoneout fields); 0 = use the general cell. */
 int32_t asr_lstm_fuses_variants(int32_t T, int32_t N, int32_t H);
 /* 1 when asr_lstm_forward/backward take this shape (a persistent engine exists for it); 0 = use the general-cell
- * entry points below (any N, H <= 1024), e.g. H = 800 of BASELINE config 4. */
+ * entry points below (any N, H <= 1024).  The tensor-core engine is instantiated for H in {128, 256, 384, 512, 640,
+ * 768, 832, 896} and any N that is a multiple of 8 (batches wider than one cooperative wave run as several
+ * launches over consecutive batch groups).  Other widths up to 896, e.g. H = 800 of BASELINE config 4, are meant to
+ * be run zero-padded at the next instantiated width (W = U = b = 0 for the extra units keeps them at exactly 0 in
+ * both passes; asr-study_b200/engine.py does this at parameter load / export), ragged batches padded with zero
+ * utterances and zero dlogits rows. */
 int32_t asr_lstm_persistent_supported(int32_t T, int32_t N, int32_t H, int32_t training);
 
 size_t  asr_lstm_flags_bytes(void);
