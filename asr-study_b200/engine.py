@@ -810,12 +810,14 @@ class AcousticEngine:
                            cur_stream())
         return out, out_len
 
-    def beam(self, logits, in_len, beam_width=100, merge_repeated=True):
+    def beam(self, logits, in_len, beam_width=100, merge_repeated=True, tag=""):
+        """tag: suffix of the workspace / output buffer names, so that two searches can be in flight on two streams
+        (a pipelined evaluator decodes group k while group k+1 runs forward)."""
         T, N, Cc = logits.shape
         wsb = lib.asr_ctc_beam_workspace_bytes(T, N, Cc, beam_width)
-        ws = self._buf("beam_ws", (wsb // 4 + 1,), torch.int32)
-        out = self._buf("beam_out", (N, T), torch.int32)
-        out_len = self._buf("beam_len", (N,), torch.int32)
+        ws = self._buf("beam_ws" + tag, (wsb // 4 + 1,), torch.int32)
+        out = self._buf("beam_out" + tag, (N, T), torch.int32)
+        out_len = self._buf("beam_len" + tag, (N,), torch.int32)
         lib.asr_ctc_beam(ptr(logits), T, N, Cc, ptr(in_len), Cc - 1, beam_width, int(merge_repeated), ptr(out),
                          ptr(out_len), ptr(ws), cur_stream())
         return out, out_len

@@ -373,33 +373,72 @@ def run_infer(args):
 
     G = max(1, args.decode_group)
     nb_fwd = nb
-    big = torch.empty(T_FRAMES, G * nb_fwd, C, dtype=torch.float32, device=dev)
-    big_len = torch.empty(G * nb_fwd, dtype=torch.int32, device=dev)
+    # --overlap_decode: the beam search of group k (one warp per utterance, ~17 KB of shared memory each, latency-bound
+    # for ~80 ms per launch) runs on a second stream under the forward passes of group k+1.  Its CTAs spread over all
+    # SMs, so the forward kernels must be able to share an SM with them: the recurrences give up their exclusive
+    # shared-memory reservation and the GEMMs use the non-persistent 96 KB tiling (the persistent one needs 192 KB).
+    overlap = bool(args.overlap_decode)
+    if overlap:
+        os.environ["ASR_LSTM_EXCLUSIVE"] = "0"
+        os.environ["ASR_B200_GEMM"] = "tc1"
+    bigs = [torch.empty(T_FRAMES, G * nb_fwd, C, dtype=torch.float32, device=dev) for _ in range(2)]
+    big_lens = [torch.empty(G * nb_fwd, dtype=torch.int32, device=dev) for _ in range(2)]
+    outs_h = [torch.empty(G * nb_fwd, T_FRAMES, dtype=torch.int32).pin_memory() for _ in range(2)]
+    lens_h = [torch.empty(G * nb_fwd, dtype=torch.int32).pin_memory() for _ in range(2)]
+    main = torch.cuda.current_stream()
+    dec = torch.cuda.Stream(device=dev) if overlap else main
+    ev_fwd = [torch.cuda.Event() for _ in range(2)]
+    ev_dec = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0}
 
     def batch():
-        """G forward batches (host pcm -> H2D -> MFCC -> BiLSTM) then one beam-search launch over all G * nb utterances."""
+        """G forward batches (host pcm -> H2D -> MFCC -> BiLSTM) then one beam-search launch over all G * nb utterances
+        and the D2H copy of its labels; with overlap the search + copy of this group run on `dec` while the caller goes
+        on to the next group's forward passes (double-buffered logits / outputs)."""
+        k = state["k"]
+        state["k"] = k + 1
+        p = k & 1
+        big, big_len = bigs[p], big_lens[p]
+        if k >= 2:
+            ev_dec[p].synchronize()                       # host: the pinned outputs of group k-2 are complete (and consumed)
+            main.wait_event(ev_dec[p])                    # device: its search no longer reads big[p]
         for g in range(G):
             pcm = pcm_host.to(dev, non_blocking=True)
             x, lens = feat.batch(pcm, off, t_max=T_FRAMES, time_major=True)
             logits = eng.forward(x, training=False)
             big[:, g * nb_fwd:(g + 1) * nb_fwd].copy_(logits)
             big_len[g * nb_fwd:(g + 1) * nb_fwd].copy_(lens)
-        out, out_len = eng.beam(big, big_len, W, True)
-        return big, big_len, out.cpu(), out_len.cpu()
+        ev_fwd[p].record(main)
+        dec.wait_event(ev_fwd[p])
+        with torch.cuda.stream(dec):
+            out, out_len = eng.beam(big, big_len, W, True, tag=str(p))
+            outs_h[p].copy_(out, non_blocking=True)
+            lens_h[p].copy_(out_len, non_blocking=True)
+            ev_dec[p].record(dec)
+        if not overlap:
+            ev_dec[p].synchronize()
+        return p
+
+    def drain():
+        for e in ev_dec:
+            e.synchronize()
+        torch.cuda.synchronize()
 
     for _ in range(2):
-        logits, lens, out, out_len = batch()
-    torch.cuda.synchronize()
+        batch()
+    drain()
     nb = G * nb_fwd
     nbatches = max(1, total // nb)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.asr_launch_count()
-    e0.record()
+    e0.record(main)
     for _ in range(nbatches):
-        logits, lens, out, out_len = batch()
-    e1.record()
-    torch.cuda.synchronize()
+        p = batch()
+    main.wait_stream(dec)                                 # the last search and its D2H copy are inside the timed region
+    e1.record(main)
+    drain()
     ms = e0.elapsed_time(e1)
+    logits, lens, out, out_len = bigs[p], big_lens[p], outs_h[p], lens_h[p]
     launches = (lib.asr_launch_count() - l0) // nbatches
     # LER parity on a sample: oracle beam on the SAME logits
     k = min(args.ler_sample, nb)
@@ -410,7 +449,9 @@ def run_infer(args):
     res = {"metric": "clips/sec (inference: MFCC -> 3xBiLSTM-512 fwd -> CTC beam search width %d)" % W,
            "value": nb * nbatches / (ms / 1e3), "unit": "clips/s", "n_gpus": 1, "clips": nb * nbatches,
            "ms_per_batch": ms / nbatches, "batch": nb, "forward_batch": nb_fwd, "higher_is_better": True, "data": "synthetic",
-           "config": {"workload": "C5: synthetic 16 kHz 10 s clips, 26-MFCC, 3xBiLSTM-512, beam %d, host pcm -> labels" % W},
+           "config": {"workload": "C5: synthetic 16 kHz 10 s clips, 26-MFCC, 3xBiLSTM-512, beam %d, host pcm -> labels" % W,
+                      "decode": ("beam search of group k on a second stream under the forward passes of group k+1" if overlap
+                                 else "in line: forward passes, then the beam search, then the next group")},
            "gpu_launches": int(launches),
            "ler_parity": {"sample": k, "identical_label_sequences": same,
                           "ler_device_vs_truth": oc.ler(truth[:k], got), "ler_oracle_vs_truth": oc.ler(truth[:k], ref),
@@ -439,9 +480,10 @@ def main():
     ap.add_argument("--beam_width", type=int, default=100)
     ap.add_argument("--ler_sample", type=int, default=4)
     ap.add_argument("--sharpen", type=float, default=60.0, help="infer mode: factor on the random-init Dense kernel")
-    ap.add_argument("--decode_group", type=int, default=8,
+    ap.add_argument("--decode_group", type=int, default=16,
                     help="infer mode: forward batches decoded by ONE beam-search launch (one warp per utterance: the "
                          "search is latency-bound, so more utterances per launch is nearly free)")
+    ap.add_argument("--overlap_decode", type=int, default=1, help="infer mode: decode group k under the forward passes of group k+1")
     ap.add_argument("--hidden", type=int, default=512, help="BiLSTM width (BASELINE config: 512; brsmv1's own default: 256)")
     ap.add_argument("--layers", type=int, default=3, help="BiLSTM layers (BASELINE config: 3; brsmv1's own default: 5)")
     ap.add_argument("--dd", action="store_true", help="39-dim MFCC (13 + delta + delta-delta: brsmv1's own default) instead of 26")
