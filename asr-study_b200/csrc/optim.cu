@@ -14,11 +14,38 @@ __device__ __forceinline__ float eff_grad(const float* g, const float* p, const 
   return v;
 }
 
+// 16-byte accesses over the body of the bucket (the bucket and every tensor in it are 16-byte aligned), scalar tail
+__device__ __forceinline__ float4 eff_grad4(const float* g, const float* p, const uint8_t* mask, int64_t q, float gs,
+                                            float wd) {
+  const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + q);
+  float4 r = make_float4(gs * gv.x, gs * gv.y, gs * gv.z, gs * gv.w);
+  if (mask) {
+    const uchar4 mk = __ldg(reinterpret_cast<const uchar4*>(mask) + q);
+    if (mk.x | mk.y | mk.z | mk.w) {
+      const float4 pv = reinterpret_cast<const float4*>(p)[q];
+      if (mk.x) r.x = fmaf(2.0f * wd, pv.x, r.x);
+      if (mk.y) r.y = fmaf(2.0f * wd, pv.y, r.y);
+      if (mk.z) r.z = fmaf(2.0f * wd, pv.z, r.z);
+      if (mk.w) r.w = fmaf(2.0f * wd, pv.w, r.w);
+    }
+  }
+  return r;
+}
+__device__ __forceinline__ bool aligned16(const void* a, const void* b, const void* c, const void* d, const void* e) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d)) & 15) == 0 && (reinterpret_cast<uintptr_t>(e) & 3) == 0;
+}
+
 __global__ void __launch_bounds__(256)
 sqnorm_kernel(const float* __restrict__ g, const float* __restrict__ p, const uint8_t* __restrict__ mask, int64_t n,
               float gs, float wd, double* __restrict__ out) {
   double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t nq = aligned16(g, p, g, p, mask) ? n / 4 : 0;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = eff_grad4(g, p, mask, q, gs, wd);
+    acc += ((double)v.x * (double)v.x + (double)v.y * (double)v.y) + ((double)v.z * (double)v.z + (double)v.w * (double)v.w);
+  }
+  for (int64_t i = 4 * nq + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = eff_grad(g, p, mask, i, gs, wd);
     acc += (double)v * (double)v;
   }
@@ -45,7 +72,25 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             const uint8_t* __restrict__ mask, int64_t n, float gs, float wd, const double* __restrict__ sqnorm,
             float clipnorm, float lr_t, float b1, float b2, float eps) {
   const float sc = clip_scale(sqnorm, clipnorm);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t nq = aligned16(p, g, m, v, mask) ? n / 4 : 0;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const float4 ge = eff_grad4(g, p, mask, q, gs, wd);
+    float4 pv = reinterpret_cast<float4*>(p)[q], mv = reinterpret_cast<float4*>(m)[q], vv = reinterpret_cast<float4*>(v)[q];
+    const float gi[4] = {ge.x * sc, ge.y * sc, ge.z * sc, ge.w * sc};
+    float* pe = &pv.x; float* me = &mv.x; float* ve = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                          // same arithmetic, element by element, as the scalar tail
+      const float mi = b1 * me[k] + (1.0f - b1) * gi[k];
+      const float vi = b2 * ve[k] + (1.0f - b2) * gi[k] * gi[k];
+      me[k] = mi;
+      ve[k] = vi;
+      pe[k] = pe[k] - lr_t * mi / (sqrtf(vi) + eps);
+    }
+    reinterpret_cast<float4*>(m)[q] = mv;
+    reinterpret_cast<float4*>(v)[q] = vv;
+    reinterpret_cast<float4*>(p)[q] = pv;
+  }
+  for (int64_t i = 4 * nq + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = eff_grad(g, p, mask, i, gs, wd) * sc;
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
@@ -69,7 +114,7 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
 }
 
 inline int grid_for(int64_t n) {
-  int64_t b = (n + 255) / 256;
+  int64_t b = (n / 4 + 255) / 256;                         // one 16-byte quad per thread and trip
   const int64_t cap = 148 * 8;   // 8 resident 256-thread CTAs per SM on 148 SMs
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
