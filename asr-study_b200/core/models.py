@@ -187,14 +187,95 @@ class CTCModel(object):
                     cb.on_epoch_end(epoch, logs)
         return self.history
 
-    def evaluate_generator(self, generator, val_samples, max_q_size=10, nb_worker=1, **kw):
-        seen, agg = 0, np.zeros(4)
-        while seen < val_samples:
-            x, y = next(generator)
-            n = np.asarray(x[0]).shape[0]
-            agg += np.asarray(self.test_on_batch(x, y)) * n
-            seen += n
-        return list(agg / max(seen, 1))
+    def evaluate_generator(self, generator, val_samples, max_q_size=10, nb_worker=1, decode_group=None, **kw):
+        """Same result as test_on_batch per batch, weighted by batch size (what Keras' evaluate_generator returns), as a
+        device pipeline: the forward pass and the CTC loss of every batch run on the current stream and nothing is read
+        back per batch; the logits of `decode_group` batches are decoded by ONE launch on a second stream, under the
+        next group's forward passes (the beam search is one warp per utterance and latency-bound: a launch over 1 024
+        utterances costs what a launch over 64 does), and label error rates are formed on the host when a group's
+        labels arrive.  decode_group=1 is the batch-by-batch order."""
+        import os
+        eng, dev = self.engine, self.device
+        beam = not self.decoder["is_greedy"]
+        G = int(decode_group or (16 if beam else 4))
+        main = torch.cuda.current_stream(dev)
+        dec = torch.cuda.Stream(device=dev) if G > 1 else main
+        # the search CTAs spread over all SMs: let the forward kernels share an SM with them (csrc/lstm_tc2.cu
+        # exclusive_smem, csrc/api.cu engine selection) for the duration of this call
+        saved = {k: os.environ.get(k) for k in ("ASR_LSTM_EXCLUSIVE", "ASR_B200_GEMM")}
+        if beam and G > 1:
+            os.environ["ASR_LSTM_EXCLUSIVE"] = "0"
+            os.environ.setdefault("ASR_B200_GEMM", "tc1")
+        C = self.spec.num_classes
+        pending = []                                       # groups in flight: (event, pinned labels, truth rows, n real per batch)
+        losses, seen, ler_sum = [], 0, 0.0
+        done_ev = [None, None]
+
+        def finish(item):
+            ev, out_h, rows, spans = item
+            ev.synchronize()
+            total = 0.0
+            mat = out_h.numpy()
+            for (c0, n), r in zip(spans, rows):
+                total += metrics.ler(r, mat[c0:c0 + n]) * n
+            return total
+
+        try:
+            k = 0
+            while seen < val_samples:
+                batches = []
+                while seen < val_samples and len(batches) < G:
+                    x, y = next(generator)
+                    batches.append(x)
+                    seen += np.asarray(x[0]).shape[0]
+                p = k & 1
+                k += 1
+                if done_ev[p] is not None:                 # the search two groups back no longer reads this buffer pair
+                    main.wait_event(done_ev[p])
+                prepared = [self._device_batch(x[0], x[2], x[1], False) for x in batches]
+                Tmax = max(int(b[0].shape[0]) for b in prepared)
+                Ntot = sum(int(b[0].shape[1]) for b in prepared)
+                big = eng._buf("eval_logits%d" % p, (Tmax, Ntot, C), torch.float32)
+                big_len = eng._buf("eval_len%d" % p, (Ntot,), torch.int32)
+                spans, rows, c0 = [], [], 0
+                for x, (xt, lens, (flat, off, mx), N) in zip(batches, prepared):
+                    logits = eng.forward(xt, training=False)
+                    loss, _ = eng.ctc(logits, lens, flat, off, mx, want_grad=False)
+                    losses.append(loss[:N].clone())
+                    T, Np = int(xt.shape[0]), int(xt.shape[1])
+                    big[:T, c0:c0 + Np].copy_(logits)
+                    big_len[c0:c0 + Np].copy_(lens)
+                    spans.append((c0, N))
+                    rows.append(_label_rows(x[1]))
+                    c0 += Np
+                ev_f = torch.cuda.Event()
+                ev_f.record(main)
+                dec.wait_event(ev_f)
+                with torch.cuda.stream(dec):
+                    if beam:
+                        out, _ = eng.beam(big, big_len, self.decoder["beam_width"], self.decoder["merge_repeated"], tag=str(p))
+                    else:
+                        out, _ = eng.greedy(big, big_len, True)
+                    out_h = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+                    out_h.copy_(out, non_blocking=True)
+                    ev_d = torch.cuda.Event()
+                    ev_d.record(dec)
+                done_ev[p] = ev_d
+                pending.append((ev_d, out_h, rows, spans))
+                if len(pending) > 1 or G == 1:             # host: labels of the previous group, while this one runs
+                    ler_sum += finish(pending.pop(0))
+            while pending:
+                ler_sum += finish(pending.pop(0))
+            main.wait_stream(dec)
+        finally:
+            for key, val in saved.items():
+                if val is None:
+                    os.environ.pop(key, None)
+                else:
+                    os.environ[key] = val
+        n_real = sum(int(l.numel()) for l in losses)
+        ctc = float(torch.cat(losses).sum().item()) / max(n_real, 1)
+        return [ctc + self._reg(), ctc, 0.0, ler_sum / max(n_real, 1)]
 
     # ---- checkpoint (weights + optimiser state + meta; the .h5 wire format needs h5py: next row) ----
     def save(self, path, meta=None):

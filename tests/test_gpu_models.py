@@ -102,6 +102,39 @@ def test_fit_evaluate_predict_save_load(tmp_path):
     assert mv2.spec.mi == (1.0, 0.5, 0.5) and np.array_equal(mv2.predict([x[0], x[2]]), mv.predict([x[0], x[2]]))
 
 
+@pytest.mark.parametrize("greedy", [True, False])
+def test_evaluate_generator_grouped_decode_matches_batch_by_batch(greedy):
+    """evaluate_generator decodes groups of batches with one launch on a second stream (under the next group's forward
+    passes); the metrics must be exactly those of test_on_batch batch by batch, for ragged batch lengths too."""
+    from asr_study_b200.core import models
+    from asr_study_b200.datasets.dataset_generator import DatasetGenerator
+    from asr_study_b200.datasets.dummy import Dummy
+    from asr_study_b200.preprocessing import audio
+    from asr_study_b200.preprocessing.text import simple_char_parser
+    dl = Dummy(num_speakers=3, num_utterances_per_speaker=7, max_duration=0.9, min_duration=0.3, max_label_length=6,
+               split=[.0, .0], seed=5).to_dict_list()
+    g = DatasetGenerator(audio.MFCC(num_cep=13, d=True, dd=False), simple_char_parser, batch_size=3, shuffle=False, seed=0)
+    (te,) = g.flow_from_dl(dl, ["test"])
+    assert te.len == 21
+    m = models.brsmv1(num_features=26, num_hiddens=128, num_layers=2, dropout=0.0, is_greedy=greedy, beam_width=8)
+    m.engine.params.p("dense.W").mul_(8.0)                # peaky posteriors: non-trivial label sequences
+    n_batches = (te.len + 2) // 3
+    seen, agg = 0, np.zeros(4)
+    for _ in range(n_batches):
+        x, y = next(te)
+        n = np.asarray(x[0]).shape[0]
+        agg += np.asarray(m.test_on_batch(x, y)) * n
+        seen += n
+    ref = agg / seen
+    assert seen == te.len
+    for G in (1, 2, 4):
+        got = np.asarray(m.evaluate_generator(te, te.len, decode_group=G))
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-7, err_msg=f"decode_group={G}")
+    assert ref[3] > 0.0
+    import os
+    assert os.environ.get("ASR_LSTM_EXCLUSIVE") is None    # the co-residency switches are restored
+
+
 def test_train_and_eval_cli(tmp_path):
     sys.path.insert(0, ROOT)
     import eval as eval_cli
