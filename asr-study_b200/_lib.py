@@ -89,6 +89,7 @@ SIGNATURES = {
     "asr_ctc_workspace_bytes": (_SZ, [_I32, _I32, _I32]),
     "asr_ctc_loss_grad": (_I32, [_P, _I32, _I32, _I32, _P, _P, _P, _I32, _I32, _F, _P, _P, _P, _P]),
     "asr_ctc_greedy": (_I32, [_P, _I32, _I32, _I32, _P, _I32, _I32, _P, _P, _P]),
+    "asr_edit_distance": (_I32, [_P, _I32, _I32, _P, _P, _P, _I32, _I32, _P, _P]),
     "asr_ctc_beam_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "asr_ctc_beam": (_I32, [_P, _I32, _I32, _I32, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "asr_grad_sqnorm": (_I32, [_P, _P, _P, _I64, _F, _F, _P, _P]),

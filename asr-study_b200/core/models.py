@@ -39,6 +39,54 @@ class SGD(object):
         self.kind = "sgd"
 
 
+class _GeneratorFeed(object):
+    """Keras-1 GeneratorEnqueuer for the one-worker case: a daemon thread pulls next(generator) into a bounded queue
+    until `total_samples` utterances have been fetched (never more: the generator's position after the call is what a
+    synchronous loop would leave).  nb_worker=0: no thread."""
+
+    def __init__(self, generator, total_samples, max_q_size, nb_worker, device):
+        import queue
+        import threading
+        self.gen, self.total, self.thread = generator, int(total_samples), None
+        if not nb_worker or self.total <= 0:
+            return
+        self.q = queue.Queue(maxsize=max(1, int(max_q_size)))
+        self.stop = threading.Event()
+
+        def work():
+            if torch.cuda.is_available():
+                torch.cuda.set_device(device)           # new threads start on device 0
+            fetched = 0
+            try:
+                while fetched < self.total and not self.stop.is_set():
+                    item = next(self.gen)
+                    fetched += np.asarray(item[0][0]).shape[0]
+                    while not self.stop.is_set():
+                        try:
+                            self.q.put(item, timeout=0.1)
+                            break
+                        except queue.Full:
+                            pass
+            except BaseException as e:                  # surfaces in get()
+                self.q.put(e)
+
+        self.thread = threading.Thread(target=work, daemon=True)
+        self.thread.start()
+
+    def get(self):
+        if self.thread is None:
+            return next(self.gen)
+        item = self.q.get()
+        if isinstance(item, BaseException):
+            raise item
+        return item
+
+    def close(self):
+        if self.thread is not None:
+            self.stop.set()
+            self.thread.join(timeout=5.0)
+
+
 def _label_rows(labels):
     if labels is None:
         return None
@@ -104,15 +152,27 @@ class CTCModel(object):
             packed = pack_labels(rows, self.device)
         return xt, torch.as_tensor(lens, device=self.device), packed, N
 
-    def _decode(self, logits, lens):
+    def _decode(self, logits, lens, with_len=False):
         if self.decoder["is_greedy"]:
             out, out_len = self.engine.greedy(logits, lens, True)
         else:
             out, out_len = self.engine.beam(logits, lens, self.decoder["beam_width"], self.decoder["merge_repeated"])
-        return out
+        return (out, out_len) if with_len else out
+
+    def _stats(self, loss, logits, lens, flat, off, mx, N):
+        """[loss, ctc_loss, decoder_loss, decoder_ler] of one batch as a DEVICE tensor (no read-back): the decode and the
+        label error rate (core/metrics.py:4-8, asr_edit_distance) run on the device, so a training loop only
+        synchronises when it reads its logs."""
+        out, out_len = self._decode(logits, lens, with_len=True)
+        ler = self.engine.ler(out, out_len, flat, off, mx)[:N].mean()
+        ctc = loss[:N].mean()
+        return torch.stack([ctc + self._reg_dev(), ctc, torch.zeros_like(ctc), ler])
 
     # ---- train / eval / predict ------------------------------------------------------
     def train_on_batch(self, x, y=None):
+        return [float(v) for v in self._train_stats(x).tolist()]
+
+    def _train_stats(self, x):
         feats, labels, x_len = x[0], x[1], x[2]
         xt, lens, (flat, off, mx), N = self._device_batch(feats, x_len, labels, True)
         gb = N * self.world_size
@@ -123,19 +183,14 @@ class CTCModel(object):
         else:
             kw.update(momentum=o.momentum)
         loss = self.engine.train_step(xt, lens, flat, off, mx, global_batch=gb, allreduce=self.allreduce, **kw)
-        dec = self._decode(self.engine.last_logits, lens)[:N]
-        ctc = float(loss[:N].mean().item())
-        reg = self._reg()
-        return [ctc + reg, ctc, 0.0, metrics.ler(_label_rows(labels), dec)]
+        return self._stats(loss, self.engine.last_logits, lens, flat, off, mx, N)
 
     def test_on_batch(self, x, y=None):
         feats, labels, x_len = x[0], x[1], x[2]
         xt, lens, (flat, off, mx), N = self._device_batch(feats, x_len, labels, False)
         logits = self.engine.forward(xt, training=False)
         loss, _ = self.engine.ctc(logits, lens, flat, off, mx, want_grad=False)
-        dec = self._decode(logits, lens)[:N]
-        ctc = float(loss[:N].mean().item())
-        return [ctc + self._reg(), ctc, 0.0, metrics.ler(_label_rows(labels), dec)]
+        return [float(v) for v in self._stats(loss, logits, lens, flat, off, mx, N).tolist()]
 
     def predict(self, x, batch_size=None, verbose=0):
         """x = [inputs, inputs_length] (predict mode, utils/core_utils.py:76-93) -> -1-padded label matrix."""
@@ -151,12 +206,19 @@ class CTCModel(object):
         xt, lens, _, N = self._device_batch(feats, x_len, None, False)
         return self.engine.forward(xt, training=False)[:, :N].transpose(0, 1).contiguous()
 
-    def _reg(self):
+    def _reg_dev(self):
+        """sum of the l2(weight_decay) regularisers (core/models.py:263-264,279) as a device scalar — a reported metric,
+        not part of the step (the optimiser folds the l2 gradient in itself)."""
+        P = self.engine.params
         wd = self.spec.weight_decay
         if not wd:
-            return 0.0
-        P = self.engine.params
-        return float(wd * (P.flat * P.flat * P.decay.float()).sum().item())
+            return torch.zeros((), dtype=torch.float32, device=self.device)
+        if getattr(self, "_decayf", None) is None:
+            self._decayf = P.decay.float()
+        return wd * torch.dot(P.flat * self._decayf, P.flat)
+
+    def _reg(self):
+        return float(self._reg_dev().item())
 
     def fit_generator(self, generator, samples_per_epoch, nb_epoch, validation_data=None, nb_val_samples=None,
                       max_q_size=10, nb_worker=1, callbacks=None, verbose=1, initial_epoch=0, **kw):
@@ -164,13 +226,22 @@ class CTCModel(object):
         for cb in callbacks:
             if hasattr(cb, "set_model"):
                 cb.set_model(self)
+        # Keras runs the generator on a worker thread behind a queue of max_q_size batches (train.py:213-217:
+        # max_q_size=10, nb_worker=1), so featurisation overlaps the training step; nb_worker=0 pulls in line.  The
+        # worker fetches exactly the batches this call consumes.  Per batch nothing is read back: the metrics are
+        # accumulated on the device and read once per epoch.
+        feed = _GeneratorFeed(generator, max(0, nb_epoch - initial_epoch) * samples_per_epoch, max_q_size,
+                              nb_worker, self.device)
         for epoch in range(initial_epoch, nb_epoch):
-            seen, agg, t0 = 0, np.zeros(4), time.time()
+            seen, t0 = 0, time.time()
+            agg_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
             while seen < samples_per_epoch:
-                x, y = next(generator)
+                x, y = feed.get()
                 n = np.asarray(x[0]).shape[0]
-                agg += np.asarray(self.train_on_batch(x, y)) * n
+                agg_dev += self._train_stats(x) * n
                 seen += n
+            agg = agg_dev.cpu().numpy().astype(np.float64)
+            t_train = time.time() - t0
             logs = dict(zip(["loss", "ctc_loss", "decoder_loss", "decoder_ler"], agg / max(seen, 1)))
             if validation_data is not None and nb_val_samples:
                 v = self.evaluate_generator(validation_data, nb_val_samples)
@@ -181,10 +252,11 @@ class CTCModel(object):
                 show = {k: round(float(logs[k]), 4) for k in ("loss", "decoder_ler", "val_loss", "val_decoder_ler")
                         if k in logs}
                 print("Epoch %d/%d - %.1fs - %s - %.1f utt/s" % (epoch + 1, nb_epoch, time.time() - t0, show,
-                                                                  seen / max(time.time() - t0, 1e-9)))
+                                                                  seen / max(t_train, 1e-9)))
             for cb in callbacks:
                 if hasattr(cb, "on_epoch_end"):
                     cb.on_epoch_end(epoch, logs)
+        feed.close()
         return self.history
 
     def evaluate_generator(self, generator, val_samples, max_q_size=10, nb_worker=1, decode_group=None, **kw):
@@ -192,8 +264,8 @@ class CTCModel(object):
         device pipeline: the forward pass and the CTC loss of every batch run on the current stream and nothing is read
         back per batch; the logits of `decode_group` batches are decoded by ONE launch on a second stream, under the
         next group's forward passes (the beam search is one warp per utterance and latency-bound: a launch over 1 024
-        utterances costs what a launch over 64 does), and label error rates are formed on the host when a group's
-        labels arrive.  decode_group=1 is the batch-by-batch order."""
+        utterances costs what a launch over 64 does), followed by the label-error-rate kernel; one read-back at the
+        end.  The generator runs on a worker thread like fit_generator's.  decode_group=1 is the batch-by-batch order."""
         import os
         eng, dev = self.engine, self.device
         beam = not self.decoder["is_greedy"]
@@ -207,25 +279,16 @@ class CTCModel(object):
             os.environ["ASR_LSTM_EXCLUSIVE"] = "0"
             os.environ.setdefault("ASR_B200_GEMM", "tc1")
         C = self.spec.num_classes
-        pending = []                                       # groups in flight: (event, pinned labels, truth rows, n real per batch)
-        losses, seen, ler_sum = [], 0, 0.0
+        losses, seen = [], 0
+        ler_sum = torch.zeros((), dtype=torch.float32, device=dev)
         done_ev = [None, None]
-
-        def finish(item):
-            ev, out_h, rows, spans = item
-            ev.synchronize()
-            total = 0.0
-            mat = out_h.numpy()
-            for (c0, n), r in zip(spans, rows):
-                total += metrics.ler(r, mat[c0:c0 + n]) * n
-            return total
-
+        feed = _GeneratorFeed(generator, val_samples, max_q_size, nb_worker, dev)
         try:
             k = 0
             while seen < val_samples:
                 batches = []
                 while seen < val_samples and len(batches) < G:
-                    x, y = next(generator)
+                    x, y = feed.get()
                     batches.append(x)
                     seen += np.asarray(x[0]).shape[0]
                 p = k & 1
@@ -237,7 +300,7 @@ class CTCModel(object):
                 Ntot = sum(int(b[0].shape[1]) for b in prepared)
                 big = eng._buf("eval_logits%d" % p, (Tmax, Ntot, C), torch.float32)
                 big_len = eng._buf("eval_len%d" % p, (Ntot,), torch.int32)
-                spans, rows, c0 = [], [], 0
+                rows, real, c0 = [], [], 0
                 for x, (xt, lens, (flat, off, mx), N) in zip(batches, prepared):
                     logits = eng.forward(xt, training=False)
                     loss, _ = eng.ctc(logits, lens, flat, off, mx, want_grad=False)
@@ -245,29 +308,27 @@ class CTCModel(object):
                     T, Np = int(xt.shape[0]), int(xt.shape[1])
                     big[:T, c0:c0 + Np].copy_(logits)
                     big_len[c0:c0 + Np].copy_(lens)
-                    spans.append((c0, N))
-                    rows.append(_label_rows(x[1]))
+                    rows += _label_rows(x[1]) + [np.zeros(0, np.int32)] * (Np - N)
+                    real += list(range(c0, c0 + N))
                     c0 += Np
+                gflat, goff, gmx = pack_labels(rows, dev)  # the group's labels, padding columns empty
+                real_idx = torch.as_tensor(real, dtype=torch.int64, device=dev)
                 ev_f = torch.cuda.Event()
                 ev_f.record(main)
                 dec.wait_event(ev_f)
                 with torch.cuda.stream(dec):
                     if beam:
-                        out, _ = eng.beam(big, big_len, self.decoder["beam_width"], self.decoder["merge_repeated"], tag=str(p))
+                        out, out_len = eng.beam(big, big_len, self.decoder["beam_width"], self.decoder["merge_repeated"], tag=str(p))
                     else:
-                        out, _ = eng.greedy(big, big_len, True)
-                    out_h = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-                    out_h.copy_(out, non_blocking=True)
-                    ev_d = torch.cuda.Event()
-                    ev_d.record(dec)
-                done_ev[p] = ev_d
-                pending.append((ev_d, out_h, rows, spans))
-                if len(pending) > 1 or G == 1:             # host: labels of the previous group, while this one runs
-                    ler_sum += finish(pending.pop(0))
-            while pending:
-                ler_sum += finish(pending.pop(0))
+                        out, out_len = eng.greedy(big, big_len, True)
+                    ler_sum += eng.ler(out, out_len, gflat, goff, gmx)[real_idx].sum()
+                    for t in (gflat, goff, real_idx):      # allocated on the caller's stream, consumed on `dec`
+                        t.record_stream(dec)
+                    done_ev[p] = torch.cuda.Event()
+                    done_ev[p].record(dec)
             main.wait_stream(dec)
         finally:
+            feed.close()
             for key, val in saved.items():
                 if val is None:
                     os.environ.pop(key, None)
@@ -275,7 +336,7 @@ class CTCModel(object):
                     os.environ[key] = val
         n_real = sum(int(l.numel()) for l in losses)
         ctc = float(torch.cat(losses).sum().item()) / max(n_real, 1)
-        return [ctc + self._reg(), ctc, 0.0, ler_sum / max(n_real, 1)]
+        return [ctc + self._reg(), ctc, 0.0, float(ler_sum.item()) / max(n_real, 1)]
 
     # ---- checkpoint (weights + optimiser state + meta; the .h5 wire format needs h5py: next row) ----
     def save(self, path, meta=None):

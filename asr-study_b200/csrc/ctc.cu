@@ -595,6 +595,83 @@ extern "C" int32_t asr_ctc_loss_grad(const float* logits, int32_t T, int32_t N, 
   return ASR_OK;
 }
 
+// ---- K10: label error rate ---------------------------------------------------------------------
+// core/metrics.py:4-8: tf.edit_distance(hyp, truth, normalize=True) per utterance (Levenshtein distance over label
+// ids, divided by the truth length; an empty truth gives 0 for an empty hypothesis and +inf otherwise, as TF does).
+// One warp per utterance, anti-diagonal wavefront: cell (i, j) of the DP table depends on (i-1, j), (i, j-1) and
+// (i-1, j-1), so all cells of one anti-diagonal are independent; lane l owns the truth positions j = l + 1, l + 33, ...
+// and three rotating diagonals live in shared memory.  A few dozen labels per utterance: latency, not bandwidth.
+__global__ void __launch_bounds__(32)
+edit_distance_kernel(const int* __restrict__ hyp, int hyp_stride, const int* __restrict__ hyp_len,
+                     const int* __restrict__ truth, const int* __restrict__ truth_off, int normalize,
+                     float* __restrict__ out) {
+  extern __shared__ int sd[];                           // 3 diagonals of (n + 1) cells, indexed by j
+  const int u = blockIdx.x, lane = threadIdx.x;
+  const int* a = hyp + (size_t)u * hyp_stride;          // hypothesis, length m
+  int m = 0;
+  if (hyp_len) m = max(hyp_len[u], 0);
+  else {                                                // -1 padded row: count the leading non-negative labels
+    for (int base = 0; base < hyp_stride; base += 32) {
+      const int i = base + lane;
+      const unsigned neg = __ballot_sync(0xffffffffu, i >= hyp_stride || a[i] < 0);
+      if (neg) { m = base + __ffs(neg) - 1; break; }
+      m = min(base + 32, hyp_stride);
+    }
+  }
+  m = min(m, hyp_stride);
+  const int t0 = truth_off[u], n = truth_off[u + 1] - t0;
+  const int* b = truth + t0;
+  float res;
+  if (n == 0) {
+    res = (m == 0) ? 0.0f : (normalize ? CUDART_INF_F : (float)m);
+  } else if (m == 0) {
+    res = normalize ? 1.0f : (float)n;
+  } else {
+    int* d0 = sd;                                       // diagonal k - 2
+    int* d1 = sd + (n + 1);                             // diagonal k - 1
+    int* d2 = sd + 2 * (n + 1);                         // diagonal k   (cells (i, j) with i + j = k)
+    // D(i, 0) = i, D(0, j) = j; diagonal k holds D(k - j, j) at index j
+    for (int j = lane; j <= n; j += 32) { d0[j] = 0; d1[j] = 0; }
+    if (lane == 0) { d0[0] = 0; d1[0] = 1; d1[1] = 1; }   // k = 0: D(0,0) = 0;  k = 1: D(1,0) = 1, D(0,1) = 1
+    __syncwarp();
+    for (int k = 2; k <= m + n; ++k) {
+      const int jlo = max(0, k - m), jhi = min(n, k);
+      for (int j = jlo + lane; j <= jhi; j += 32) {
+        const int i = k - j;
+        int v;
+        if (j == 0) v = i;
+        else if (i == 0) v = j;
+        else {
+          const int sub = d0[j - 1] + (a[i - 1] != b[j - 1]);      // D(i-1, j-1) on diagonal k-2
+          const int del = d1[j] + 1;                               // D(i-1, j)   on diagonal k-1
+          const int ins = d1[j - 1] + 1;                           // D(i, j-1)   on diagonal k-1
+          v = min(sub, min(del, ins));
+        }
+        d2[j] = v;
+      }
+      __syncwarp();
+      int* tmp = d0; d0 = d1; d1 = d2; d2 = tmp;
+    }
+    const int dist = d1[n];                             // diagonal m + n holds D(m, n) at index n
+    res = normalize ? (float)dist / (float)n : (float)dist;
+  }
+  if (lane == 0) out[u] = res;
+}
+
+extern "C" int32_t asr_edit_distance(const int32_t* hyp, int32_t N, int32_t hyp_stride, const int32_t* hyp_len,
+                                     const int32_t* truth, const int32_t* truth_off, int32_t max_truth_len,
+                                     int32_t normalize, float* out, void* stream) {
+  ASR_CHECK_ARG(hyp && truth && truth_off && out, "asr_edit_distance: null argument");
+  ASR_CHECK_ARG(N >= 1 && hyp_stride >= 1 && max_truth_len >= 0, "asr_edit_distance: bad shape");
+  const size_t smem = (size_t)3 * (max_truth_len + 1) * sizeof(int);
+  ASR_CHECK_ARG(smem <= 200 * 1024, "asr_edit_distance: truth of %d labels needs %zu B of shared memory", max_truth_len, smem);
+  if (smem > 48 * 1024)
+    ASR_CUDA(cudaFuncSetAttribute(edit_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edit_distance_kernel<<<N, 32, smem, (cudaStream_t)stream>>>(hyp, hyp_stride, hyp_len, truth, truth_off, normalize, out);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
 extern "C" int32_t asr_ctc_greedy(const float* logits, int32_t T, int32_t N, int32_t C, const int32_t* in_len,
                                   int32_t blank, int32_t merge_repeated, int32_t* out_labels, int32_t* out_len,
                                   void* stream) {

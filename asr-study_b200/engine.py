@@ -810,6 +810,15 @@ class AcousticEngine:
                            cur_stream())
         return out, out_len
 
+    def ler(self, hyp, hyp_len, labels_flat, label_off, max_label_len, normalize=True):
+        """core/metrics.py:4-8 on the device: per-utterance tf.edit_distance(hyp, truth, normalize=True) of a decode
+        kernel's output [N, T] / [N] against the sparse labels -> f32 [N] (no host round trip)."""
+        N = hyp.shape[0]
+        out = self._buf("ler_out", (N,), torch.float32)
+        lib.asr_edit_distance(ptr(hyp), N, hyp.shape[1], ptr(hyp_len), ptr(labels_flat), ptr(label_off),
+                              int(max_label_len), int(normalize), ptr(out), cur_stream())
+        return out
+
     def beam(self, logits, in_len, beam_width=100, merge_repeated=True, tag=""):
         """tag: suffix of the workspace / output buffer names, so that two searches can be in flight on two streams
         (a pipelined evaluator decodes group k while group k+1 runs forward)."""

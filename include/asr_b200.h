@@ -270,6 +270,14 @@ int32_t asr_ctc_greedy(const float* logits, int32_t T, int32_t N, int32_t C,
                        const int32_t* in_len, int32_t blank, int32_t merge_repeated,
                        int32_t* out_labels, int32_t* out_len, void* stream);
 
+/* K10 label error rate         replaces tf.edit_distance(hyp, truth, normalize=True), core/metrics.py:4-8
+ * hyp i32 [N, hyp_stride] (-1 padded: what K7 / K8 emit) with hyp_len i32 [N] (or NULL: count the leading labels >= 0),
+ * truth i32 flat + truth_off i32 [N+1] (the sparse-label contract of K6), max_truth_len >= every truth length.
+ * out f32 [N] = Levenshtein distance (/ truth length when normalize; empty truth: 0 for an empty hyp, +inf otherwise). */
+int32_t asr_edit_distance(const int32_t* hyp, int32_t N, int32_t hyp_stride, const int32_t* hyp_len,
+                          const int32_t* truth, const int32_t* truth_off, int32_t max_truth_len,
+                          int32_t normalize, float* out, void* stream);
+
 /* K8  prefix beam search       replaces tf.nn.ctc_beam_search_decoder
  * (top_paths = 1), core/ctc_utils.py:44-50; utils/core_utils.py:70-71 */
 size_t  asr_ctc_beam_workspace_bytes(int32_t T, int32_t N, int32_t C, int32_t beam_width);
