@@ -54,7 +54,7 @@ class _GeneratorFeed(object):
         self.stop = threading.Event()
 
         def work():
-            if torch.cuda.is_available():
+            if torch.cuda.is_available() and torch.device(device).type == "cuda":
                 torch.cuda.set_device(device)           # new threads start on device 0
             fetched = 0
             try:
