@@ -33,6 +33,21 @@ def test_beam_matches_oracle(T, C, W, scale):
     assert got2 == ref2
 
 
+def test_tensorflow_known_answer_beam_search_on_the_device():
+    """K8 on TensorFlow's own 'hibernating beam search' vectors (tests/golden/ctc_tf_beam_known_answer.json): the top
+    path TF expects at beam_width 2 is [1, 0]; wider beams find the more probable [0, 1, 0]."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ctc_tf_beam_known_answer.json")))
+    p = np.asarray(d["probs"], np.float64)
+    logits = np.zeros((1, d["max_time"], p.shape[1]), np.float32)
+    logits[0, :d["seq_len"]] = (np.log(p) + d["offset"])[:d["seq_len"]]
+    assert _beam(logits, [d["seq_len"]], d["beam_width"], merge=False) == [d["top_path_width_2"]]
+    assert _beam(logits, [d["seq_len"]], d["beam_width"]) == [d["top_path_width_2"]]
+    for W in (3, 16, 100):
+        assert _beam(logits, [d["seq_len"]], W) == [d["second_path_width_2"]]
+
+
 def test_beam_peaky_equals_greedy_and_empty():
     T, C = 64, 28
     seq = np.random.RandomState(0).randint(0, C, size=T)

@@ -39,6 +39,20 @@ def test_loss_and_grad_vs_oracle(seed, T, N):
         assert np.all(grad[n, lens[n]:] == 0)
 
 
+def test_tensorflow_known_answers_on_the_device():
+    """K6 on the known-answer pair of TensorFlow's own ctc_loss_op_test.py (tests/golden/ctc_tf_known_answer.json):
+    -ln p and d loss / d logits as TF prints them (loss 1e-4 relative, gradient 1e-4 absolute: the bars of this file;
+    the fp64 oracle meets the same constants to 5e-7 in tests/test_oracle_ctc.py)."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ctc_tf_known_answer.json")))
+    logits = np.log(np.stack([np.asarray(c["probs"], np.float64) for c in d["cases"]])).astype(np.float32)
+    assert d["blank"] == logits.shape[2] - 1
+    loss, grad, _, _ = _run(logits, [5, 5], [np.asarray(c["targets"], np.int32) for c in d["cases"]])
+    np.testing.assert_allclose(loss, [c["loss"] for c in d["cases"]], rtol=1e-4)
+    assert np.abs(grad - np.stack([np.asarray(c["grad_wrt_logits"]) for c in d["cases"]])).max() < 1e-4
+
+
 def test_edge_cases_empty_label_long_label_infeasible():
     rng = np.random.RandomState(3)
     T, C = 12, 6

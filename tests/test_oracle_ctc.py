@@ -35,6 +35,55 @@ def test_tf_style_known_answer_is_rederived():
         assert np.isclose(loss, ref, rtol=1e-10) or (np.isinf(loss) and np.isinf(ref))
 
 
+def test_tensorflow_known_answers_loss_and_gradient():
+    """The known-answer pair of TensorFlow's own ctc_loss_op_test.py (tests/golden/ctc_tf_known_answer.json: inputs,
+    -ln p and d loss / d logits 'from Alex Graves' implementation'): the oracle reproduces TF's printed constants to
+    their last digit, loss and gradient, for the (merge-repeated, blank = C-1, internal softmax) convention
+    tf.nn.ctc_loss is called with at core/ctc_utils.py:68."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ctc_tf_known_answer.json")))
+    for case in d["cases"]:
+        p = np.asarray(case["probs"], np.float64)
+        assert np.abs(p.sum(axis=1) - 1.0).max() < 2e-6                    # typed-in rows are distributions
+        loss, grad = oc.ctc_loss_grad_single(np.log(p), p.shape[0], case["targets"], d["blank"])
+        assert abs(loss - case["loss"]) < 5e-6                              # TF prints 6 significant digits
+        assert np.abs(grad - np.asarray(case["grad_wrt_logits"])).max() < 2e-6
+    # batched entry point, float32 like the kernels' inputs, both cases at once
+    logits = np.log(np.stack([np.asarray(c["probs"], np.float64) for c in d["cases"]])).astype(np.float32)
+    loss, grad = oc.ctc_loss_grad(logits, [5, 5], [np.asarray(c["targets"]) for c in d["cases"]])
+    np.testing.assert_allclose(loss, [c["loss"] for c in d["cases"]], atol=5e-6)
+    assert np.abs(grad - np.stack([np.asarray(c["grad_wrt_logits"]) for c in d["cases"]])).max() < 2e-6
+
+
+def _tf_beam_case():
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ctc_tf_beam_known_answer.json")))
+    p = np.asarray(d["probs"], np.float64)
+    assert np.abs(p.sum(axis=1) - 1.0).max() < 2e-6
+    logits = np.zeros((1, d["max_time"], p.shape[1]), np.float32)      # frames past seq_len are zero-padded, as in TF's test
+    logits[0, :d["seq_len"]] = (np.log(p) + d["offset"])[:d["seq_len"]]
+    return d, p, logits
+
+
+def test_tensorflow_known_answer_beam_search():
+    """TensorFlow's own 'hibernating beam search' test (tests/golden/ctc_tf_beam_known_answer.json): at beam_width 2 the
+    top path TF expects is [1, 0] although [0, 1, 0] is the more probable labelling — the oracle's restatement of
+    CTCBeamSearchDecoder reproduces that pruning artefact, finds [0, 1, 0] at wider beams like exhaustive enumeration,
+    and ignores both the +2.0 offset on the inputs and the frames past the sequence length."""
+    d, p, logits = _tf_beam_case()
+    assert oc.beam_decode(logits, [d["seq_len"]], beam_width=d["beam_width"], merge_repeated=False) == [d["top_path_width_2"]]
+    assert oc.beam_decode(logits, [d["seq_len"]], beam_width=d["beam_width"]) == [d["top_path_width_2"]]
+    probs = oc.brute_force_label_probs(np.log(p[:d["seq_len"]]), d["blank"])
+    best = max(probs, key=probs.get)
+    assert list(best) == d["second_path_width_2"]
+    for W in (3, 16, 100):
+        assert oc.beam_decode(logits, [d["seq_len"]], beam_width=W) == [list(best)]
+    assert oc.beam_decode(logits - d["offset"], [d["seq_len"]], beam_width=2) == [d["top_path_width_2"]]
+    assert oc.greedy_decode(logits, [d["seq_len"]]) == [[0, 1, 0]]
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_loss_and_grad_match_torch(seed):
     rng = np.random.RandomState(seed)
