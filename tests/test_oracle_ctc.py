@@ -84,6 +84,27 @@ def test_tensorflow_known_answer_beam_search():
     assert oc.greedy_decode(logits, [d["seq_len"]]) == [[0, 1, 0]]
 
 
+def test_tensorflow_known_answers_greedy_decoder_and_edit_distance():
+    """tests/golden/ctc_tf_greedy_known_answer.json: TF's own greedy-decoder test (repeats separated by a blank survive
+    the merge; frames past the sequence length and -inf inputs are harmless) and the worked example of the
+    tf.edit_distance docstring (empty truth -> inf, empty hypothesis -> 1.0, one missing label of two -> 0.5): the
+    conventions core/ctc_utils.py:42 and core/metrics.py:8 inherit."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ctc_tf_greedy_known_answer.json")))
+    with np.errstate(divide="ignore"):
+        logits = np.log(np.asarray(d["probs"], np.float64)).astype(np.float32)
+    assert oc.greedy_decode(logits, d["seq_lens"], blank=d["blank"]) == d["decoded"]
+    assert oc.greedy_decode(logits, d["seq_lens"]) == d["decoded"]                    # blank defaults to C - 1
+    e = d["edit_distance_doc_example"]
+    from asr_study_b200.core import metrics
+    for h, t, want in zip(e["hyp"], e["truth"], e["expected"]):
+        want = float(want)
+        for fn in (oc.ler, metrics.ler):
+            got = fn([t], [h])
+            assert (np.isinf(got) and np.isinf(want)) or got == want, (h, t, got, want)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_loss_and_grad_match_torch(seed):
     rng = np.random.RandomState(seed)

@@ -117,3 +117,42 @@ def test_clipnorm_scales_globally():
     n = om.clip_adam_step(p, g, st, clipnorm=400.0)
     assert abs(n - 1000.0) < 1e-3
     np.testing.assert_allclose(st["m"]["a"], 0.1 * 300.0 * 0.4, rtol=1e-6)
+
+
+def test_recurrence_structure_matches_torch_lstm_when_the_inner_activation_is_swapped(monkeypatch):
+    """Independent pin of everything in the BiLSTM restatement EXCEPT the inner activation: with hard_sigmoid swapped
+    for the logistic function (and its derivative), Bidirectional(LSTM) must be torch.nn.LSTM(bidirectional=True) —
+    same gate order (i, f, candidate, o: Keras-1 W/U column blocks = torch's weight row blocks), bias placement,
+    zero initial state, reverse direction run from the last frame and written back in time order, [fwd | bwd]
+    concatenation — forward outputs and every parameter / input gradient.  hard_sigmoid itself is pinned on its
+    definition (Keras-1 / Theano: clip(0.2 x + 0.5, 0, 1)) in test_hard_sigmoid_and_gate_order."""
+    import torch
+    monkeypatch.setattr(ol, "hard_sigmoid", lambda z: 1.0 / (1.0 + np.exp(-z)))
+    monkeypatch.setattr(ol, "_dhs", lambda a: a * (1.0 - a))
+    rng = np.random.RandomState(11)
+    N, T, D, H = 3, 9, 5, 7
+    p = {}
+    for d in "fb":
+        W, U, b = ol.init_lstm(rng, D, H)
+        p["W" + d], p["U" + d], p["b" + d] = W.astype(np.float64), U.astype(np.float64), (b + 0.1 * rng.randn(4 * H))
+    x = rng.randn(N, T, D)
+    dout = rng.randn(N, T, 2 * H)
+    out, caches = ol.bilstm_forward(x, p, dtype=np.float64)
+    dx, grads = ol.bilstm_backward(dout, caches)
+
+    net = torch.nn.LSTM(D, H, batch_first=True, bidirectional=True).double()
+    with torch.no_grad():
+        for d, suf in (("f", ""), ("b", "_reverse")):
+            getattr(net, "weight_ih_l0" + suf).copy_(torch.tensor(p["W" + d].T))
+            getattr(net, "weight_hh_l0" + suf).copy_(torch.tensor(p["U" + d].T))
+            getattr(net, "bias_ih_l0" + suf).copy_(torch.tensor(p["b" + d]))
+            getattr(net, "bias_hh_l0" + suf).zero_()
+    xt = torch.tensor(x, requires_grad=True)
+    yt, _ = net(xt)
+    np.testing.assert_allclose(out, yt.detach().numpy(), atol=1e-12)
+    (yt * torch.tensor(dout)).sum().backward()
+    np.testing.assert_allclose(dx, xt.grad.numpy(), atol=1e-11)
+    for d, suf in (("f", ""), ("b", "_reverse")):
+        np.testing.assert_allclose(grads["W" + d], getattr(net, "weight_ih_l0" + suf).grad.numpy().T, atol=1e-11)
+        np.testing.assert_allclose(grads["U" + d], getattr(net, "weight_hh_l0" + suf).grad.numpy().T, atol=1e-11)
+        np.testing.assert_allclose(grads["b" + d], getattr(net, "bias_ih_l0" + suf).grad.numpy(), atol=1e-11)
