@@ -1,6 +1,9 @@
 """Oracle: CTC loss/gradient, best-path and prefix-beam decode, LER (numpy).
 
-TEST INFRASTRUCTURE ONLY — see oracle/__init__.py.  PARITY UNPINNED: the
+TEST INFRASTRUCTURE ONLY — see oracle/__init__.py.  PARITY PINNED ON THE DEPENDENCY'S OWN KNOWN ANSWERS (the
+reference itself holds no test or golden vector for this path): loss, gradient, greedy and beam decode and the
+edit distance reproduce the constants of TensorFlow's ctc_loss_op_test.py / ctc_decoder_ops_test.py and the
+tf.edit_distance docstring (tests/golden/ctc_tf_*.json, tests/test_oracle_ctc.py).  The
 reference only *calls* TensorFlow 1.3.0 here (un-vendored, not installed):
   core/ctc_utils.py:68-70  tf.nn.ctc_loss(labels, time-major logits, seq_len)
   core/ctc_utils.py:42     tf.nn.ctc_greedy_decoder(y_pred, seq_len)
@@ -10,7 +13,7 @@ reference only *calls* TensorFlow 1.3.0 here (un-vendored, not installed):
 This file restates the published algorithms with TF-1.3 conventions (SURVEY.md
 8c hypotheses 4-7): softmax applied internally, blank = num_classes-1, standard
 merge-repeated topology, zero gradient past seq_len, argmax ties -> lowest
-index.  Independent pins live in tests/ (brute-force path enumeration,
+index.  Further independent pins live in tests/ (brute-force path enumeration,
 torch.nn.functional.ctc_loss, finite differences).
 """
 from __future__ import annotations

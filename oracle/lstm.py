@@ -2,7 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY — see oracle/__init__.py.  PARITY UNPINNED: the time
 loop, Bidirectional wrapper and autodiff live in un-vendored Keras 1.2.2 /
-TF 1.3.0; only the cell step is reference code.
+TF 1.3.0; only the cell step is reference code.  Independent pins (tests/test_oracle_lstm.py): torch.nn.LSTM on
+the whole bidirectional restatement with the inner activation swapped on both sides (structure: 1e-12), finite
+differences for BPTT.
 
 Follows /root/reference/core/layers.py:432-469 (LSTM.step, the non-LN / non-MI
 / non-zoneout branch that brsmv1 and graves2006 use by default) under
