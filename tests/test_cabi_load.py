@@ -50,3 +50,29 @@ def test_missing_library_is_an_error_not_a_fallback(monkeypatch):
     fresh = L._Lib()
     with pytest.raises(L.AsrError, match="no CPU"):
         fresh.load()
+
+
+def test_shape_queries_of_the_tensor_core_recurrences():
+    """Host-only queries (no launch): which (N, H) the tensor-core recurrences take, what the engine pads to, and that
+    the scratch every launch clears fits the buffer asr_lstm_flags_bytes() sizes."""
+    from asr_study_b200._lib import lib
+    from asr_study_b200.engine import TC_WIDTHS, tc_width
+    T = 999
+    for H in TC_WIDTHS:
+        for N in (8, 16, 32, 40, 64, 128, 256):          # any multiple of 8: more groups than one wave -> several launches
+            assert lib.asr_lstm_fuses_masks(T, N, H) == 1 and lib.asr_lstm_fuses_variants(T, N, H) == 1, (N, H)
+            assert lib.asr_lstm_persistent_supported(T, N, H, 1) == 1
+        for N in (1, 5, 13, 43):                          # ragged: the engine pads these (engine._padded_batch)
+            assert lib.asr_lstm_fuses_masks(T, N, H) == 0, (N, H)
+    for H in (100, 200, 320, 800, 960, 1024):             # no instantiation: zero-padded by the engine, or general cell
+        assert lib.asr_lstm_fuses_masks(T, 32, H) == 0
+        assert (tc_width(H) in TC_WIDTHS) == (128 < H <= 896)
+    assert lib.asr_lstm_persistent_supported(T, 2, 100, 1) == 1       # graves2006 / C1: the fp32 persistent engine
+    assert lib.asr_lstm_persistent_supported(T, 16, 800, 1) == 0      # un-padded BiLSTM-800: general cell only
+    # widest exchange ring of any launch (BPTT reduce-scatter, H = 768: 24 CTAs, three 16-sample groups per wave)
+    ring = 2 * 3 * 2 * 24 * 8 * 24 * 32 * 8
+    assert lib.asr_lstm_flags_bytes() >= 8192 + ring
+    # error path of the label-error-rate entry
+    from asr_study_b200 import AsrError
+    with pytest.raises(AsrError, match="null"):
+        lib.asr_edit_distance(None, 1, 1, None, None, None, 1, 1, None, None)
