@@ -9,7 +9,6 @@ the reference (un-imported names, core/models.py:122,129): out of scope, they ra
 """
 from __future__ import annotations
 
-import math
 import pickle
 import time
 
@@ -17,7 +16,6 @@ import numpy as np
 import torch
 
 from ..engine import AcousticEngine, ModelSpec, pack_labels
-from . import ctc_utils, metrics
 from .layers import LSTM
 
 _PAD = 16          # batch rows are padded to a multiple of 16 (tensor-core tile / 16-byte operand rows)

@@ -14,7 +14,7 @@ import ctypes as C
 import math
 import os
 import dataclasses
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import torch
