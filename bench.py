@@ -89,13 +89,21 @@ def synth_batch(n, seed):
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # --------------------------------------------------------------------------------------
-def cpu_step(pcm, labels, params, state):
+def cpu_step(pcm, labels, params, state, dropout=0.2):
     from oracle import mfcc as omf
     from oracle import model as om
-    feat = omf.MFCC(num_cep=13, d=True, dd=False)
+    feat = omf.MFCC(num_cep=13, d=True, dd=(F == 39))
     x, lens = omf.pad_batch([feat(c) for c in pcm])
-    _, ctc, grads, _ = om.loss_and_grads(params, x, lens, labels, weight_decay=1e-4, dtype=np.float32)
-    om.clip_adam_step(params, grads, state, lr=1e-3, clipnorm=400.0)
+    masks = None
+    if dropout > 0:                                        # the same work as the GPU arm: fresh variational masks per step
+        rng = state.setdefault("mask_rng", np.random.RandomState(17))
+        masks, D, n = {}, F, len(pcm)
+        for l in range(L):
+            masks[l] = {k: ((rng.rand(n, w) >= dropout) / (1.0 - dropout)).astype(np.float32)
+                        for k, w in (("Wf", D), ("Wb", D), ("Uf", H), ("Ub", H))}
+            D = 2 * H
+    _, ctc, grads, _ = om.loss_and_grads(params, x, lens, labels, weight_decay=1e-4, masks=masks, dtype=np.float32)
+    om.clip_adam_step(params, grads, state.setdefault("adam", {}), lr=1e-3, clipnorm=400.0)
     return float(ctc.mean())
 
 
@@ -125,7 +133,11 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "utt/s", "n_gpus": args.gpus, "steps": steps,
            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "C2: 10 s clips, 26-MFCC, 3xBiLSTM-512, Dense-28, CTC, Adam (CPU sample)"},
+           "config": {"workload": ("C2" if (F, H, L) == (26, 512, 3) else "custom (not the BASELINE config)") +
+                                  ": synthetic 16 kHz 10 s clips, %d-MFCC, %dxBiLSTM-%d, Dense-28, CTC, " % (F, L, H) +
+                                  "Adam(1e-3, clipnorm 400), l2 1e-4, variational dropout 0.2",
+                      "per_gpu_batch": n_sample, "global_batch": n_sample, "frames": T_FRAMES, "parallelism": "cpu",
+                      "input_pipeline": "in line"},
            "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
