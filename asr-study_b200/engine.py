@@ -390,12 +390,12 @@ class AcousticEngine:
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
         assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
+        if self.logical_h:                              # zero-padded width: widen caller-supplied masks (values irrelevant)
+            masks, zmasks = self._widen_masks(masks, zmasks)
         # ragged batches (the last batch of an epoch, predict.py's batch of 1): the tensor-core recurrences work on
         # groups of 8 / 16 samples, so the batch is padded with zero utterances up to the next group boundary.  Utterances
         # are independent (no batch statistics anywhere on the path) and backward() pads dlogits with zero rows, so
         # the padding contributes nothing to any gradient; callers only ever see the first N samples.
-        if self.logical_h:                              # zero-padded width: widen caller-supplied masks (values irrelevant)
-            masks, zmasks = self._widen_masks(masks, zmasks)
         Np = self._padded_batch(T, N)
         self._pad = (N, Np) if Np != N else None
         if self._pad:
