@@ -304,7 +304,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     if rank == 0:
-        if args.cpu_baseline:
+        if args.cpu_baseline and world == 1:            # the CPU port beside the GPU number: rank 0 at N = 1 only
             n_sample = 16
             v, dt = cpu_arm(n_sample, 1, 0)
             out["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": os.cpu_count(), "kind": "port",
