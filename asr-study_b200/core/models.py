@@ -230,31 +230,33 @@ class CTCModel(object):
         # accumulated on the device and read once per epoch.
         feed = _GeneratorFeed(generator, max(0, nb_epoch - initial_epoch) * samples_per_epoch, max_q_size,
                               nb_worker, self.device)
-        for epoch in range(initial_epoch, nb_epoch):
-            seen, t0 = 0, time.time()
-            agg_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
-            while seen < samples_per_epoch:
-                x, y = feed.get()
-                n = np.asarray(x[0]).shape[0]
-                agg_dev += self._train_stats(x) * n
-                seen += n
-            agg = agg_dev.cpu().numpy().astype(np.float64)
-            t_train = time.time() - t0
-            logs = dict(zip(["loss", "ctc_loss", "decoder_loss", "decoder_ler"], agg / max(seen, 1)))
-            if validation_data is not None and nb_val_samples:
-                v = self.evaluate_generator(validation_data, nb_val_samples)
-                logs.update({"val_" + k: val for k, val in zip(self.metrics_names, v)})
-            for k, v in logs.items():
-                self.history.setdefault(k, []).append(float(v))
-            if verbose:
-                show = {k: round(float(logs[k]), 4) for k in ("loss", "decoder_ler", "val_loss", "val_decoder_ler")
-                        if k in logs}
-                print("Epoch %d/%d - %.1fs - %s - %.1f utt/s" % (epoch + 1, nb_epoch, time.time() - t0, show,
-                                                                  seen / max(t_train, 1e-9)))
-            for cb in callbacks:
-                if hasattr(cb, "on_epoch_end"):
-                    cb.on_epoch_end(epoch, logs)
-        feed.close()
+        try:
+            for epoch in range(initial_epoch, nb_epoch):
+                seen, t0 = 0, time.time()
+                agg_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
+                while seen < samples_per_epoch:
+                    x, y = feed.get()
+                    n = np.asarray(x[0]).shape[0]
+                    agg_dev += self._train_stats(x) * n
+                    seen += n
+                agg = agg_dev.cpu().numpy().astype(np.float64)
+                t_train = time.time() - t0
+                logs = dict(zip(["loss", "ctc_loss", "decoder_loss", "decoder_ler"], agg / max(seen, 1)))
+                if validation_data is not None and nb_val_samples:
+                    v = self.evaluate_generator(validation_data, nb_val_samples)
+                    logs.update({"val_" + k: val for k, val in zip(self.metrics_names, v)})
+                for k, v in logs.items():
+                    self.history.setdefault(k, []).append(float(v))
+                if verbose:
+                    show = {k: round(float(logs[k]), 4) for k in ("loss", "decoder_ler", "val_loss", "val_decoder_ler")
+                            if k in logs}
+                    print("Epoch %d/%d - %.1fs - %s - %.1f utt/s" % (epoch + 1, nb_epoch, time.time() - t0, show,
+                                                                      seen / max(t_train, 1e-9)))
+                for cb in callbacks:
+                    if hasattr(cb, "on_epoch_end"):
+                        cb.on_epoch_end(epoch, logs)
+        finally:
+            feed.close()                                    # also on an exception: the worker must not outlive the call
         return self.history
 
     def evaluate_generator(self, generator, val_samples, max_q_size=10, nb_worker=1, decode_group=None, **kw):

@@ -50,3 +50,51 @@ def test_feed_surfaces_generator_errors():
     with pytest.raises(RuntimeError, match="generator broke"):
         feed.get()
     feed.close()
+
+
+def test_fit_generator_loop_consumes_exactly_the_epochs_and_aggregates_on_read_back(monkeypatch):
+    """The epoch loop of CTCModel.fit_generator with the device step replaced by a stub (CPU): it pulls exactly
+    nb_epoch * samples_per_epoch utterances through the worker, weights the per-batch metrics by batch size, calls the
+    callbacks once per epoch, and stops the worker when the step raises."""
+    import torch
+
+    from asr_study_b200.core.models import CTCModel
+    m = CTCModel.__new__(CTCModel)
+    m.device, m.history = torch.device("cpu"), {}
+    calls = []
+
+    def stats(x):
+        k = float(x[0][0, 0, 0])
+        calls.append(k)
+        return torch.tensor([k + 1.0, k, 0.0, 0.5])
+
+    monkeypatch.setattr(m, "_train_stats", stats, raising=False)
+    log = []
+    ends = []
+
+    class CB(object):
+        def set_model(self, model):
+            self.model = model
+
+        def on_epoch_end(self, epoch, logs):
+            ends.append((epoch, dict(logs)))
+
+    g = _gen(4, log)
+    hist = m.fit_generator(g, samples_per_epoch=12, nb_epoch=3, callbacks=[CB()], verbose=0, max_q_size=2, nb_worker=1)
+    assert calls == [float(k) for k in range(9)] and log == list(range(9))
+    assert [e for e, _ in ends] == [0, 1, 2]
+    np.testing.assert_allclose(hist["ctc_loss"], [1.0, 4.0, 7.0])          # batch means 0,1,2 | 3,4,5 | 6,7,8
+    np.testing.assert_allclose(hist["loss"], [2.0, 5.0, 8.0])
+    np.testing.assert_allclose(hist["decoder_ler"], [0.5, 0.5, 0.5])
+    assert next(g)[0][0][0, 0, 0] == 9.0
+
+    def boom(x):
+        raise RuntimeError("step failed")
+
+    monkeypatch.setattr(m, "_train_stats", boom, raising=False)
+    import threading
+    before = threading.active_count()
+    with pytest.raises(RuntimeError, match="step failed"):
+        m.fit_generator(_gen(4, []), samples_per_epoch=400, nb_epoch=1, verbose=0, max_q_size=2, nb_worker=1)
+    time.sleep(0.5)
+    assert threading.active_count() <= before                            # the worker was stopped
