@@ -143,7 +143,7 @@ class Feature:
 
     def _standarize(self, feats):
         """audio.py:70-75 — per-utterance CMVN, population std, +eps."""
-        feats = np.array(feats, dtype=np.float64)
+        feats = np.array(feats)              # in place in the reference: float64, or float32 behind a context window
         if self.mean_norm:
             feats -= np.mean(feats, axis=0, keepdims=True)
         if self.var_norm:
@@ -157,7 +157,10 @@ class Feature:
         if c == 0:
             return feats
         T, F = feats.shape
-        out = np.zeros((T, F * (2 * c + 1)), dtype=feats.dtype)
+        # audio.py:89-91 builds the widened matrix as np.array([], np.float32): with a context window the features are
+        # rounded to float32 BEFORE the CMVN of audio.py:65, which then runs in float32 (found by running the reference's
+        # own class, oracle/make_golden.py; without a context the whole chain stays float64)
+        out = np.zeros((T, F * (2 * c + 1)), dtype=np.float32)
         for off in range(-c, c + 1):
             lo, hi = max(0, -off), min(T, T - off)
             if hi <= lo:                       # utterance shorter than the offset: the whole block stays "empty_mfcc"

@@ -9,6 +9,9 @@ from oracle import model as om
 from tests.util_gpu import dev, norm_err
 
 pytestmark = pytest.mark.gpu
+# every parameter gradient, norm-wise per tensor (max|d| / max|ref|): ~3x the worst measured error (3.7e-3, H = 512, bf16
+# operands in the BPTT product and the gradient GEMMs); see DESIGN.md section 2
+GRAD_BAR = 1e-2
 
 
 def _setup(N, T, F, H, L, C, seed, wd=1e-4):
@@ -57,8 +60,8 @@ def test_train_step_gradients_and_adam_parity(N, T, F, H, L):
     np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
     got = eng.params.export("grad")
     for k, g in grads.items():
-        # 16-bit tensor-core operands (bf16 in the backward GEMMs): 3e-2 norm-wise per tensor
-        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+        # 16-bit tensor-core operands (bf16 in the backward GEMMs): 1e-2 norm-wise per tensor (GRAD_BAR)
+        assert norm_err(got[k], g) < GRAD_BAR, (k, norm_err(got[k], g))
     # optimiser: replay the oracle's clip+Adam on the DEVICE gradients -> isolates K9
     p0 = {k: v.copy() for k, v in params.items()}
     st = {}
@@ -99,7 +102,7 @@ def test_ragged_batch_is_padded_onto_the_tensor_core_engine(N, T, F, H, L, dropo
     np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
     got = eng.params.export("grad")
     for k, g in grads.items():
-        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+        assert norm_err(got[k], g) < GRAD_BAR, (k, norm_err(got[k], g))
     logits = eng.forward(feats, training=False)
     assert logits.shape == (T, N, C) and logits.is_contiguous()
     out, out_len = eng.greedy(logits, dev(lens))
@@ -149,7 +152,7 @@ def test_variational_dropout_forward_backward_parity(N, T, F, H, L):
     np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
     got = eng.params.export("grad")
     for k, g in grads.items():
-        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+        assert norm_err(got[k], g) < GRAD_BAR, (k, norm_err(got[k], g))
     # and it differs from the no-dropout forward (the masks really act)
     plain, _ = om.forward(params, x, dtype=np.float64)
     assert norm_err(got_logits, plain) > 1e-2
@@ -180,7 +183,7 @@ VARIANTS = [
 @pytest.mark.parametrize("sw", VARIANTS)
 def test_brsmv1_switches_train_step_parity(sw):
     """Whole training step with the switches on vs the fp64 oracle, same masks on both sides: logits 1e-3,
-    CTC loss 1e-3 rel, every parameter gradient (incl. the MI / LN vectors and the residual projection) 3e-2."""
+    CTC loss 1e-3 rel, every parameter gradient (incl. the MI / LN vectors and the residual projection) 1e-2."""
     from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
     N, T, F, H, L, C = 8, 18, 26, 64, 2, 28
     rng = np.random.RandomState(17)
@@ -223,7 +226,7 @@ def test_brsmv1_switches_train_step_parity(sw):
     got = eng.params.export("grad")
     assert set(got) == set(grads)
     for k, g in grads.items():
-        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+        assert norm_err(got[k], g) < GRAD_BAR, (k, norm_err(got[k], g))
     # inference phase: zoneout blends with (1 - level), no masks
     logits_eval = eng.forward(feats, training=False).cpu().numpy().transpose(1, 0, 2)
     p_after = {k: v.astype(np.float64) for k, v in eng.params.export("flat").items()}
@@ -268,7 +271,7 @@ def test_config4_stack_blstm800_logfbank40(pad_width, monkeypatch):
     got = eng.params.export("grad")
     for k, g in grads.items():
         assert got[k].shape == g.shape
-        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+        assert norm_err(got[k], g) < GRAD_BAR, (k, norm_err(got[k], g))
     if pad_width:                                    # the padding stays exactly zero through the optimiser step
         P = eng.params
         for k in ("l1.Wf", "l0.Uf", "l2.bb", "dense.W"):
@@ -327,12 +330,12 @@ def test_zero_padded_widths_on_the_tensor_core_engine(H, N, T, L, sw):
     assert set(got) == set(grads)
     for k, g in grads.items():
         assert got[k].shape == g.shape
-        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+        assert norm_err(got[k], g) < GRAD_BAR, (k, norm_err(got[k], g))
 
 
 def test_eyben_heterogeneous_stack_parity():
     """eyben (core/models.py:76-103): Dense(78) -> BiLSTM(120) -> BiLSTM(27) -> Dense(28), 39 features: whole train step
-    vs the fp64 oracle (logits 1e-3, loss 1e-3 rel, gradients 3e-2), widths that are not multiples of 8 included."""
+    vs the fp64 oracle (logits 1e-3, loss 1e-3 rel, gradients 1e-2), widths that are not multiples of 8 included."""
     from asr_study_b200.core import models
     from asr_study_b200.engine import pack_labels
     N, T, F, C = 16, 14, 39, 28
@@ -357,7 +360,7 @@ def test_eyben_heterogeneous_stack_parity():
     np.testing.assert_allclose(loss.cpu().numpy(), ctc, rtol=1e-3)
     got = eng.params.export("grad")
     for k, g in grads.items():
-        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+        assert norm_err(got[k], g) < GRAD_BAR, (k, norm_err(got[k], g))
 
 
 @pytest.mark.parametrize("H", [512, 256, 384, 128])
@@ -402,8 +405,60 @@ def test_elementwise_switches_on_the_tensor_core_engine(sw, H):
     got = eng.params.export("grad")
     assert set(got) == set(grads)
     for k, g in grads.items():
-        assert norm_err(got[k], g) < 3e-2, (k, norm_err(got[k], g))
+        assert norm_err(got[k], g) < GRAD_BAR, (k, norm_err(got[k], g))
     logits_eval = eng.forward(feats, training=False).cpu().numpy().transpose(1, 0, 2)
     p_after = {k: v.astype(np.float64) for k, v in eng.params.export("flat").items()}
     ref_eval, _ = om.forward_general(p_after, x, zoneout=spec.zoneout)
     assert norm_err(logits_eval, ref_eval) < 1e-3
+
+
+def test_full_size_c2_train_step_parity():
+    """ONE training step at the configuration bench.py times (BASELINE configs[1]: N = 32, T = 999, 26 MFCC,
+    3 x BiLSTM-512, 28 classes, l2 1e-4, variational dropout 0.2 with the SAME masks on both sides) against the fp64
+    oracle: logits 1e-3 norm-wise, per-utterance CTC loss 1e-3 relative, every parameter gradient GRAD_BAR norm-wise,
+    and the element-wise worst case reported next to it.  The measured errors are written to
+    gpurun_out/c2_full_parity.json (copied to profiles/ by the builder) so that the bars can be held against them."""
+    import json
+    import os
+    from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
+    N, T, F, H, L, C = 32, 999, 26, 512, 3, 28
+    rng = np.random.RandomState(2026)
+    params = om.init_params(F, H, L, C, seed=4321)
+    x = rng.randn(N, T, F).astype(np.float32)
+    lens = np.full(N, T, np.int32)
+    lens[1::4] = rng.randint(T // 2, T, size=len(lens[1::4]))        # ragged: zero frames behind the shorter utterances
+    for n in range(N):
+        x[n, lens[n]:] = 0.0
+    labels = om.synth_labels(99, N)
+    masks_np, D = {}, F
+    for l in range(L):
+        masks_np[l] = {k: ((rng.rand(N, w) >= 0.2) / 0.8).astype(np.float32) for k, w in (("Wf", D), ("Wb", D), ("Uf", H), ("Ub", H))}
+        D = 2 * H
+    eng = AcousticEngine(ModelSpec(F, H, L, C, weight_decay=1e-4, dropout=0.2), init_params=params)
+    masks_dev = {l: {k: dev(v) for k, v in m.items()} for l, m in masks_np.items()}
+    flat, off, mx = pack_labels(labels, "cuda")
+    feats = dev(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    loss = eng.train_step(feats, dev(lens), flat, off, mx, masks=masks_dev, lr=1e-3, clipnorm=400.0)
+    torch.cuda.synchronize()
+    assert eng.lstm_status() == 0 and not eng._use_general
+    got_logits = eng.last_logits.cpu().numpy().transpose(1, 0, 2)
+    got = eng.params.export("grad")
+    total, ctc, grads, ref_logits = om.loss_and_grads(params, x, lens, labels, weight_decay=0.0, masks=masks_np, dtype=np.float64)
+    rec = {"config": dict(N=N, T=T, F=F, H=H, L=L, C=C, dropout=0.2, ragged=True),
+           "logits_normwise": norm_err(got_logits, ref_logits),
+           "loss_rel_max": float(np.max(np.abs(loss.cpu().numpy() - ctc) / np.abs(ctc))),
+           "grad_normwise": {k: norm_err(got[k], g) for k, g in grads.items()},
+           "grad_l2_rel": {k: float(np.linalg.norm(got[k] - g) / max(np.linalg.norm(g), 1e-30)) for k, g in grads.items()}}
+    rec["grad_normwise_worst"] = max(rec["grad_normwise"].values())
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/c2_full_parity.json", "w") as f:
+        json.dump(rec, f, indent=1)
+    assert rec["logits_normwise"] < 1e-3, rec["logits_normwise"]
+    assert rec["loss_rel_max"] < 1e-3, rec["loss_rel_max"]
+    for k, e in rec["grad_normwise"].items():
+        assert e < GRAD_BAR, (k, e)
+    # best-path labels of the device logits: bit-exact against the oracle's decode of the same logits
+    out, out_len = eng.greedy(eng.last_logits, dev(lens))
+    ref_dec = oc.greedy_decode(got_logits, lens)
+    out, out_len = out.cpu().numpy(), out_len.cpu().numpy()
+    assert [out[n, :out_len[n]].tolist() for n in range(N)] == ref_dec

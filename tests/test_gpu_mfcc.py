@@ -21,15 +21,24 @@ def _clip(seed, secs):
 
 def _feat(kind):
     from asr_study_b200.preprocessing import audio
-    return {"mfcc26": audio.MFCC(num_cep=13, d=True, dd=False), "mfcc39": audio.MFCC(),
-            "logfbank40": audio.LogFbank(),
-            "mfcc13_raw": audio.MFCC(d=False, dd=False, mean_norm=False, var_norm=False)}[kind]
+    return {"mfcc26": lambda: audio.MFCC(num_cep=13, d=True, dd=False), "mfcc39": lambda: audio.MFCC(),
+            "logfbank40": lambda: audio.LogFbank(),
+            "logfbank123": lambda: audio.LogFbank(append_energy=True, d=True, dd=True),
+            "mfcc26_ctx2_s2": lambda: audio.MFCC(num_cep=13, d=True, dd=False, num_context=2, stride=2),
+            "mfcc26_ctx9": lambda: audio.MFCC(num_cep=13, d=True, dd=False, num_context=9),
+            "mfcc13_raw": lambda: audio.MFCC(d=False, dd=False, mean_norm=False, var_norm=False)}[kind]()
 
 
-@pytest.mark.parametrize("kind", ["mfcc26", "mfcc39", "logfbank40", "mfcc13_raw"])
+@pytest.mark.parametrize("kind", ["mfcc26", "mfcc39", "logfbank40", "logfbank123", "mfcc26_ctx2_s2", "mfcc26_ctx9", "mfcc13_raw"])
 def test_single_clip_matches_reference_golden(kind):
+    """golden = the reference's own preprocessing/audio.py classes run on the same clips (incl. the 10 s BASELINE clip
+    for the C2 / C4 features)"""
     f = _feat(kind)
+    seen = 0
     for seed, secs in zip(G["clip_seeds"], G["clip_seconds"]):
+        if f"{kind}_{int(seed)}" not in G.files:
+            continue
+        seen += 1
         got = f(_clip(seed, secs))
         ref = G[f"{kind}_{int(seed)}"]
         assert got.shape == ref.shape and got.dtype == np.float32
@@ -38,6 +47,22 @@ def test_single_clip_matches_reference_golden(kind):
             continue
         scale = max(1.0, np.abs(ref).max()) if kind == "mfcc13_raw" else 1.0
         assert np.abs(got - ref).max() <= TOL * scale, (kind, seed, np.abs(got - ref).max())
+    assert seen >= 2
+
+
+def test_fbank_class_matches_reference_call():
+    """FBank (audio.py:160-306).  The reference's FBank()(sig) itself raises (its _call returns the tuple (feat, energy),
+    which _standarize cannot take), so the pin is FBank._call's feat: un-normalised mel energies, compared element-wise
+    relative (sums of non-negative terms, fp32 kernel vs fp64 reference)."""
+    from asr_study_b200.preprocessing import audio
+    f = audio.FBank(mean_norm=False, var_norm=False)
+    assert str(f) == "fbank" and f.num_feats == 40
+    for seed, secs in zip(G["clip_seeds"], G["clip_seconds"]):
+        if f"fbank40_{int(seed)}" not in G.files:
+            continue
+        got, ref = f(_clip(seed, secs)), G[f"fbank40_{int(seed)}"]
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=1e-3)
 
 
 @pytest.mark.parametrize("time_major", [True, False])
