@@ -33,7 +33,8 @@ class LstmFwdArgs(C.Structure):
                 ("h16", C.c_void_p), ("hT16", C.c_void_p), ("h32", C.c_void_p),
                 ("gates", C.c_void_p), ("cell", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p),
                 ("mask_next", C.c_void_p), ("hm16", C.c_void_p), ("hmT16", C.c_void_p), ("hT16u", C.c_void_p),
-                ("mi", C.c_void_p), ("uh", C.c_void_p), ("zoneout", C.c_float), ("zmask", C.c_void_p)]
+                ("mi", C.c_void_p), ("uh", C.c_void_p), ("zoneout", C.c_float), ("zmask", C.c_void_p),
+                ("zx16", C.c_void_p), ("gates16", C.c_void_p), ("cell16", C.c_void_p), ("opts", C.c_int32)]
 
 
 class LstmBwdArgs(C.Structure):
@@ -43,7 +44,12 @@ class LstmBwdArgs(C.Structure):
                 ("dz32", C.c_void_p), ("dbias", C.c_void_p), ("flags", C.c_void_p), ("mask_u", C.c_void_p),
                 ("dh2", C.c_void_p), ("mask_dh", C.c_void_p),
                 ("mi", C.c_void_p), ("zx", C.c_void_p), ("uh", C.c_void_p), ("dmi", C.c_void_p), ("duhT16", C.c_void_p),
-                ("zoneout", C.c_float), ("zmask", C.c_void_p)]
+                ("zoneout", C.c_float), ("zmask", C.c_void_p),
+                ("gates16", C.c_void_p), ("cell16", C.c_void_p), ("opts", C.c_int32)]
+
+
+LSTM_SHARED_SM, LSTM_PIN_FP32, LSTM_GROUP16 = 1, 2, 4
+GEMM_BACKGROUND, GEMM_TILE128 = 1, 2
 
 
 class LstmVariant(C.Structure):
@@ -78,9 +84,10 @@ SIGNATURES = {
     "asr_gemm_tn": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _P]),
     "asr_gemm_tn_ex": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I32, _P]),
     "asr_lstm_flags_bytes": (_SZ, []),
-    "asr_lstm_fuses_masks": (_I32, [_I32, _I32, _I32]),
-    "asr_lstm_persistent_supported": (_I32, [_I32, _I32, _I32, _I32]),
-    "asr_lstm_fuses_variants": (_I32, [_I32, _I32, _I32]),
+    "asr_lstm_fuses_masks": (_I32, [_I32, _I32, _I32, _I32]),
+    "asr_lstm_persistent_supported": (_I32, [_I32, _I32, _I32, _I32, _I32]),
+    "asr_lstm_fuses_variants": (_I32, [_I32, _I32, _I32, _I32]),
+    "asr_lstm_fp16_storage": (_I32, [_I32, _I32, _I32, _I32]),
     "asr_lstm_forward": (_I32, [C.POINTER(LstmFwdArgs), _P]),
     "asr_lstm_backward": (_I32, [C.POINTER(LstmBwdArgs), _P]),
     "asr_lstm_cell_forward": (_I32, [C.POINTER(LstmFwdArgs), C.POINTER(LstmVariant), _P, _P]),
@@ -100,6 +107,8 @@ SIGNATURES = {
     "asr_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P]),
     "asr_mask_cast": (_I32, [_P, _I32, _I64, _P, _I32, _P, _I32, _I64, _I64, _I32, _I32, _P]),
     "asr_dropout_mask": (_I32, [_P, _I64, _F, C.c_uint64, C.c_uint64, _P]),
+    "asr_bernoulli_mask": (_I32, [_P, _I64, _F, _F, C.c_uint64, C.c_uint64, _P]),
+    "asr_add_gaussian_noise": (_I32, [_P, _I64, _I32, _I64, _F, C.c_uint64, C.c_uint64, _P]),
     "asr_add_mask": (_I32, [_P, _P, _P, _I64, _P, _I64, _I32, _P]),
     "asr_mask_combine": (_I32, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),
 }
@@ -132,7 +141,7 @@ class _Lib:
         fn = self.raw(name)
         res = SIGNATURES[name][0]
         if res is not _I32 or name in ("asr_version", "asr_mfcc_num_feats", "asr_mfcc_num_frames", "asr_lstm_fuses_masks",
-                                     "asr_lstm_persistent_supported", "asr_lstm_fuses_variants"):
+                                     "asr_lstm_persistent_supported", "asr_lstm_fuses_variants", "asr_lstm_fp16_storage"):
             return fn
 
         def checked(*a):

@@ -9,14 +9,18 @@ the reference (un-imported names, core/models.py:122,129): out of scope, they ra
 """
 from __future__ import annotations
 
-import pickle
+import io
+import json
+import os
 import time
 
 import numpy as np
 import torch
 
+from .._lib import AsrError
 from ..engine import AcousticEngine, ModelSpec, pack_labels
-from .layers import LSTM
+from .layers import (LSTM, Bidirectional, Dense, Dropout, GaussianNoise, Input, Tensor, TimeDistributed, _Merge,   # noqa: F401
+                     l2, merge, recurrent)
 
 _PAD = 16          # batch rows are padded to a multiple of 16 (tensor-core tile / 16-byte operand rows)
 
@@ -102,9 +106,8 @@ class CTCModel(object):
     def __init__(self, spec: ModelSpec, device=None, seed=4321, is_greedy=True, beam_width=100,
                  merge_repeated=True, input_std_noise=0.0):
         if device is None:
-            import os
             device = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
-        self.spec = spec
+        self.spec, self.seed = spec, int(seed)
         self.engine = AcousticEngine(spec, device=device, seed=seed)
         self.device = self.engine.device
         self.optimizer = Adam()
@@ -113,8 +116,7 @@ class CTCModel(object):
         self.allreduce = None
         self.world_size = 1
         self.history = {}
-        self._noise_rng = torch.Generator(device=self.device)
-        self._noise_rng.manual_seed(1234)
+        self._noise_offset = 0
 
     # ---- Keras-facing plumbing --------------------------------------------------
     def compile(self, loss=None, optimizer=None, metrics=None, loss_weights=None, **kw):
@@ -127,10 +129,22 @@ class CTCModel(object):
             return name
         raise ValueError("No such layer: %s" % name)
 
-    def set_data_parallel(self, allreduce, world_size):
+    def set_data_parallel(self, allreduce, world_size, rank=0):
         """allreduce(grad_slice) must SUM in place across ranks; it is called on slices that tile the flat gradient
-        bucket exactly once per step, each as soon as it is complete, and may return a handle with .wait()."""
+        bucket exactly once per step, each as soon as it is complete, and may return a handle with .wait().  The
+        parameters are initialised from the same seed on every rank; the dropout / zoneout / noise streams are offset
+        by the rank so that the replicas draw different masks for their different utterances."""
         self.allreduce, self.world_size = allreduce, int(world_size)
+        self.engine.set_rank(int(rank))
+
+    def check_status(self):
+        """Raises if a persistent recurrence kernel's watchdog fired (a peer CTA never delivered its slice): its outputs
+        are then partial and every later step would train on garbage.  One 4-byte read-back; the training loop calls it
+        once per epoch and the evaluator once per call, never per step."""
+        st = self.engine.lstm_status()
+        if st != 0:
+            raise AsrError("persistent BiLSTM kernel aborted (status %d: 1 = watchdog timeout, 2 = TMEM allocation); "
+                           "the step's gradients are not valid" % st)
 
     # ---- batches ------------------------------------------------------------------
     def _device_batch(self, x, x_len, labels, training):
@@ -139,8 +153,8 @@ class CTCModel(object):
         Np = (N + _PAD - 1) // _PAD * _PAD
         xt = torch.zeros(T, Np, F, dtype=torch.float32, device=self.device)
         xt[:, :N] = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 0, 2))).to(self.device)
-        if training and self.input_std_noise > 0:           # GaussianNoise(std), core/models.py:67,251
-            xt[:, :N] += self.input_std_noise * torch.randn(T, N, F, device=self.device, generator=self._noise_rng)
+        if training and self.input_std_noise > 0:           # GaussianNoise(std), core/models.py:67,251 (train phase only)
+            self._noise_offset = self.engine.add_gaussian_noise(xt, N, self.input_std_noise, self._noise_offset)
         lens = np.zeros(Np, np.int32)
         lens[:N] = np.asarray(x_len).reshape(-1)[:N]
         rows = _label_rows(labels)
@@ -207,13 +221,7 @@ class CTCModel(object):
     def _reg_dev(self):
         """sum of the l2(weight_decay) regularisers (core/models.py:263-264,279) as a device scalar — a reported metric,
         not part of the step (the optimiser folds the l2 gradient in itself)."""
-        P = self.engine.params
-        wd = self.spec.weight_decay
-        if not wd:
-            return torch.zeros((), dtype=torch.float32, device=self.device)
-        if getattr(self, "_decayf", None) is None:
-            self._decayf = P.decay.float()
-        return wd * torch.dot(P.flat * self._decayf, P.flat)
+        return self.engine.l2_penalty()
 
     def _reg(self):
         return float(self._reg_dev().item())
@@ -240,6 +248,7 @@ class CTCModel(object):
                     agg_dev += self._train_stats(x) * n
                     seen += n
                 agg = agg_dev.cpu().numpy().astype(np.float64)
+                self.check_status()
                 t_train = time.time() - t0
                 logs = dict(zip(["loss", "ctc_loss", "decoder_loss", "decoder_ler"], agg / max(seen, 1)))
                 if validation_data is not None and nb_val_samples:
@@ -266,18 +275,15 @@ class CTCModel(object):
         next group's forward passes (the beam search is one warp per utterance and latency-bound: a launch over 1 024
         utterances costs what a launch over 64 does), followed by the label-error-rate kernel; one read-back at the
         end.  The generator runs on a worker thread like fit_generator's.  decode_group=1 is the batch-by-batch order."""
-        import os
         eng, dev = self.engine, self.device
         beam = not self.decoder["is_greedy"]
         G = int(decode_group or (16 if beam else 4))
         main = torch.cuda.current_stream(dev)
         dec = torch.cuda.Stream(device=dev) if G > 1 else main
-        # the search CTAs spread over all SMs: let the forward kernels share an SM with them (csrc/lstm_tc2.cu
-        # exclusive_smem, csrc/api.cu engine selection) for the duration of this call
-        saved = {k: os.environ.get(k) for k in ("ASR_LSTM_EXCLUSIVE", "ASR_B200_GEMM")}
-        if beam and G > 1:
-            os.environ["ASR_LSTM_EXCLUSIVE"] = "0"
-            os.environ.setdefault("ASR_B200_GEMM", "tc1")
+        # the search CTAs spread over all SMs: let the forward kernels share an SM with them for the duration of this
+        # call (ASR_LSTM_SHARED_SM / ASR_GEMM_TILE128 flags of the C ABI, passed per launch by the engine)
+        shared_before = eng.shared_sm
+        eng.shared_sm = bool(beam and G > 1)
         C = self.spec.num_classes
         losses, seen = [], 0
         ler_sum = torch.zeros((), dtype=torch.float32, device=dev)
@@ -329,74 +335,166 @@ class CTCModel(object):
             main.wait_stream(dec)
         finally:
             feed.close()
-            for key, val in saved.items():
-                if val is None:
-                    os.environ.pop(key, None)
-                else:
-                    os.environ[key] = val
+            eng.shared_sm = shared_before
+        self.check_status()
         n_real = sum(int(l.numel()) for l in losses)
         ctc = float(torch.cat(losses).sum().item()) / max(n_real, 1)
         return [ctc + self._reg(), ctc, 0.0, float(ler_sum.item()) / max(n_real, 1)]
 
-    # ---- checkpoint (weights + optimiser state + meta; the .h5 wire format needs h5py: next row) ----
+    # ---- checkpoint: weights + optimiser state + meta (core/callbacks.py:36-56, utils/core_utils.py:49-131) ----------
+    # The reference writes Keras' HDF5 layout plus a `meta` group; h5py is not installable here, so the same content goes
+    # into one .npz archive: arrays `p/<name>`, `m/<name>`, `v/<name>` and a JSON document `config` (spec, optimiser,
+    # decoder, step, seeds / mask offsets, input_std_noise, meta).  Nothing in it is executable (no pickle).
     def save(self, path, meta=None):
         P = self.engine.params
-        blob = dict(spec=self.spec.__dict__, params=P.export("flat"), m=P.export("m"), v=P.export("v"),
-                    step=self.engine.step_count, optimizer=self.optimizer.__dict__, decoder=self.decoder,
-                    meta=meta or {})
-        with open(path, "wb") as f:
-            pickle.dump(blob, f)
+        arrays = {}
+        for which, tag in (("flat", "p"), ("m", "m"), ("v", "v")):
+            for k, v in P.export(which).items():
+                arrays["%s/%s" % (tag, k)] = v
+        spec = dict(self.spec.__dict__)
+        for k in ("layer_norm", "mi", "layer_hiddens"):
+            spec[k] = list(spec[k]) if spec[k] is not None else None
+        cfg = dict(format="asr_b200_ckpt/2", spec=spec, optimizer=dict(self.optimizer.__dict__), decoder=self.decoder,
+                   step=int(self.engine.step_count), seed=self.seed, mask_offset=int(self.engine._mask_offset),
+                   noise_offset=int(self._noise_offset), input_std_noise=self.input_std_noise, meta=meta or {})
+        arrays["config"] = np.frombuffer(json.dumps(cfg, default=_jsonable).encode("utf-8"), dtype=np.uint8)
+        buf = io.BytesIO()
+        np.savez(buf, **arrays)
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(buf.getvalue())
+        os.replace(tmp, path)
 
     @classmethod
-    def load(cls, path, device=None, **kw):
-        with open(path, "rb") as f:
-            blob = pickle.load(f)
-        m = cls(ModelSpec(**blob["spec"]), device=device, **kw)
+    def load(cls, path, device=None, mode="train", **kw):
+        """mode (utils/core_utils.py:49-59): 'train' keeps the saved decoder; 'eval' / 'predict' switch to the beam search
+        (width 400 unless overridden: utils/core_utils.py:67-72)."""
+        if mode not in ("train", "predict", "eval"):
+            raise ValueError("mode must be one of (train, predict, eval)")
+        with np.load(path, allow_pickle=False) as z:
+            cfg = json.loads(bytes(z["config"]).decode("utf-8"))
+            groups = {t: {k[2:]: z[k] for k in z.files if k.startswith(t + "/")} for t in ("p", "m", "v")}
+        spec = dict(cfg["spec"])
+        for k in ("layer_norm", "mi", "layer_hiddens"):
+            spec[k] = tuple(spec[k]) if spec.get(k) is not None else None
+        m = cls(ModelSpec(**spec), device=device, seed=cfg.get("seed", 4321), input_std_noise=cfg.get("input_std_noise", 0.0), **kw)
         P = m.engine.params
-        P.load(blob["params"])
-        for name in ("m", "v"):
-            P.load(blob[name], which=name)
-        m.engine.step_count = blob["step"]
-        o = blob["optimizer"]
+        P.load(groups["p"])
+        P.load(groups["m"], which="m")
+        P.load(groups["v"], which="v")
+        m.engine.step_count = int(cfg["step"])
+        m.engine._mask_offset = int(cfg.get("mask_offset", 0))
+        m._noise_offset = int(cfg.get("noise_offset", 0))
+        o = cfg["optimizer"]
         m.optimizer = Adam(o["lr"], o["beta_1"], o["beta_2"], o["epsilon"], o["clipnorm"]) if o["kind"] == "adam" \
             else SGD(o["lr"], o["momentum"], o["clipnorm"])
-        m.decoder = blob["decoder"]
-        return m, blob.get("meta", {})
+        m.decoder = dict(cfg["decoder"])
+        if mode in ("eval", "predict"):
+            m.decoder.update(is_greedy=kw.get("is_greedy", False), beam_width=kw.get("beam_width", 400))
+        return m, cfg.get("meta", {})
+
+
+def _jsonable(o):
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    return str(o)
 
 
 # -------------------------------------------------------------------------------------------
 # factories
 # -------------------------------------------------------------------------------------------
-def ctc_model(inputs, output, **kwargs):
-    """core/models.py:31-52.  ``inputs`` = num_features, ``output`` = list of LSTM layer records followed by
-    the number of classes: ``ctc_model(26, [LSTM(100), 28])`` is graves2006."""
-    *layers, num_classes = output
-    input_dense = kwargs.pop("input_dense", None)
-    widths = [l.output_dim for l in layers]
-    hs = set(widths)
-    if not layers or not all(isinstance(l, LSTM) for l in layers):
-        raise NotImplementedError("the engine stacks BiLSTM layers")
-    wd = kwargs.pop("weight_decay", 0.0)
+def _lower(inputs, output):
+    """Walk the record graph from `output` back to `inputs` and return the ModelSpec fields of the chain
+        Input -> [GaussianNoise] -> [TimeDistributed(Dense(P))] -> [Dropout] ->
+        L x ( Bidirectional(LSTM) [-> merge([., previous], 'sum')] ) -> TimeDistributed(Dense(C))
+    which is every topology of core/models.py on the BiLSTM hot path (graves2006 :55-73, eyben :76-103, brsmv1 :217-281)
+    and the README recipe."""
+    if not isinstance(inputs, Tensor) or not isinstance(output, Tensor):
+        raise TypeError("ctc_model(inputs, output) takes the symbolic input and logits tensors (core/models.py:31-52)")
+    t = output
+    if not isinstance(t.producer, TimeDistributed):
+        raise NotImplementedError("the logits must come from TimeDistributed(Dense(num_classes)) (core/models.py:71, 278)")
+    num_classes, decays = t.producer.layer.output_dim, [t.producer.layer.weight_decay]
+    t = t.parents[0]
+    lstms, residual = [], None
+    while isinstance(t.producer, (Bidirectional, _Merge)):
+        if isinstance(t.producer, _Merge):
+            new_o, skip = t.parents
+            if not isinstance(new_o.producer, Bidirectional) or new_o.parents[0] is not skip:
+                raise NotImplementedError("merge([new_o, o]) must add a Bidirectional layer's output to its own input "
+                                          "(core/models.py:273-274)")
+            residual, t = t.producer.mode, new_o
+            res_here = True
+        else:
+            res_here = False
+        lstms.append((t.producer.layer, res_here))
+        t = t.parents[0]
+    lstms.reverse()
+    if not lstms:
+        raise NotImplementedError("the engine stacks Bidirectional(LSTM) layers; none found between inputs and logits")
+    if residual is not None and not all(r for _, r in lstms):
+        raise NotImplementedError("the residual merge is applied to every layer or to none (core/models.py:260-276)")
+    input_dropout, proj, noise = None, None, 0.0
+    if isinstance(t.producer, Dropout):
+        input_dropout, t = t.producer.p, t.parents[0]
+    if isinstance(t.producer, TimeDistributed):
+        proj, t = t.producer.layer, t.parents[0]
+        decays.append(proj.weight_decay)
+    if isinstance(t.producer, GaussianNoise):
+        noise, t = t.producer.sigma, t.parents[0]
+    if t is not inputs or t.producer is not None:
+        raise NotImplementedError("unsupported layer between the input and the first Bidirectional(LSTM): %r"
+                                  % type(t.producer).__name__)
+    layers = [l for l, _ in lstms]
+    for l in layers:
+        decays += [0.0 if l.W_regularizer is None else l.W_regularizer.l2 if isinstance(l.W_regularizer, l2) else float(l.W_regularizer),
+                   0.0 if l.U_regularizer is None else l.U_regularizer.l2 if isinstance(l.U_regularizer, l2) else float(l.U_regularizer)]
+    if len(set(decays)) != 1:
+        raise NotImplementedError("the l2 weight decay is tied across the LSTM and Dense layers (core/models.py:227-230)")
     dps = {(l.dropout_W, l.dropout_U) for l in layers}
-    if len(dps) != 1 or len(set(dps.pop())) != 1:
+    if len(dps) != 1 or len(set(next(iter(dps)))) != 1:
         raise NotImplementedError("dropout_W and dropout_U are tied and equal across layers (core/models.py:229-230)")
     sw = {(l.zoneout_h, l.layer_norm, l.mi) for l in layers}
     if len(sw) != 1:
         raise NotImplementedError("zoneout / layer_norm / mi are tied across layers (core/models.py:260-271)")
     zo, ln, mi = sw.pop()
-    spec = ModelSpec(int(inputs), widths[0], len(layers), int(num_classes), float(wd), kwargs.pop("name", "ctc_model"),
-                     float(layers[0].dropout_W), zoneout=zo, layer_norm=ln, mi=mi, residual=kwargs.pop("residual", None),
-                     input_dropout=bool(kwargs.pop("input_dropout", False)),
-                     layer_hiddens=tuple(widths) if len(hs) > 1 else None, input_dense=input_dense)
+    dp = float(layers[0].dropout_W)
+    if input_dropout is not None and input_dropout != dp and dp > 0:
+        raise NotImplementedError("the input Dropout shares the layers' dropout level (core/models.py:257-258)")
+    widths = [l.output_dim for l in layers]
+    num_features = inputs.shape[-1]
+    if residual is not None and (proj is None or proj.output_dim != 2 * widths[0]):
+        raise NotImplementedError("the residual stack needs the TimeDistributed(Dense(2 * num_hiddens)) input projection "
+                                  "(core/models.py:253-255)")
+    fields = dict(num_features=int(num_features), num_hiddens=widths[0], num_layers=len(layers), num_classes=int(num_classes),
+                  weight_decay=float(decays[0]), dropout=dp if input_dropout is None else float(input_dropout or dp),
+                  zoneout=zo, layer_norm=ln, mi=mi, residual=residual, input_dropout=input_dropout is not None and input_dropout > 0,
+                  layer_hiddens=tuple(widths) if len(set(widths)) > 1 else None,
+                  input_dense=(proj.output_dim if (proj is not None and residual is None) else None))
+    return fields, noise
+
+
+def ctc_model(inputs, output, **kwargs):
+    """core/models.py:31-52: given the acoustic net's input tensor [N, T, F] and its logits tensor [N, T, C], returns the
+    model [inputs, labels, inputs_length] -> [CTC loss per utterance, greedy decode].  Keyword arguments (device, seed,
+    is_greedy, beam_width, merge_repeated, name) configure the engine / decoder."""
+    fields, noise = _lower(inputs, output)
+    spec = ModelSpec(name=kwargs.pop("name", "ctc_model"), **fields)
+    kwargs.setdefault("input_std_noise", noise)
     return CTCModel(spec, **kwargs)
 
 
 def graves2006(num_features=26, num_hiddens=100, num_classes=28, std=.6, **kw):
     """core/models.py:55-73: GaussianNoise(std) -> Bidirectional(LSTM(H)) -> TimeDistributed(Dense(C))."""
-    if num_hiddens % 64:
-        # the kernels take any H through the fp32 engine; H=100 is the reference default
-        pass
-    return ctc_model(num_features, [LSTM(num_hiddens), num_classes], name="graves2006", input_std_noise=std, **kw)
+    x = Input(name="inputs", shape=(None, num_features))
+    o = GaussianNoise(std)(x)
+    o = Bidirectional(LSTM(num_hiddens, return_sequences=True, consume_less="gpu"))(o)
+    o = TimeDistributed(Dense(num_classes))(o)
+    return ctc_model(x, o, name="graves2006", **kw)
 
 
 def eyben(num_features=39, num_hiddens=[78, 120, 27], num_classes=28, **kw):
@@ -404,10 +502,15 @@ def eyben(num_features=39, num_hiddens=[78, 120, 27], num_classes=28, **kw):
     TimeDistributed(Dense(C)); a zero entry drops that layer (:90-99).  Heterogeneous widths run on the general-cell
     engine (any H <= 1024)."""
     assert len(num_hiddens) == 3
-    layers = [LSTM(n) for n in num_hiddens[1:] if n]
-    if not layers:
-        raise NotImplementedError("eyben without a recurrent layer is a plain Dense stack, outside the BiLSTM hot path")
-    return ctc_model(num_features, layers + [num_classes], name="eyben", input_dense=num_hiddens[0] or None, **kw)
+    x = Input(name="inputs", shape=(None, num_features))
+    o = x
+    if num_hiddens[0]:
+        o = TimeDistributed(Dense(num_hiddens[0]))(o)
+    for n in num_hiddens[1:]:
+        if n:
+            o = Bidirectional(LSTM(n, return_sequences=True, consume_less="gpu"))(o)
+    o = TimeDistributed(Dense(num_classes))(o)
+    return ctc_model(x, o, name="eyben", **kw)
 
 
 def maas(*a, **k):
@@ -422,12 +525,22 @@ def brsmv1(num_features=39, num_classes=28, num_hiddens=256, num_layers=5, dropo
            input_dropout=False, input_std_noise=.0, weight_decay=1e-4, residual=None, layer_norm=None, mi=None,
            activation='tanh', **kw):
     """core/models.py:217-281: N x BiLSTM + Dense trunk with l2(weight_decay) and variational dropout
-    (dropout_W = dropout_U = dropout, masks constant over time) on the tensor-core engines.  zoneout, layer_norm,
-    mi, residual='sum' (with its TimeDistributed(Dense(2H)) input projection) and input_dropout switch the
-    recurrence to the general-cell engine (csrc/lstm_cell.cu)."""
-    if residual not in (None, "sum"):
-        raise NotImplementedError("merge mode %r: only 'sum' keeps the layer width the next Bidirectional expects" % residual)
-    layers = [LSTM(num_hiddens, zoneout_c=zoneout, zoneout_h=zoneout, mi=mi, layer_norm=layer_norm,
-                   activation=activation, dropout_W=dropout, dropout_U=dropout) for _ in range(num_layers)]
-    return ctc_model(num_features, layers + [num_classes], name="brsmv1", weight_decay=weight_decay,
-                     input_std_noise=input_std_noise, residual=residual, input_dropout=input_dropout, **kw)
+    (dropout_W = dropout_U = dropout, masks constant over time) on the tensor-core engines; zoneout and mi are
+    template switches of the same kernels, layer_norm / residual='sum' (with its TimeDistributed(Dense(2H)) input
+    projection) / input_dropout run on the general-cell engine (csrc/lstm_cell.cu)."""
+    x = Input(name="inputs", shape=(None, num_features))
+    o = x
+    if input_std_noise is not None:
+        o = GaussianNoise(input_std_noise)(o)
+    if residual is not None:
+        o = TimeDistributed(Dense(num_hiddens * 2, W_regularizer=l2(weight_decay)))(o)
+    if input_dropout:
+        o = Dropout(dropout)(o)
+    for _ in range(num_layers):
+        new_o = Bidirectional(LSTM(num_hiddens, return_sequences=True, W_regularizer=l2(weight_decay),
+                                   U_regularizer=l2(weight_decay), dropout_W=dropout, dropout_U=dropout,
+                                   zoneout_c=zoneout, zoneout_h=zoneout, mi=mi, layer_norm=layer_norm,
+                                   activation=activation))(o)
+        o = merge([new_o, o], mode=residual) if residual is not None else new_o
+    o = TimeDistributed(Dense(num_classes, W_regularizer=l2(weight_decay)))(o)
+    return ctc_model(x, o, name="brsmv1", **kw)

@@ -63,7 +63,6 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {      // two LL
 __device__ __forceinline__ void st_volatile_v2(uint2* p, uint2 v) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
-
 // NB = samples per CTA group (8 or 16).  NB = 8 spreads N = 32 over 128 CTAs instead of 64: the MMA still runs at
 // N = 16 (rows 8..15 of the B operand stay zero, their accumulator columns are never read) and costs the same issue
 // slots, while the LL exchange, the shared-memory staging and the gate math per CTA are halved.
@@ -235,8 +234,6 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       // ---- pull h_{t-1} of this group: poll the LL words (data + tag in one 8-byte access) ----------
       // side outputs of the previous step first: the extra ~350 cycles let the peers' LL words land in L2, so
       // the first probe usually hits (a probe that races the store costs a second full L2 round trip)
-      if (p_t >= 0) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);
-      if (delay1 > 0) __nanosleep(delay1);
       // warp w polls (and stages) the K range [H/4 * w, H/4 * (w + 1)) of all NB samples: V4W 16-byte accesses
       // (2 LL words = 4 K columns each) per sample, consecutive lanes on consecutive addresses
       const uint4* src = reinterpret_cast<const uint4*>(xb + (size_t)((s - 1) & 1) * WORDS);
@@ -250,6 +247,8 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         const int f = q * 32 + lane;
         vidx[q] = (f / V4W) * (H / 4) + warp * V4W + (f % V4W);
       }
+      if (p_t >= 0) side_stores(p_t, p_hv, p_gi, p_gf, p_gg, p_go, p_cs);
+      if (delay1 > 0) __nanosleep(delay1);
       uint4 w[QPT];
 #pragma unroll
       for (int q = 0; q < QPT; ++q) w[q] = ld_volatile_v4(src + vidx[q]);
@@ -383,318 +382,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward through time (v2): 4 x 4 CTA grid per (direction, batch group), H = 512
-//   CTA (r, c) owns the 32 hidden units [128r + 32c, +32) for the element-wise BPTT step, and the
-//   [128 units of row block r] x [512 gate columns of column block c] tile of U (bf16) in TMEM.
-//   Column block c = the gate columns (g, u) of the units owned by the four CTAs (., c).
-//   step:  hop 1  gather dz_{prev} of column c (LL ring, written by the 4 CTAs of the column)
-//          MMA    P_c[128 units of row r][n] = U_tile . dz_c^T          (32 TS-mode tcgen05.mma)
-//          hop 2  warp w holds the rows owned by CTA (r, w): send them there (LL ring, fp32)
-//                 and sum the four partials that arrive for my own units -> dh_rec
-//          element-wise BPTT -> dz (published to hop 1 of the next step) + side outputs
-// ------------------------------------------------------------------------------------------------
-template <int NB>
-__global__ void __launch_bounds__(THREADS, 1)
-bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf1, uint2* __restrict__ xbuf2, int delay1,
-           int delay2) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int H = 512, K4 = 4 * H;
-  constexpr int KC = 8;                                  // 512-wide K block = 8 chunks of 64
-  constexpr int B_CHUNK = NM * 128;
-  constexpr int WORDS1 = NB * 256;                       // hop-1 LL words per (dir, grp, column, parity)
-  constexpr int WPT1 = WORDS1 / THREADS;
-  constexpr int WORDS2 = NB * 32;                        // hop-2 LL words per (dir, grp, r, recv, send, parity)
-  constexpr int NPT = NB / 4;
-  const int T = a.T, N = a.N;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
-  const int r = cta >> 2, c = cta & 3;
-  const int u0 = cta * UPC, n0 = grp * NB;
-
-  uint8_t* sB = smem;
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sB + KC * B_CHUNK);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  __shared__ int s_dead;
-
-  if (tid == 0) {
-    tc::mbar_init(mma_bar, 4);   // one tcgen05.commit per warp
-    tc::fence_mbar_init();
-    s_dead = 0;
-  }
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < KC * B_CHUNK / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
-  tc::tcgen05_fence_before();
-  __syncthreads();
-  tc::tcgen05_fence_after();
-  if (*tmem_slot != 0u) { if (tid == 0) atomicExch(flags + STATUS_IDX, 2); }
-  constexpr uint32_t tmem = 0u;           // whole TMEM allocated -> base column 0 (see forward kernel)
-
-  // one-time: U tile -> TMEM.  lane m <-> unit 128r + m ; K index k = (r'*4 + g)*32 + j <-> gate column
-  // g*H + 128r' + 32c + j   (two bf16 per 32-bit column)
-  {
-    const __nv_bfloat16* Ub = reinterpret_cast<const __nv_bfloat16*>(a.U16) + (size_t)dir * H * K4 +
-                              (size_t)(128 * r + tid) * K4;
-#pragma unroll 1
-    for (int sp = 0; sp < 8; ++sp) {                     // 2 segments (64 K elements) per tcgen05.st
-      uint32_t rr[32];
-#pragma unroll
-      for (int hs = 0; hs < 2; ++hs) {
-        const int seg = 2 * sp + hs, rp = seg >> 2, g = seg & 3;
-        const uint4* src = reinterpret_cast<const uint4*>(Ub + g * H + 128 * rp + 32 * c);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 v = __ldg(src + q);
-          rr[hs * 16 + 4 * q] = v.x; rr[hs * 16 + 4 * q + 1] = v.y; rr[hs * 16 + 4 * q + 2] = v.z; rr[hs * 16 + 4 * q + 3] = v.w;
-        }
-      }
-      tc::tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + A_COL + sp * 32, rr);
-    }
-    tc::tmem_st_wait();
-  }
-  tc::tcgen05_fence_before();
-  __syncthreads();
-  tc::tcgen05_fence_after();
-
-  const uint32_t idesc = tc::umma_idesc_f16(128, NM, 1);
-  const uint32_t sB_addr = tc::smem_u32(sB);
-  const int u = u0 + lane;
-  float dc_carry[NPT], mu[NPT], md0[NPT], md1[NPT], db[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int i = 0; i < NPT; ++i) {
-    dc_carry[i] = 0.0f;
-    mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;
-    // dL/d(output) = (dz_f . Wf^T) * B_Wf + (dz_b . Wb^T) * B_Wb of the layer above: the two GEMM results arrive
-    // separately (dh, dh2) and are combined here with the masks (constant over time) instead of by a combine kernel
-    md0[i] = a.mask_dh ? a.mask_dh[((size_t)0 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
-    md1[i] = a.mask_dh ? a.mask_dh[((size_t)1 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
-  }
-
-  int* status = flags + STATUS_IDX;
-  // hop 1: [(dir,grp)][column 4][parity 2][WORDS1]
-  uint2* x1 = xbuf1 + ((size_t)(dir * G + grp) * 4 + c) * 2 * WORDS1;
-  // hop 2: [(dir,grp)][r 4][recv 4][send 4][parity 2][WORDS2]
-  uint2* x2row = xbuf2 + ((size_t)(dir * G + grp) * 4 + r) * 4 * 4 * 2 * WORDS2;
-  __nv_bfloat16* dz16 = reinterpret_cast<__nv_bfloat16*>(a.dz16);
-  const size_t R = (size_t)T * N;
-
-  auto side_stores = [&](int t, const float (&dz)[NPT][4]) {
-#pragma unroll
-    for (int i = 0; i < NPT; ++i) {
-      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        dz16[(row * 2 + dir) * K4 + g * H + u] = __float2bfloat16_rn(dz[i][g]);
-        if (a.dz32) a.dz32[(row * 2 + dir) * K4 + g * H + u] = dz[i][g];
-      }
-    }
-    if (a.dzT16) {
-      static_assert(NPT == 4 || NPT == 2, "packed transposed store: 2 or 4 samples per thread");
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        __nv_bfloat16* dstT = reinterpret_cast<__nv_bfloat16*>(a.dzT16) + (size_t)(dir * K4 + g * H + u) * R + (size_t)t * N + n0 + warp * NPT;
-        const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]);
-        if constexpr (NPT == 4) {
-          const __nv_bfloat162 p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&p0);
-          pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-          *reinterpret_cast<uint2*>(dstT) = pk;
-        } else {
-          *reinterpret_cast<__nv_bfloat162*>(dstT) = p0;
-        }
-      }
-    }
-  };
-  float p_dz[NPT][4];
-  int p_t = -1;
-
-  PROF_DECL;
-  for (int s = 0; s < T; ++s) {
-    PROF(7);
-    const int t = dir ? s : (T - 1 - s);
-    const int t_fprev = dir ? (t + 1) : (t - 1);
-    const bool has_fprev = dir ? (t + 1 < T) : (t > 0);
-    float dho[NPT], dho2[NPT], gi[NPT], gf[NPT], gg[NPT], go[NPT], cc[NPT], cp[NPT];
-#pragma unroll
-    for (int i = 0; i < NPT; ++i) {
-      const size_t row = (size_t)t * N + n0 + warp * NPT + i;
-      dho[i] = __ldg(a.dh + row * 2 * H + dir * H + u);            // consumed after both hops: the load latency stays hidden
-      dho2[i] = a.dh2 ? __ldg(a.dh2 + row * 2 * H + dir * H + u) : 0.0f;
-      const float* gp = a.gates + (row * 2 + dir) * 4 * H;
-      gi[i] = __ldg(gp + u); gf[i] = __ldg(gp + H + u); gg[i] = __ldg(gp + 2 * H + u); go[i] = __ldg(gp + 3 * H + u);
-      cc[i] = __ldg(a.cell + (row * 2 + dir) * H + u);
-      cp[i] = has_fprev ? __ldg(a.cell + ((((size_t)t_fprev * N + n0 + warp * NPT + i) * 2 + dir) * H + u)) : 0.0f;
-    }
-    float dh_rec[NPT];
-#pragma unroll
-    for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
-    if (s > 0) {
-      const uint32_t tag = (uint32_t)s;
-      const int par = (s - 1) & 1;
-      // ---- hop 1: dz_{prev} of my column block -> smem B ------------------------------------------
-      {
-        if (p_t >= 0) side_stores(p_t, p_dz);              // first: gives the peers' LL words time to land in L2
-        if (delay1 > 0) __nanosleep(delay1);
-        const uint4* src = reinterpret_cast<const uint4*>(x1 + (size_t)par * WORDS1) + tid;
-        constexpr int QPT1 = WPT1 / 2;
-        uint4 w[QPT1];
-#pragma unroll
-        for (int q = 0; q < QPT1; ++q) w[q] = ld_volatile_v4(src + q * THREADS);
-        bool ok;
-        long long t0 = 0;
-        do {
-          ok = true;
-#pragma unroll
-          for (int q = 0; q < QPT1; ++q)
-            if (w[q].y != tag || w[q].w != tag) {
-              w[q] = ld_volatile_v4(src + q * THREADS);
-              ok = false;
-            }
-          if (!ok) {
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > WATCHDOG_CYCLES) {
-              atomicExch(status, 1);
-              s_dead = 1;
-              break;
-            }
-          }
-        } while (!ok);
-        PROF(0);
-#pragma unroll
-        for (int q = 0; q < QPT1; ++q) {
-          const int i = 2 * (tid + q * THREADS);
-          const int n = i >> 8, k = 2 * (i & 255);
-          *reinterpret_cast<uint2*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = make_uint2(w[q].x, w[q].z);
-        }
-      }
-      // per-warp MMA issue (see the forward kernel): thread tid staged K columns [4 tid, 4 tid + 4) of every sample,
-      // so warp w owns K range [128 w, 128 (w + 1)) = MMAs 8w .. 8w + 7 and TMEM accumulator w
-      tc::fence_proxy_async_smem();
-      __syncwarp();
-      PROF(1);
-      if (tc::elect_one_sync()) {
-        tc::tcgen05_fence_after();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int kb = warp * 8 + j;
-          const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-          tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL + kb * 8, bd, idesc, j > 0);
-        }
-        tc::umma_commit(mma_bar);
-      }
-      if (!tc::mbar_wait(mma_bar, (uint32_t)((s - 1) & 1), WATCHDOG_CYCLES)) {
-        atomicExch(status, 1);
-        s_dead = 1;
-      }
-      tc::tcgen05_fence_after();
-      PROF(2);
-      // ---- hop 2 (send): my warp's 32 rows are the units of CTA (r, warp) -----------------------------
-      {
-        uint32_t r0[NB], r1[NB], r2[NB], r3[NB];
-        const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
-        tc::tmem_ldn(tq, r0);
-        tc::tmem_ldn(tq + NM, r1);
-        tc::tmem_ldn(tq + 2 * NM, r2);
-        tc::tmem_ldn(tq + 3 * NM, r3);
-        tc::tmem_ld_wait();
-        uint2* dst = x2row + ((size_t)(warp * 4 + c) * 2 + par) * WORDS2 + lane;
-#pragma unroll
-        for (int n = 0; n < NB; ++n) {
-          const float pv = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) + (__uint_as_float(r2[n]) + __uint_as_float(r3[n]));
-          st_volatile_v2(dst + n * 32, make_uint2(__float_as_uint(pv), tag));
-        }
-      }
-      tc::tcgen05_fence_before();
-      PROF(3);
-      // ---- hop 2 (receive): four partials for each of my (unit, sample) ---------------------------------
-      {
-        uint2 w[4 * NPT];
-        if (delay2 > 0) __nanosleep(delay2);
-        const uint2* src = x2row + ((size_t)(c * 4) * 2 + par) * WORDS2 + lane;   // + send*2*WORDS2 + n*32
-#pragma unroll
-        for (int sd = 0; sd < 4; ++sd)
-#pragma unroll
-          for (int i = 0; i < NPT; ++i) w[sd * NPT + i] = ld_volatile_v2(src + (size_t)sd * 2 * WORDS2 + (warp * NPT + i) * 32);
-        bool ok;
-        long long t0 = 0;
-        do {
-          ok = true;
-#pragma unroll
-          for (int sd = 0; sd < 4; ++sd)
-#pragma unroll
-            for (int i = 0; i < NPT; ++i)
-              if (w[sd * NPT + i].y != tag) {
-                w[sd * NPT + i] = ld_volatile_v2(src + (size_t)sd * 2 * WORDS2 + (warp * NPT + i) * 32);
-                ok = false;
-              }
-          if (!ok) {
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > WATCHDOG_CYCLES) {
-              atomicExch(status, 1);
-              s_dead = 1;
-              break;
-            }
-          }
-        } while (!ok);
-#pragma unroll
-        for (int i = 0; i < NPT; ++i)
-          dh_rec[i] = mu[i] * ((__uint_as_float(w[i].x) + __uint_as_float(w[NPT + i].x)) +
-                               (__uint_as_float(w[2 * NPT + i].x) + __uint_as_float(w[3 * NPT + i].x)));
-      }
-      __syncthreads();                                   // all warps done with TMEM D and sB before the next step
-      PROF(4);
-      if (s_dead) break;
-    }
-    float dz[NPT][4];
-    uint2* xo = x1 + (size_t)(s & 1) * WORDS1;
-#pragma unroll
-    for (int i = 0; i < NPT; ++i) {
-      const float dh = fmaf(dho2[i], md1[i], fmaf(dho[i], md0[i], dh_rec[i]));
-      const float tch = asr::tanh_fast(cc[i]);
-      const float d_o = dh * tch * asr::hard_sigmoid_grad(go[i]);
-      const float dc = dc_carry[i] + dh * go[i] * (1.0f - tch * tch);
-      dz[i][0] = dc * gg[i] * asr::hard_sigmoid_grad(gi[i]);
-      dz[i][1] = dc * cp[i] * asr::hard_sigmoid_grad(gf[i]);
-      dz[i][2] = dc * gi[i] * (1.0f - gg[i] * gg[i]);
-      dz[i][3] = d_o;
-      dc_carry[i] = dc * gf[i];
-      // publish to hop 1 of the next step: K index k = (r*4 + g)*32 + lane, pairs of adjacent units
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float other = __shfl_down_sync(0xffffffffu, dz[i][g], 1);
-        if (!(lane & 1)) {
-          const __nv_bfloat162 pk = __floats2bfloat162_rn(dz[i][g], other);
-          uint2 wv;
-          wv.x = *reinterpret_cast<const uint32_t*>(&pk);
-          wv.y = (uint32_t)(s + 1);
-          st_volatile_v2(xo + (size_t)(warp * NPT + i) * 256 + (((r * 4 + g) * 32 + lane) >> 1), wv);
-        }
-      }
-    }
-    PROF(5);
-    // stash the side outputs (dz for the dW/dU/dX GEMMs); written while the next hop-1 poll is in flight
-#pragma unroll
-    for (int i = 0; i < NPT; ++i)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        db[g] += dz[i][g];
-        p_dz[i][g] = dz[i][g];
-      }
-    p_t = t;
-    PROF(6);
-  }
-  if (p_t >= 0 && !s_dead) side_stores(p_t, p_dz);
-  PROF_DUMP(8);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);
-  tc::tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward through time (v3): ONE exchange per step.  H a multiple of 64 up to 896: H / 32 CTAs per (direction,
+// backward through time: ONE exchange per step.  H a multiple of 64 up to 896: H / 32 CTAs per (direction,
 //   batch group); the figures below are for H = 512 (16 CTAs, 4 blocks).  Wider layers (5 to 7 blocks: the U slice
 //   fills 448 of the 512 TMEM columns, which leaves room for four accumulators) run the product in two rounds of
 //   at most four blocks; the rows of a last half block (H = 832) beyond H are zero and are never sent.
@@ -704,9 +392,9 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 //       P_j[u][n] = sum_{k in own columns} U[u][k] * dz_t[n][k]            (4 blocks x 8 TS-mode tcgen05.mma)
 //   is its partial contribution to dh_rec of ALL 512 units.  Warp w of CTA j holds, for block b, the rows of the
 //   units owned by CTA 4b + w and sends them there (reduce-scatter through the LL ring); every CTA sums the 16
-//   partials that arrive for its own units.  The 4 x 4 kernel above needs two dependent exchanges per step
-//   (gather dz of a column block, then reduce partials along a row: ~2.0 k + ~1.1 k cycles of 4.5 k); this one
-//   needs one, with the same wire bytes per CTA as the forward all-gather (partials travel as bf16 pairs — the
+//   partials that arrive for its own units.  A row-partitioned kernel (round 1's first BPTT) needs two dependent
+//   exchanges per step (gather dz of a column block, then reduce partials along a row: ~2.0 k + ~1.1 k cycles of
+//   4.5 k); this one needs one, with the same wire bytes per CTA as the forward all-gather (partials travel as bf16 pairs — the
 //   operands of the product are bf16 already, see DESIGN.md for the error budget).
 // ------------------------------------------------------------------------------------------------
 template <int H, int NB, bool VAR>
@@ -885,9 +573,9 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
     for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
     if (s > 0) {
       // ---- receive: NCTA partials (bf16 pairs of two samples) for each of my (unit, sample pair) --------------
-      if (p_t >= 0) side_stores(p_t, p_dz, p_du);   // first: gives the peers' LL words time to land in L2
       const uint32_t tag = (uint32_t)s;
       const uint2* src = xb + ((size_t)((s - 1) & 1) * NCTA + cta) * SLOT + (size_t)(warp * PPT) * NCTA * 32 + lane;
+      if (p_t >= 0) side_stores(p_t, p_dz, p_du);   // first: gives the peers' LL words time to land in L2
       uint2 w[PPT * NCTA];
 #pragma unroll
       for (int q = 0; q < PPT * NCTA; ++q) w[q] = ld_volatile_v2(src + q * 32);
@@ -1051,9 +739,8 @@ bwd3_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xb
 static int max_groups(int H) { return 148 / (2 * (H / UPC)); }
 // samples per CTA group: 8 when the batch then still fits one cooperative wave (more SMs, half the exchange per CTA),
 // else 16; a batch of more than max_groups() groups runs as several launches over consecutive groups (grp0)
-static int group_size(int N, int H) {
-  const char* e = getenv("ASR_LSTM_GROUP");
-  if (e && atoi(e) == 16) return (N % 16 == 0) ? 16 : 0;
+static int group_size(int N, int H, int opts) {
+  if (opts & ASR_LSTM_GROUP16) return (N % 16 == 0) ? 16 : 0;
   if (N % 8 == 0 && N / 8 <= max_groups(H)) return 8;
   if (N % 16 == 0) return 16;
   return (N % 8 == 0) ? 8 : 0;
@@ -1064,12 +751,10 @@ static int group_size(int N, int H) {
 static bool width_ok(int H) {
   return H == 128 || H == 256 || H == 384 || H == 512 || H == 640 || H == 768 || H == 832 || H == 896;
 }
-static bool shape_ok(int T, int N, int H) { return T >= 1 && width_ok(H) && N >= 8 && group_size(N, H) != 0; }
-bool shape_supported(int T, int N, int H, bool) { return shape_ok(T, N, H); }
-bool supports_fwd(const asr_lstm_fwd_args* a) { return a->U16 && (a->h16 || a->hm16) && shape_ok(a->T, a->N, a->H); }
-bool supports_bwd(const asr_lstm_bwd_args* a) { return a->U16 && a->dz16 && shape_ok(a->T, a->N, a->H); }
-static size_t x1_bytes_per_dg(int NB) { return (size_t)4 * 2 * NB * 256 * sizeof(uint2); }           // hop 1 per (dir, grp)
-static size_t x2_bytes_per_dg(int NB) { return (size_t)4 * 4 * 4 * 2 * NB * 32 * sizeof(uint2); }    // hop 2 per (dir, grp)
+static bool shape_ok(int T, int N, int H, int opts) { return T >= 1 && width_ok(H) && N >= 8 && group_size(N, H, opts) != 0; }
+bool shape_supported(int T, int N, int H, int opts) { return shape_ok(T, N, H, opts); }
+bool supports_fwd(const asr_lstm_fwd_args* a) { return a->zx && a->U16 && (a->h16 || a->hm16) && (!a->training || (a->gates && a->cell)) && shape_ok(a->T, a->N, a->H, a->opts); }
+bool supports_bwd(const asr_lstm_bwd_args* a) { return a->gates && a->cell && a->U16 && a->dz16 && shape_ok(a->T, a->N, a->H, a->opts); }
 static size_t fwd_ring_bytes(int H, int NB, int G) { return (size_t)2 * G * 2 * NB * (H / 2) * sizeof(uint2); }
 // [(dir, grp)][parity][dst][pair][src][unit]
 static size_t bwd3_ring_bytes(int H, int NB, int G) {
@@ -1077,7 +762,7 @@ static size_t bwd3_ring_bytes(int H, int NB, int G) {
   return (size_t)2 * G * 2 * nc * (NB / 2) * nc * 32 * sizeof(uint2);
 }
 size_t scratch_bytes(int) {                              // the largest ring any launch clears
-  size_t m = (size_t)2 * 8 * (x1_bytes_per_dg(16) + x2_bytes_per_dg(16));
+  size_t m = 0;
   for (int H = 128; H <= 896; H += 64) {
     if (!width_ok(H)) continue;
     for (int NB = 8; NB <= 16; NB += 8) {
@@ -1089,29 +774,25 @@ size_t scratch_bytes(int) {                              // the largest ring any
   return HEADER_BYTES + m;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 // The recurrence CTAs own their SM: they hold all 512 TMEM columns, and any co-resident CTA would steal issue
 // slots from a latency-bound chain.  Requesting (almost) the whole shared memory keeps every other kernel's CTAs
 // (e.g. the gradient GEMMs of the previous layer running on a low-priority side stream) on the SMs this grid
-// does not use.  ASR_LSTM_EXCLUSIVE=0 turns it off.
-static size_t exclusive_smem(size_t need) {
+// does not use.  ASR_LSTM_SHARED_SM in the argument record's opts turns it off.
+static size_t exclusive_smem(size_t need, int opts) {
   const size_t want = 200 * 1024;
-  return (env_int("ASR_LSTM_EXCLUSIVE", 1) && need < want) ? want : need;
+  return (!(opts & ASR_LSTM_SHARED_SM) && need < want) ? want : need;
 }
 
 template <int H, int NB, bool VAR>
 static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   constexpr int KC = H / 64;
-  const size_t smem = exclusive_smem(1024 + (size_t)KC * NM * 128 + 4 * NB * 32 * 4 + 64);
+  const size_t smem = exclusive_smem(1024 + (size_t)KC * NM * 128 + 4 * NB * 32 * 4 + 64, a->opts);
   const int Gall = a->N / NB, gm = max_groups(H);
   ASR_CUDA(cudaFuncSetAttribute(fwd_kernel<H, NB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   asr_lstm_fwd_args args = *a;
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
-  int delay1 = env_int("ASR_LSTM_FWD_DELAY_NS", 0);
+  int delay1 = 0;
   for (int grp0 = 0; grp0 < Gall; grp0 += gm) {          // one launch per max_groups() batch groups (C2: a single launch)
     const int G = Gall - grp0 < gm ? Gall - grp0 : gm;
     ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + fwd_ring_bytes(H, NB, G), st));
@@ -1122,30 +803,11 @@ static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   return ASR_OK;
 }
 
-template <int NB>
-static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
-  const int G = a->N / NB;
-  const size_t smem = exclusive_smem(1024 + (size_t)8 * NM * 128 + 64);
-  const size_t x1 = (size_t)2 * G * x1_bytes_per_dg(NB), x2 = (size_t)2 * G * x2_bytes_per_dg(NB);
-  ASR_CUDA(cudaFuncSetAttribute(bwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + x1 + x2, st));
-  ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));
-  asr_lstm_bwd_args args = *a;
-  int* flags = a->flags;
-  uint2* xbuf1 = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
-  uint2* xbuf2 = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES + x1);
-  int delay1 = env_int("ASR_LSTM_BWD_DELAY1_NS", 0), delay2 = env_int("ASR_LSTM_BWD_DELAY2_NS", 0);
-  void* kargs[] = {&args, &flags, &xbuf1, &xbuf2, &delay1, &delay2};
-  ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd_kernel<NB>, dim3(16, 2, G), dim3(THREADS), kargs, smem, st));
-  asr::count_launch();
-  return ASR_OK;
-}
-
 template <int H, int NB, bool VAR>
 static int32_t launch_bwd3(const asr_lstm_bwd_args* a, cudaStream_t st) {
   constexpr int NCTA = H / UPC;
   const int Gall = a->N / NB, gm = max_groups(H);
-  const size_t smem = exclusive_smem(1024 + (size_t)2 * NM * 128 + 64);
+  const size_t smem = exclusive_smem(1024 + (size_t)2 * NM * 128 + 64, a->opts);
   ASR_CUDA(cudaFuncSetAttribute(bwd3_kernel<H, NB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ASR_CUDA(cudaMemsetAsync(a->dbias, 0, (size_t)2 * 4 * a->H * sizeof(float), st));      // accumulated over all groups
   if (VAR && a->mi) ASR_CUDA(cudaMemsetAsync(a->dmi, 0, (size_t)3 * 2 * 4 * a->H * sizeof(float), st));
@@ -1162,14 +824,10 @@ static int32_t launch_bwd3(const asr_lstm_bwd_args* a, cudaStream_t st) {
   return ASR_OK;
 }
 
-// ASR_LSTM_BWD=v2 pins the two-exchange 4 x 4 kernel (fp32 partials; the cross-check of the single-exchange one)
 int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
-  const char* e = getenv("ASR_LSTM_BWD");
-  const bool g8 = group_size(a->N, a->H) == 8;
+  const bool g8 = group_size(a->N, a->H, a->opts) == 8;
   const bool var = a->mi != nullptr || a->zoneout > 0.0f;
   if (var) ASR_CHECK_ARG(!a->mi || (a->zx && a->uh && a->dmi && a->duhT16), "lstmtc2 backward: MI needs zx, uh, dmi and duhT16");
-  if (!var && a->H == 512 && e && strcmp(e, "v2") == 0 && a->N / (g8 ? 8 : 16) <= max_groups(512))
-    return g8 ? launch_bwd<8>(a, st) : launch_bwd<16>(a, st);
 #define ASR_BWD3_CASE(HH)                                                                             \
   case HH:                                                                                            \
     if (var) return g8 ? launch_bwd3<HH, 8, true>(a, st) : launch_bwd3<HH, 16, true>(a, st);          \
@@ -1190,7 +848,7 @@ int32_t backward(const asr_lstm_bwd_args* a, cudaStream_t st) {
 }
 
 int32_t forward(const asr_lstm_fwd_args* a, cudaStream_t st) {
-  const bool g8 = group_size(a->N, a->H) == 8;
+  const bool g8 = group_size(a->N, a->H, a->opts) == 8;
   const bool var = a->mi != nullptr || a->zoneout > 0.0f;
   if (var) ASR_CHECK_ARG(!a->mi || !a->training || a->uh, "lstmtc2 forward: training with MI needs the uh buffer");
 #define ASR_FWD_CASE(HH)                                                                              \

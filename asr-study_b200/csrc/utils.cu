@@ -282,3 +282,39 @@ extern "C" int32_t asr_dropout_mask(float* out, int64_t n, float p, uint64_t see
   ASR_LAUNCH_CHECK();
   return ASR_OK;
 }
+
+// same generator, caller-chosen keep value: zoneout keep masks are 0 / 1 (core/layers_utils.py:34-42 multiplies the
+// K.dropout result by (1 - level) again), the element-wise input Dropout of core/models.py:257-258 is 0 / 1/(1-p)
+extern "C" int32_t asr_bernoulli_mask(float* out, int64_t n, float p, float keep_value, uint64_t seed, uint64_t offset,
+                                      void* stream) {
+  ASR_CHECK_ARG(out && n > 0 && p >= 0.0f && p < 1.0f, "asr_bernoulli_mask: bad argument");
+  dropout_mask_kernel<<<grid_1d(n), 256, 0, (cudaStream_t)stream>>>(out, n, p, keep_value, seed, offset);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+// GaussianNoise(std) of core/models.py:67,251 (train phase): x[r, c] += std * n, n ~ N(0, 1) by Box-Muller on two
+// 24-bit uniforms of the counter-based generator above
+__global__ void gaussian_noise_kernel(float* __restrict__ x, int64_t rows, int cols, int64_t ld, float stdv, uint64_t seed,
+                                      uint64_t offset) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(offset + (uint64_t)i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u1 = ((float)(uint32_t)(z >> 40) + 1.0f) * (1.0f / 16777216.0f);      // (0, 1]
+    const float u2 = (float)(uint32_t)((z >> 16) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+    const float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    const int64_t r = i / cols;
+    x[r * ld + (i - r * cols)] += stdv * g;
+  }
+}
+
+extern "C" int32_t asr_add_gaussian_noise(float* x, int64_t rows, int32_t cols, int64_t ld, float stdv, uint64_t seed,
+                                          uint64_t offset, void* stream) {
+  ASR_CHECK_ARG(x && rows > 0 && cols > 0 && ld >= cols && stdv >= 0.0f, "asr_add_gaussian_noise: bad argument");
+  gaussian_noise_kernel<<<grid_1d(rows * cols), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, stdv, seed, offset);
+  ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}

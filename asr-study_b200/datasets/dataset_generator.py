@@ -16,30 +16,47 @@ import scipy.sparse
 
 
 class DatasetIterator(object):
+    """Data parallel: under torchrun every rank builds the SAME iterator (same seed => same permutation) and
+    takes every world_size-th utterance of it, i.e. its share of each global batch of batch_size * world_size
+    utterances; ``len`` is then the rank's share of the corpus, so train.py's samples_per_epoch = flow.len walks the
+    corpus once per epoch across all ranks (the tail is wrapped so that every rank yields the same number of
+    utterances and no rank ever sees an empty batch).  rank / world_size default to RANK / WORLD_SIZE."""
+
     def __init__(self, inputs, labels=None, batch_size=32, shuffle=False, seed=None, input_parser=None,
-                 label_parser=None, mode="train"):
+                 label_parser=None, mode="train", rank=None, world_size=None):
         if labels is not None and len(inputs) != len(labels):
             raise ValueError("inputs and labels should have the same length. Found: len(inputs) = %s, "
                              "len(labels) = %s" % (len(inputs), len(labels)))
+        import os
         self.inputs, self.labels = list(inputs), (list(labels) if labels is not None else None)
         self.batch_size, self.shuffle = batch_size, shuffle
         self.input_parser, self.label_parser, self.mode = input_parser, label_parser, mode
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1")) if world_size is None else int(world_size)
+        self.rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
+        if not 0 <= self.rank < self.world_size:
+            raise ValueError("rank %d outside world of %d" % (self.rank, self.world_size))
         self.lock = threading.Lock()
+        if seed is None and self.world_size > 1:
+            seed = 1234                                       # the ranks must draw the same permutation
         self._rng = np.random.RandomState(None if seed is None else int(seed))
         self._order, self._pos = None, 0
 
     @property
     def len(self):
-        return len(self.inputs)
+        n, w = len(self.inputs), self.world_size
+        return (n + w - 1) // w
 
     def __iter__(self):
         return self
 
     def _next_indices(self):
-        n = len(self.inputs)
-        if self._order is None or self._pos >= n:
-            self._order = self._rng.permutation(n) if self.shuffle else np.arange(n)
-            self._pos = 0
+        n, w = len(self.inputs), self.world_size
+        if self._order is None or self._pos >= len(self._order):
+            order = self._rng.permutation(n) if self.shuffle else np.arange(n)
+            if w > 1:
+                pad = (-n) % w
+                order = np.concatenate([order, order[:pad]])[self.rank::w]
+            self._order, self._pos = order, 0
         idx = self._order[self._pos:self._pos + self.batch_size]
         self._pos += self.batch_size
         return np.sort(idx)                                   # dataset_generator.py:200
@@ -97,9 +114,10 @@ class DatasetGenerator(object):
         self.input_parser, self.label_parser = input_parser, label_parser
         self.batch_size, self.shuffle, self.seed, self.mode = batch_size, shuffle, seed, mode
 
-    def flow(self, inputs, labels):
+    def flow(self, inputs, labels, rank=None, world_size=None):
         return DatasetIterator(inputs, labels, batch_size=self.batch_size, shuffle=self.shuffle, seed=self.seed,
-                               input_parser=self.input_parser, label_parser=self.label_parser, mode=self.mode)
+                               input_parser=self.input_parser, label_parser=self.label_parser, mode=self.mode,
+                               rank=rank, world_size=world_size)
 
     def flow_from_dl(self, dl, datasets=None):
         def pick(name):

@@ -12,14 +12,14 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-import os
 import dataclasses
 from dataclasses import dataclass
 
 import numpy as np
 import torch
 
-from ._lib import LstmBwdArgs, LstmFwdArgs, LstmVariant, LstmVariantGrads, cur_stream, lib, ptr
+from ._lib import (GEMM_BACKGROUND, GEMM_TILE128, LSTM_SHARED_SM, LstmBwdArgs, LstmFwdArgs, LstmVariant, LstmVariantGrads,
+                   cur_stream, lib, ptr)
 
 F16, BF16 = 0, 1
 F16_LO = 16          # fp16(v - fp16(v)): the low half of a split-precision operand (csrc/utils.cu)
@@ -202,12 +202,17 @@ class ParamBucket:
 class AcousticEngine:
     """Forward / backward / optimiser step for one rank."""
 
-    def __init__(self, spec: ModelSpec, device="cuda:0", seed=4321, init_params: dict | None = None):
+    def __init__(self, spec: ModelSpec, device="cuda:0", seed=4321, init_params: dict | None = None, pad_width=True,
+                 overlap=True, fp16_storage=True):
+        """pad_width: widths without a tensor-core instantiation run zero-padded at the next one (else on the general
+        cell); overlap: gradient GEMMs / weight preparation on a side stream beside the recurrences; fp16_storage: zx and
+        the saved gates / cell state are fp16 in HBM and move through TMA (csrc/lstm_tc4.cu) where that engine takes the
+        shape."""
         # widths without a tensor-core instantiation (e.g. the BiLSTM-800 of BASELINE config 4) run zero-padded at the
         # next instantiated width; self.spec is the device spec, self.user_spec the model's own
         self.user_spec = spec
         Hl = spec.num_hiddens
-        if not spec.general and not spec.layer_hiddens and tc_width(Hl) != Hl and os.environ.get("ASR_B200_PAD_WIDTH", "1") != "0":
+        if not spec.general and not spec.layer_hiddens and tc_width(Hl) != Hl and pad_width:
             spec = dataclasses.replace(spec, num_hiddens=tc_width(Hl))
         self.spec = spec
         self.logical_h = Hl if spec.num_hiddens != Hl else None
@@ -230,10 +235,41 @@ class AcousticEngine:
         # main stream; the GEMM CTAs fill the 20 idle SMs and never delay the critical path.
         self._main = torch.cuda.Stream(device=self.device, priority=-1)
         self._side = torch.cuda.Stream(device=self.device, priority=0)
-        self.overlap = os.environ.get("ASR_B200_OVERLAP", "1") != "0"
-        self._mask_rng = torch.Generator(device=self.device)
-        self._mask_rng.manual_seed(seed + 17)
+        self.overlap = bool(overlap)
+        self.fp16_storage = bool(fp16_storage)
+        self.shared_sm = False          # let other kernels' CTAs share SMs with the recurrences / pin the small GEMM tiling
+        self._seed = int(seed)
         self._mask_seed, self._mask_offset = (seed + 17) * 0x9E3779B1 & 0xFFFFFFFFFFFFFFFF, 0
+        self._l2 = torch.zeros(1, dtype=torch.float64, device=self.device)
+
+    def set_rank(self, rank: int):
+        """data parallel: same parameters on every rank (same init seed), different dropout / zoneout / noise streams."""
+        self._mask_seed = ((self._seed + 17) * 0x9E3779B1 + 0x632BE59BD9B4E019 * int(rank)) & 0xFFFFFFFFFFFFFFFF
+
+    @property
+    def lstm_opts(self) -> int:
+        return LSTM_SHARED_SM if self.shared_sm else 0
+
+    @property
+    def gemm_flags(self) -> int:
+        return GEMM_TILE128 if self.shared_sm else 0
+
+    def add_gaussian_noise(self, xt, n_real, std, offset):
+        """GaussianNoise(std) on the first n_real utterances of time-major features [T, Np, F] (train phase,
+        core/models.py:67,251); returns the advanced generator offset."""
+        T, Np, F = xt.shape
+        lib.asr_add_gaussian_noise(ptr(xt), T, n_real * F, Np * F, float(std), self._mask_seed ^ 0xA5A5A5A5, int(offset), cur_stream())
+        return int(offset) + T * n_real * F
+
+    def l2_penalty(self):
+        """sum of the l2(weight_decay) regularisers (core/models.py:263-264, 279) as a device scalar: the masked squared
+        norm kernel with a zero gradient scale gives (2 c p)^2 summed over the decayed tensors; c = sqrt(wd) / 2."""
+        wd = float(self.spec.weight_decay)
+        P = self.params
+        if not wd:
+            return torch.zeros((), dtype=torch.float32, device=self.device)
+        lib.asr_grad_sqnorm(ptr(P.flat), ptr(P.flat), ptr(P.decay), P.numel, 0.0, 0.5 * math.sqrt(wd), ptr(self._l2), cur_stream())
+        return self._l2[0].float()
 
     # ------------------------------------------------------------ dropout masks
     def sample_masks(self, N):
@@ -322,8 +358,9 @@ class AcousticEngine:
         R = T * N
         w = {}
         D0 = _pad8(sp.num_features)
+        sdt = torch.float16 if self._fp16 else torch.float32       # zx / gates / cell storage (csrc/lstm_tc4.cu)
         w["x16"] = self._buf("x16", (R, D0), torch.float16, zero=True)
-        w["zx"] = self._buf("zx", (R, 8 * H), torch.float32)
+        w["zx"] = self._buf("zx", (R, 8 * H), sdt)
         for l in range(L):
             w[f"h16.{l}"] = self._buf(f"h16.{l}", (R, 2 * H), torch.float16)
         w["logits"] = self._buf("logits", (T, N, Cc), torch.float32)
@@ -331,8 +368,8 @@ class AcousticEngine:
             w["xT16"] = self._buf("xT16", (sp.num_features, R), torch.bfloat16)
             for l in range(L):
                 w[f"hT16.{l}"] = self._buf(f"hT16.{l}", (2 * H, R), torch.bfloat16)
-                w[f"gates.{l}"] = self._buf(f"gates.{l}", (R, 8 * H), torch.float32)
-                w[f"cell.{l}"] = self._buf(f"cell.{l}", (R, 2 * H), torch.float32)
+                w[f"gates.{l}"] = self._buf(f"gates.{l}", (R, 8 * H), sdt)
+                w[f"cell.{l}"] = self._buf(f"cell.{l}", (R, 2 * H), sdt)
             w["dlogits"] = self._buf("dlogits", (T, N, Cc), torch.float32)
             w["dl16"] = self._buf("dl16", (R, _pad8(Cc)), torch.bfloat16, zero=True)
             w["dlT16"] = self._buf("dlT16", (Cc, R), torch.bfloat16)
@@ -379,8 +416,8 @@ class AcousticEngine:
             lib.asr_cast_rows(ptr(P.p("dense.W")), Cc, ptr(wdb), dp, H2, Cc, BF16, st)
 
     def _gemm(self, din, dout, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, alpha=1.0, acc=0):
-        lib.asr_gemm_tn(din, dout, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(Cm), ldc, ptr(bias), float(alpha), acc,
-                        cur_stream())
+        lib.asr_gemm_tn_ex(din, dout, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(Cm), ldc, ptr(bias), float(alpha), acc,
+                           self.gemm_flags, cur_stream())
 
     # ---------------------------------------------------------------- forward
     def forward(self, feats_tm: torch.Tensor, training=False, masks=None, zmasks=None, input_mask=None) -> torch.Tensor:
@@ -404,7 +441,11 @@ class AcousticEngine:
             fp[:, N:].zero_()
             if masks is not None:
                 masks = {l: {k: torch.cat([v, torch.ones(Np - N, v.shape[1], dtype=v.dtype, device=v.device)])
-                             for k, v in m.items()} for l, m in masks.items()}
+                             for k, v in m.items() if k in ("Wf", "Wb", "Uf", "Ub")} for l, m in masks.items()}
+            if input_mask is not None:                  # [T * N, D] time-major rows -> [T * Np, D]
+                im = torch.ones(T, Np, input_mask.shape[1], dtype=input_mask.dtype, device=input_mask.device)
+                im[:, :N].copy_(input_mask.view(T, N, -1))
+                input_mask = im.view(T * Np, -1)
             self.last_logits = self._forward(fp, training, masks, zmasks, input_mask)[:, :N].contiguous()
         else:
             self.last_logits = self._forward(feats_tm, training, masks, zmasks, input_mask)
@@ -432,23 +473,32 @@ class AcousticEngine:
         """N itself when the tensor-core engine takes it (or cannot take the model at all); else the next group boundary."""
         sp = self.spec
         H = sp.hs[0]
-        if sp.general or lib.asr_lstm_fuses_masks(T, N, H):
-            return N
-        for Np in (_pad8(N), (N + 15) // 16 * 16):
-            if Np != N and lib.asr_lstm_fuses_masks(T, Np, H):
-                return Np
-        return N
+        if not sp.general:
+            if lib.asr_lstm_fuses_masks(T, N, H, self.lstm_opts):
+                return N
+            for Np in (_pad8(N), (N + 15) // 16 * 16):
+                if Np != N and lib.asr_lstm_fuses_masks(T, Np, H, self.lstm_opts):
+                    return Np
+        # fp32 / general-cell paths: the dU GEMM reads h and dz shifted by one time step = N columns of the transposed
+        # 16-bit copies, and a GEMM operand starts on a 16-byte boundary: N must be a multiple of 8 there as well
+        return _pad8(N)
 
     def _forward(self, feats_tm, training, masks, zmasks, input_mask):
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
         # the persistent engines cover the reference's shapes; anything else (e.g. H = 800) runs on the general cell
-        self._use_general = (sp.general or not lib.asr_lstm_persistent_supported(T, N, sp.hs[0], int(training))
-                             or (sp.elementwise and not lib.asr_lstm_fuses_variants(T, N, sp.hs[0])))
+        # (the persistent engines hand 2H-wide fp16 rows straight to the next GEMM: 2H must be a multiple of 8 — 16-byte
+        # rows — e.g. graves2006(num_hiddens=50) is not; the general path pads its operand copies instead)
+        self._use_general = (sp.general or not lib.asr_lstm_persistent_supported(T, N, sp.hs[0], int(training), self.lstm_opts)
+                             or (sp.elementwise and not lib.asr_lstm_fuses_variants(T, N, sp.hs[0], self.lstm_opts))
+                             or (2 * sp.hs[0]) % 8 != 0)
         if self._use_general:
             return self._forward_general(feats_tm, training, masks, zmasks, input_mask)
         H, L, Cc = sp.hs[0], len(sp.hs), sp.num_classes
         R = T * N
+        # 16-bit storage of zx / gates / cell + TMA staging: the default tensor-core recurrence where it takes the shape
+        self._fp16 = bool(self.fp16_storage and not sp.elementwise and lib.asr_lstm_fp16_storage(T, N, H, self.lstm_opts))
+        zdt = OUT_F16 if self._fp16 else OUT_F32
         w = self._alloc(T, N, training)
         self._w, self._T, self._N = w, T, N
         if training and masks is None and sp.dropout > 0:
@@ -470,7 +520,7 @@ class AcousticEngine:
         src, src_dt, src_ld, Dl = feats_tm, 2, Fd, Fd              # layer input before masking
         # with dropout the recurrence of layer l-1 writes the masked operand copies of layer l itself (fused side
         # stores) when the selected engine supports it; otherwise asr_mask_cast makes them
-        fuse = masks is not None and bool(lib.asr_lstm_fuses_masks(T, N, H))
+        fuse = masks is not None and bool(lib.asr_lstm_fuses_masks(T, N, H, self.lstm_opts))
         self._fused = fuse
         prev = None                                                 # fused outputs of the previous layer
         for l in range(L):
@@ -480,7 +530,7 @@ class AcousticEngine:
                 zx = w[f"zx.{l}"] = self._buf(f"zx.{l}", (R, 8 * H), torch.float32)
                 w[f"uh.{l}"] = self._buf(f"uh.{l}", (R, 8 * H), torch.float32)
             if masks is None:
-                self._gemm(F16, OUT_F32, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, zx, 8 * H)
+                self._gemm(F16, zdt, R, 8 * H, D, x16, D, self._ws[f"WcatT16.{l}"], D, zx, 8 * H)
             else:
                 mk = masks[l]
                 mask_u = self._packed(mk, "U")
@@ -497,7 +547,7 @@ class AcousticEngine:
                         if training:
                             xmT = self._buf(f"xmT16.{l}.{i}", (Dl, R), torch.bfloat16)
                             lib.asr_mask_cast(ptr(src), src_dt, src_ld, ptr(mw), N, ptr(xmT), BF16, R, R, Dl, 1, st)
-                    lib.asr_gemm_tn(F16, OUT_F32, R, 4 * H, D, ptr(xm), D, ptr(self._views[f"WcatT16.{l}"][i * 4 * H:]), D,
+                    lib.asr_gemm_tn(F16, zdt, R, 4 * H, D, ptr(xm), D, ptr(self._views[f"WcatT16.{l}"][i * 4 * H:]), D,
                                     ptr(zx[:, i * 4 * H:]), 8 * H, None, 1.0, 0, st)
             top = l == L - 1
             fz = dict(mask_next=None, hm16=None, hmT16=None, hT16u=None)
@@ -519,14 +569,17 @@ class AcousticEngine:
                 if self._zmasks is not None:
                     zp = self._zpacked[l] = torch.stack([self._zmasks[l]["h"], self._zmasks[l]["c"]]).contiguous()
                     fz["zmask"] = zp.data_ptr()
-            a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(zx).value,
+            gbuf = ptr(w[f"gates.{l}"]).value if training else None
+            cbuf = ptr(w[f"cell.{l}"]).value if training else None
+            st16 = dict(zx=None, zx16=ptr(zx).value, gates=None, cell=None, gates16=gbuf, cell16=cbuf) if self._fp16 else \
+                dict(zx=ptr(zx).value, gates=gbuf, cell=cbuf)
+            a = LstmFwdArgs(T=T, N=N, H=H, training=int(training),
                             bias=ptr(P.p(f"l{l}.bf")).value, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"UT16.{l}"]).value,
                             h16=ptr(w[f"h16.{l}"]).value if (top or not fuse) else None,
                             hT16=ptr(w[f"hT16.{l}"]).value if training else None, h32=None,
-                            gates=ptr(w[f"gates.{l}"]).value if training else None,
-                            cell=ptr(w[f"cell.{l}"]).value if training else None,
-                            flags=ptr(self._flags).value, mask_u=ptr(mask_u).value if mask_u is not None else None, **fz)
+                            flags=ptr(self._flags).value, mask_u=ptr(mask_u).value if mask_u is not None else None,
+                            opts=self.lstm_opts, **st16, **fz)
             lib.asr_lstm_forward(C.byref(a), st)
             prev = cur
             x16, D = w[f"h16.{l}"], 2 * H
@@ -540,8 +593,17 @@ class AcousticEngine:
         """One keep mask per (layer, direction, time step, unit), shared by the batch: K.dropout(h_diff, level,
         noise_shape=(output_dim,)) inside the step (core/layers_utils.py:34-42).  {layer: {h, c: f32 [2, T, H]}}."""
         sp = self.spec
-        return {l: {k: (torch.rand(2, T, H, device=self.device, generator=self._mask_rng) >= sp.zoneout).float()
-                    for k in ("h", "c")} for l, H in enumerate(sp.hs)}
+        total = sum(2 * 2 * T * H for H in sp.hs)
+        flat = self._buf("zoneout_masks", (total,), torch.float32)
+        lib.asr_bernoulli_mask(ptr(flat), total, float(sp.zoneout), 1.0, self._mask_seed, self._mask_offset, cur_stream())
+        self._mask_offset += total
+        out, o = {}, 0
+        for l, H in enumerate(sp.hs):
+            out[l] = {}
+            for k in ("h", "c"):
+                out[l][k] = flat[o:o + 2 * T * H].view(2, T, H)
+                o += 2 * T * H
+        return out
 
     def _variant(self, l, zm):
         sp, P = self.spec, self.params
@@ -610,7 +672,10 @@ class AcousticEngine:
             zmasks = self.sample_zoneout_masks(T)
         if training and input_mask is None and sp.input_dropout and sp.dropout > 0:
             Din = PW or Fd
-            input_mask = (torch.rand(R, Din, device=self.device, generator=self._mask_rng) >= sp.dropout).float() / (1.0 - sp.dropout)
+            input_mask = self._buf("input_mask", (R, Din), torch.float32)
+            lib.asr_bernoulli_mask(ptr(input_mask), R * Din, float(sp.dropout), 1.0 / (1.0 - float(sp.dropout)), self._mask_seed,
+                                   self._mask_offset, cur_stream())
+            self._mask_offset += R * Din
         if not training:
             masks = zmasks = input_mask = None
         self._masks, self._zmasks, self._input_mask = masks, zmasks, input_mask
@@ -895,8 +960,9 @@ class AcousticEngine:
                               dmi=P.g(f"l{l}.mi_alpha").data_ptr(), duhT16=ptr(duhT).value)
                 if self._zmasks is not None:
                     vz["zmask"] = self._zpacked[l].data_ptr()
-            a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(w[f"gates.{l}"]).value,
-                            cell=ptr(w[f"cell.{l}"]).value, U=ptr(P.p(f"l{l}.Uf")).value,
+            st16 = dict(gates16=ptr(w[f"gates.{l}"]).value, cell16=ptr(w[f"cell.{l}"]).value) if self._fp16 else \
+                dict(gates=ptr(w[f"gates.{l}"]).value, cell=ptr(w[f"cell.{l}"]).value)
+            a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, opts=self.lstm_opts, **st16, U=ptr(P.p(f"l{l}.Uf")).value,
                             U16=ptr(self._ws[f"Ub16.{l}"]).value,
                             dz16=ptr(w[f"dz16.{l}"]).value, dzT16=ptr(w[f"dzT16.{l}"]).value, dz32=None,
                             dbias=ptr(P.g(f"l{l}.bf")).value, flags=ptr(self._flags).value,
@@ -918,7 +984,7 @@ class AcousticEngine:
                 for i, d in enumerate("fb"):
                     # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
                     xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
-                    bg = 1 if (side is not main and l > 0) else 0      # ASR_GEMM_BACKGROUND: runs beside the next BPTT
+                    bg = GEMM_BACKGROUND if (side is not main and l > 0) else 0      # runs beside the next BPTT
                     lib.asr_gemm_tn_ex(BF16, OUT_F32, D, 4 * H, R, ptr(xTd), R, ptr(dzT[i * 4 * H:]), R,
                                        ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, bg, sst)
                     # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence

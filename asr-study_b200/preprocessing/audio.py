@@ -15,6 +15,7 @@ two-stage resampling at the filter-ripple level; ndarray / list inputs (the hot 
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -55,6 +56,7 @@ class Feature(object):
         self.num_context = num_context
         self._plan = None
         self._ws = {}
+        self._ws_lock = threading.Lock()
 
     # -- plan -----------------------------------------------------------------
     def _config(self) -> MfccConfig:
@@ -106,11 +108,15 @@ class Feature(object):
         if out is None:
             out = torch.empty(shape, dtype=torch.float32, device=pcm.device)
         out_len = torch.empty(n, dtype=torch.int32, device=pcm.device)
-        key = (n, int(t_max), pcm.device)
-        ws = self._ws.get(key)
-        if ws is None:
-            ws = torch.zeros(lib.asr_mfcc_workspace_bytes_ex(plan, n, int(t_max)) // 8 + 1, dtype=torch.float64, device=pcm.device)
-            self._ws[key] = ws
+        # one grow-only zeroed workspace per (device, stream): the kernel leaves the bytes it used zeroed, so a larger
+        # buffer serves every smaller batch (real corpora have a different t_max for almost every batch)
+        need = lib.asr_mfcc_workspace_bytes_ex(plan, n, int(t_max)) // 8 + 1
+        key = (pcm.device, torch.cuda.current_stream(pcm.device).cuda_stream)
+        with self._ws_lock:
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < need:
+                ws = torch.zeros(need, dtype=torch.float64, device=pcm.device)
+                self._ws[key] = ws
         lib.asr_mfcc_forward(plan, ptr(pcm), ptr(offsets), n, t_max, ptr(out), ptr(out_len), int(time_major),
                              ptr(ws), cur_stream())
         return out, out_len

@@ -390,9 +390,7 @@ def run_infer(args):
     # SMs, so the forward kernels must be able to share an SM with them: the recurrences give up their exclusive
     # shared-memory reservation and the GEMMs use the non-persistent 96 KB tiling (the persistent one needs 192 KB).
     overlap = bool(args.overlap_decode)
-    if overlap:
-        os.environ["ASR_LSTM_EXCLUSIVE"] = "0"
-        os.environ["ASR_B200_GEMM"] = "tc1"
+    eng.shared_sm = overlap          # ASR_LSTM_SHARED_SM / ASR_GEMM_TILE128 flags of the C ABI, per launch
     bigs = [torch.empty(T_FRAMES, G * nb_fwd, C, dtype=torch.float32, device=dev) for _ in range(2)]
     big_lens = [torch.empty(G * nb_fwd, dtype=torch.int32, device=dev) for _ in range(2)]
     outs_h = [torch.empty(G * nb_fwd, T_FRAMES, dtype=torch.int32).pin_memory() for _ in range(2)]

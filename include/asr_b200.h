@@ -14,7 +14,9 @@
  *     in _host; `stream` is a cudaStream_t passed as void*.
  *   - no hidden allocation on the hot path: scratch is passed in; sizes come
  *     from the *_workspace_bytes queries.  Plans own small constant tables.
- *   - re-entrant; host threads may call concurrently on different streams.
+ *   - re-entrant; host threads may call concurrently on different streams.  No
+ *     process-global switches: engine / scheduling choices are explicit flag
+ *     arguments (ASR_GEMM_*, ASR_LSTM_*), never environment variables.
  *   - internal activation layout is TIME-MAJOR [T, N, *] (what TF's CTC ops
  *     consume after the reference's own transpose, core/ctc_utils.py:39,69).
  */
@@ -65,7 +67,7 @@ typedef struct {
   int32_t mean_norm, var_norm; /* per-utterance CMVN       audio.py:70-75 */
   float eps;            /* 1e-8                                        */
   int32_t stride;       /* feats[::stride]                 audio.py:82  */
-  int32_t num_context;  /* must be 0 (ASR_ERR_UNSUPPORTED otherwise)   */
+  int32_t num_context;  /* +-context frames, audio.py:88-150 (0 = off)  */
 } asr_mfcc_config;
 
 typedef struct asr_mfcc_plan asr_mfcc_plan;
@@ -113,8 +115,11 @@ int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N,
                     float alpha, int32_t accumulate, void* stream);
 /* same, with scheduling hints.  ASR_GEMM_BACKGROUND: the GEMM runs on a side stream beside a persistent
  * recurrence (e.g. dW/dU of layer l during the BPTT of layer l-1) and only gets the SMs that kernel leaves
- * idle; the non-persistent tiling is used so its CTAs are scheduled one by one as SMs free up. */
+ * idle; the non-persistent tiling is used so its CTAs are scheduled one by one as SMs free up.
+ * ASR_GEMM_TILE128: pin the non-persistent 128x128 tiling (96 KB of shared memory per CTA, two CTAs per SM), e.g.
+ * when the GEMM shares SMs with a beam search.  Both engines are tcgen05; a shape neither takes is an error. */
 #define ASR_GEMM_BACKGROUND 1
+#define ASR_GEMM_TILE128 2
 int32_t asr_gemm_tn_ex(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N,
                        int32_t K, const void* A, int64_t lda, const void* B,
                        int64_t ldb, void* C, int64_t ldc, const float* bias,
@@ -128,7 +133,7 @@ int32_t asr_gemm_tn_ex(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N
  * reverse direction consumes t = T-1..0.
  * ------------------------------------------------------------------------- */
 typedef struct {
-  int32_t T, N, H;          /* H % 32 == 0, N <= 64                           */
+  int32_t T, N, H;          /* see asr_lstm_persistent_supported() for the shapes the engines take */
   int32_t training;         /* 1: save gates/c (and transposed copies)        */
   const float* zx;          /* f32 [T, N, 2, 4H]  x_t*W  (no bias)            */
   const float* bias;        /* f32 [2, 4H]                                    */
@@ -153,7 +158,19 @@ typedef struct {
   float* uh;                /* f32 [T, N, 2, 4H]  raw recurrent product, saved when training with mi         */
   float  zoneout;           /* level in [0,1): zoneout on h and c (0 = off)                                  */
   const float* zmask;       /* f32 [2 (h|c), 2, T, H]  train-phase keep masks, NULL = inference blend 1-level */
+  /* 16-bit storage + TMA staging (lstm_tc4.cu; asr_lstm_fp16_storage() == 1): when zx16 is set it replaces zx, and
+   * training saves gates16 / cell16 instead of gates / cell.  Halves the recurrences' HBM traffic; fp32 arithmetic. */
+  const void* zx16;         /* fp16 [T, N, 2, 4H]                                                            */
+  void*  gates16;           /* fp16 [T, N, 2, 4H]                                                            */
+  void*  cell16;            /* fp16 [T, N, 2, H]                                                             */
+  int32_t opts;             /* ASR_LSTM_* flags                                                              */
 } asr_lstm_fwd_args;
+
+/* opts bits of both argument records */
+#define ASR_LSTM_SHARED_SM 1   /* do not reserve the whole SM's shared memory: other kernels' CTAs (e.g. a beam search
+                                  on a second stream) may then share SMs with the recurrence                        */
+#define ASR_LSTM_PIN_FP32  2   /* run the exact fp32 CUDA-core engine (the parity reference; N <= 32, small H)       */
+#define ASR_LSTM_GROUP16   4   /* 16-sample CTA groups even when 8-sample groups fit one cooperative wave           */
 
 typedef struct {
   int32_t T, N, H;
@@ -179,14 +196,19 @@ typedef struct {
   void*  duhT16;            /* bf16 [2*4H, T*N]                                                              */
   float  zoneout;
   const float* zmask;
+  const void* gates16;      /* fp16 copies saved by the forward call with zx16 set (replace gates / cell)     */
+  const void* cell16;
+  int32_t opts;             /* ASR_LSTM_* flags                                                              */
 } asr_lstm_bwd_args;
 
 /* 1 when the engine asr_lstm_forward/backward would select for this shape implements the fused dropout
  * fields above (mask_next/hm16/hmT16/hT16u, dh2/mask_dh); 0 = the caller must mask with asr_mask_cast /
  * asr_mask_combine instead. */
-int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H);
+int32_t asr_lstm_fuses_masks(int32_t T, int32_t N, int32_t H, int32_t opts);
 /* 1 when that engine also implements the element-wise switches (mi / zoneout fields); 0 = use the general cell. */
-int32_t asr_lstm_fuses_variants(int32_t T, int32_t N, int32_t H);
+int32_t asr_lstm_fuses_variants(int32_t T, int32_t N, int32_t H, int32_t opts);
+/* 1 when the 16-bit-storage / TMA engine (zx16, gates16, cell16) takes this shape */
+int32_t asr_lstm_fp16_storage(int32_t T, int32_t N, int32_t H, int32_t opts);
 /* 1 when asr_lstm_forward/backward take this shape (a persistent engine exists for it); 0 = use the general-cell
  * entry points below (any N, H <= 1024).  The tensor-core engine is instantiated for H in {128, 256, 384, 512, 640,
  * 768, 832, 896} and any N that is a multiple of 8 (batches wider than one cooperative wave run as several
@@ -194,7 +216,7 @@ int32_t asr_lstm_fuses_variants(int32_t T, int32_t N, int32_t H);
  * be run zero-padded at the next instantiated width (W = U = b = 0 for the extra units keeps them at exactly 0 in
  * both passes; asr-study_b200/engine.py does this at parameter load / export), ragged batches padded with zero
  * utterances and zero dlogits rows. */
-int32_t asr_lstm_persistent_supported(int32_t T, int32_t N, int32_t H, int32_t training);
+int32_t asr_lstm_persistent_supported(int32_t T, int32_t N, int32_t H, int32_t training, int32_t opts);
 
 size_t  asr_lstm_flags_bytes(void);
 int32_t asr_lstm_forward(const asr_lstm_fwd_args* a, void* stream);
@@ -333,6 +355,14 @@ int32_t asr_add_mask(const float* a, const float* b, const float* mask, int64_t 
 /* variational-dropout masks (core/layers.py:306-339 under Keras-1 K.dropout): out[i] = keep ? 1/(1-p) : 0,
  * keep ~ Bernoulli(1-p) from a counter-based generator keyed by (seed, offset + i): one launch per step. */
 int32_t asr_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* same generator with a caller-chosen keep value: out[i] = keep ? keep_value : 0.  Zoneout keep masks (0 / 1,
+ * core/layers_utils.py:34-42) and the element-wise input Dropout (0 / 1/(1-p), core/models.py:257-258). */
+int32_t asr_bernoulli_mask(float* out, int64_t n, float p, float keep_value, uint64_t seed, uint64_t offset,
+                           void* stream);
+/* GaussianNoise(std) (core/models.py:67,251; train phase only): x[r, c] += std * N(0,1) for r < rows, c < cols, row
+ * stride ld, from the same counter-based generator (Box-Muller). */
+int32_t asr_add_gaussian_noise(float* x, int64_t rows, int32_t cols, int64_t ld, float stdv, uint64_t seed,
+                               uint64_t offset, void* stream);
 /* out[c] = sum_r src[r, c]  (fp32; bias gradients) */
 int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_t cols,
                    float* out, void* stream);

@@ -2,8 +2,8 @@
 """predict.py — the reference's prediction driver surface (predict.py:17-93): load a checkpoint, decode a dataset
 subset or a single audio file, print ground truth / prediction pairs, optionally save them.
 
-  python predict.py --model run/model.pkl --dataset "dummy:split=[.5,.25]" --subset test
-  python predict.py --model run/model.pkl --file clip.wav --save out.json
+  python predict.py --model run/model.npz --dataset "dummy:split=[.5,.25]" --subset test
+  python predict.py --model run/model.npz --file clip.wav --save out.json
 
 Differences forced by this image: checkpoints are the pickle ``CTCModel.save`` writes (no h5py / Keras), the
 ``--no_decoder`` posteriors go to ``.npz`` instead of HDF5, ``--file`` takes RIFF/WAV (scipy, see

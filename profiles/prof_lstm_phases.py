@@ -17,7 +17,7 @@ flags = torch.zeros(lib.asr_lstm_flags_bytes() // 4, dtype=torch.int32, device=d
 a = LstmFwdArgs(T=T, N=N, H=H, training=1, zx=ptr(zx).value, bias=ptr(bias).value, U=ptr(U).value, U16=ptr(UT16).value,
                 h16=ptr(h16).value, hT16=ptr(hT16).value, h32=None, gates=ptr(gates).value, cell=ptr(cell).value, flags=ptr(flags).value)
 names = ["poll_LL", "smem+fence+sync", "issue", "mma_wait", "tmem_ld+xchg", "gates+publish", "side_stores", "loop_top"]
-for rep in range(2):
+for rep in range(int(os.environ.get("REPS", "2"))):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); lib.asr_lstm_forward(C.byref(a), cur_stream()); e1.record(); torch.cuda.synchronize()
     p = flags[1024:1024 + 64].view(torch.int64).cpu().numpy()
@@ -29,7 +29,7 @@ dz16 = torch.empty(R, 8 * H, dtype=torch.bfloat16, device=dev); dzT16 = torch.em
 dbias = torch.zeros(8 * H, device=dev)
 b = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(gates).value, cell=ptr(cell).value, U=ptr(U).value, U16=ptr(Ub16).value,
                 dz16=ptr(dz16).value, dzT16=ptr(dzT16).value, dz32=None, dbias=ptr(dbias).value, flags=ptr(flags).value)
-for rep in range(2):
+for rep in range(int(os.environ.get("REPS", "2"))):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); lib.asr_lstm_backward(C.byref(b), cur_stream()); e1.record(); torch.cuda.synchronize()
     p = flags[1024:1024 + 64].view(torch.int64).cpu().numpy()

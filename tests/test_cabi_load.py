@@ -60,15 +60,15 @@ def test_shape_queries_of_the_tensor_core_recurrences():
     T = 999
     for H in TC_WIDTHS:
         for N in (8, 16, 32, 40, 64, 128, 256):          # any multiple of 8: more groups than one wave -> several launches
-            assert lib.asr_lstm_fuses_masks(T, N, H) == 1 and lib.asr_lstm_fuses_variants(T, N, H) == 1, (N, H)
-            assert lib.asr_lstm_persistent_supported(T, N, H, 1) == 1
+            assert lib.asr_lstm_fuses_masks(T, N, H, 0) == 1 and lib.asr_lstm_fuses_variants(T, N, H, 0) == 1, (N, H)
+            assert lib.asr_lstm_persistent_supported(T, N, H, 1, 0) == 1
         for N in (1, 5, 13, 43):                          # ragged: the engine pads these (engine._padded_batch)
-            assert lib.asr_lstm_fuses_masks(T, N, H) == 0, (N, H)
+            assert lib.asr_lstm_fuses_masks(T, N, H, 0) == 0, (N, H)
     for H in (100, 200, 320, 800, 960, 1024):             # no instantiation: zero-padded by the engine, or general cell
-        assert lib.asr_lstm_fuses_masks(T, 32, H) == 0
+        assert lib.asr_lstm_fuses_masks(T, 32, H, 0) == 0
         assert (tc_width(H) in TC_WIDTHS) == (128 < H <= 896)
-    assert lib.asr_lstm_persistent_supported(T, 2, 100, 1) == 1       # graves2006 / C1: the fp32 persistent engine
-    assert lib.asr_lstm_persistent_supported(T, 16, 800, 1) == 0      # un-padded BiLSTM-800: general cell only
+    assert lib.asr_lstm_persistent_supported(T, 2, 100, 1, 0) == 1       # graves2006 / C1: the fp32 persistent engine
+    assert lib.asr_lstm_persistent_supported(T, 16, 800, 1, 0) == 0      # un-padded BiLSTM-800: general cell only
     # widest exchange ring of any launch (BPTT reduce-scatter, H = 768: 24 CTAs, three 16-sample groups per wave)
     ring = 2 * 3 * 2 * 24 * 8 * 24 * 32 * 8
     assert lib.asr_lstm_flags_bytes() >= 8192 + ring

@@ -82,7 +82,7 @@ def test_ragged_batch_is_padded_onto_the_tensor_core_engine(N, T, F, H, L, dropo
     from asr_study_b200._lib import lib
     C = 28
     eng, params, x, lens, labels, pack = _setup(N, T, F, H, L, C, seed=3 * N + T)
-    assert lib.asr_lstm_fuses_masks(T, N, H) == 0 and eng._padded_batch(T, N) > N
+    assert lib.asr_lstm_fuses_masks(T, N, H, 0) == 0 and eng._padded_batch(T, N) > N
     masks_np = masks_dev = None
     if dropout:
         rng = np.random.RandomState(9)
@@ -235,18 +235,17 @@ def test_brsmv1_switches_train_step_parity(sw):
 
 
 @pytest.mark.parametrize("pad_width", [True, False])
-def test_config4_stack_blstm800_logfbank40(pad_width, monkeypatch):
+def test_config4_stack_blstm800_logfbank40(pad_width):
     """BASELINE config 4 recurrent stack (5 x BiLSTM-800 on 40 log-mel features; the DS2-style conv front end is not
     in the reference) at a small T/N.  No kernel is instantiated for H = 800: the engine zero-pads the layers to 832
     units (26 CTAs per chain, seven U blocks in two MMA rounds) and runs the tensor-core recurrences; with
-    ASR_B200_PAD_WIDTH=0 it routes to the general cell instead.  Same parity bars either way, and the exported
+    AcousticEngine(pad_width=False) it routes to the general cell instead.  Same parity bars either way, and the exported
     parameters / gradients have the model's own shapes."""
     from asr_study_b200._lib import lib
     from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
-    monkeypatch.setenv("ASR_B200_PAD_WIDTH", "1" if pad_width else "0")
     N, T, F, H, L, C = 16, 12, 40, 800, 5, 28
-    assert lib.asr_lstm_persistent_supported(T, N, H, 1) == 0 and lib.asr_lstm_persistent_supported(999, 32, 512, 1) == 1
-    assert lib.asr_lstm_fuses_masks(T, N, 832) == 1
+    assert lib.asr_lstm_persistent_supported(T, N, H, 1, 0) == 0 and lib.asr_lstm_persistent_supported(999, 32, 512, 1, 0) == 1
+    assert lib.asr_lstm_fuses_masks(T, N, 832, 0) == 1
     from oracle import lstm as ol
     rng = np.random.RandomState(4)
     params, D = {}, F                        # scaled-normal U instead of the orthogonal init: ten 800 x 3200 SVDs take minutes
@@ -260,7 +259,7 @@ def test_config4_stack_blstm800_logfbank40(pad_width, monkeypatch):
     x = rng.randn(N, T, F).astype(np.float32)
     lens = np.full(N, T, np.int32)
     labels = [rng.randint(0, C - 1, size=3).astype(np.int32) for _ in range(N)]
-    eng = AcousticEngine(ModelSpec(F, H, L, C), init_params=params)
+    eng = AcousticEngine(ModelSpec(F, H, L, C), init_params=params, pad_width=pad_width)
     flat, off, mx = pack_labels(labels, "cuda")
     loss = eng.train_step(dev(np.ascontiguousarray(x.transpose(1, 0, 2))), dev(lens), flat, off, mx, lr=1e-3, clipnorm=400.0)
     torch.cuda.synchronize()

@@ -28,10 +28,8 @@ def _params(rng, D, H, scale=1.0):
 
 def _device_fwd(p, x_ntd, training=True, engine=None):
     """x [N,T,D] -> runs zx GEMM in torch fp32 (operand prep is not under test here) + asr_lstm_forward."""
-    from asr_study_b200._lib import LstmFwdArgs, lib, ptr, cur_stream
-    os.environ.pop("ASR_B200_LSTM", None)
-    if engine in ("fp32", "tc1", "tc3"):
-        os.environ["ASR_B200_LSTM"] = engine
+    from asr_study_b200._lib import LSTM_PIN_FP32, LstmFwdArgs, lib, ptr, cur_stream
+    opts = LSTM_PIN_FP32 if engine == "fp32" else 0          # explicit engine flag of the C ABI (no environment switch)
     N, T, D = x_ntd.shape
     H = p["Uf"].shape[0]
     x = dev(x_ntd.transpose(1, 0, 2)).reshape(T * N, D)
@@ -51,19 +49,16 @@ def _device_fwd(p, x_ntd, training=True, engine=None):
     a = LstmFwdArgs(T=T, N=N, H=H, training=int(training), zx=ptr(zx).value, bias=ptr(bias).value,
                     U=ptr(U).value, U16=ptr(UT16).value, h16=ptr(out["h16"]).value, hT16=ptr(out["hT16"]).value,
                     h32=ptr(out["h32"]).value, gates=ptr(out["gates"]).value, cell=ptr(out["cell"]).value,
-                    flags=ptr(flags).value)
+                    flags=ptr(flags).value, opts=opts)
     lib.asr_lstm_forward(C.byref(a), cur_stream())
     torch.cuda.synchronize()
     assert int(flags[64]) == 0, "persistent-kernel watchdog fired"
-    os.environ.pop("ASR_B200_LSTM", None)
     return out, dict(U=U, flags=flags)
 
 
 def _device_bwd(p, fwd, aux, dout_ntd, engine=None):
-    from asr_study_b200._lib import LstmBwdArgs, lib, ptr, cur_stream
-    os.environ.pop("ASR_B200_LSTM", None)
-    if engine == "fp32":
-        os.environ["ASR_B200_LSTM"] = "fp32"
+    from asr_study_b200._lib import LSTM_PIN_FP32, LstmBwdArgs, lib, ptr, cur_stream
+    opts = LSTM_PIN_FP32 if engine == "fp32" else 0
     N, T, H2 = dout_ntd.shape
     H = H2 // 2
     R = T * N
@@ -76,11 +71,10 @@ def _device_bwd(p, fwd, aux, dout_ntd, engine=None):
     a = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates=ptr(fwd["gates"]).value, cell=ptr(fwd["cell"]).value,
                     U=ptr(aux["U"]).value, U16=ptr(U16).value, dz16=ptr(out["dz16"]).value,
                     dzT16=ptr(out["dzT16"]).value, dz32=ptr(out["dz32"]).value, dbias=ptr(out["dbias"]).value,
-                    flags=ptr(aux["flags"]).value)
+                    flags=ptr(aux["flags"]).value, opts=opts)
     lib.asr_lstm_backward(C.byref(a), cur_stream())
     torch.cuda.synchronize()
     assert int(aux["flags"][64]) == 0, "persistent-kernel watchdog fired"
-    os.environ.pop("ASR_B200_LSTM", None)
     return out
 
 
@@ -202,19 +196,102 @@ def test_tensor_core_engine_T999_drift():
     assert norm_err(h, ref) < 1e-3, norm_err(h, ref)
 
 
-@pytest.mark.parametrize("engine", ["tc3", "tc"])
-@pytest.mark.parametrize("N,T,D,H", [(32, 60, 26, 512), (16, 33, 26, 256), (16, 20, 26, 128)])
-def test_forward_engines_agree_and_match_oracle(engine, N, T, D, H):
-    """LL-ring engine (default 'tc') and cluster/DSMEM engine (tc3) against the oracle on the same inputs."""
-    rng = np.random.RandomState(H + T)
+def _fp16_storage_fwd_bwd(p, x_ntd, dout_ntd, with_masks=False, seed=0):
+    """The 16-bit-storage / TMA engine (csrc/lstm_tc4.cu) through the C ABI: zx16 in, gates16 / cell16 saved, every side
+    output a TMA tile store; optional variational-dropout masks with the fused masked copies."""
+    from asr_study_b200._lib import LstmBwdArgs, LstmFwdArgs, lib, ptr, cur_stream
+    N, T, D = x_ntd.shape
+    H = p["Uf"].shape[0]
+    R = T * N
+    assert lib.asr_lstm_fp16_storage(T, N, H, 0) == 1
+    rng = np.random.RandomState(seed)
+    mW = mU = mNext = None
+    if with_masks:
+        mW = {d: ((rng.rand(N, D) >= 0.2) / 0.8).astype(np.float32) for d in "fb"}
+        mU = np.stack([((rng.rand(N, H) >= 0.2) / 0.8).astype(np.float32) for _ in "fb"])
+        mNext = np.stack([((rng.rand(N, 2 * H) >= 0.2) / 0.8).astype(np.float32) for _ in "fb"])
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xt = dev(x_ntd.transpose(1, 0, 2)).reshape(T * N, D)
+    zs = []
+    for d in "fb":
+        xm = xt if mW is None else (xt.view(T, N, D) * dev(mW[d])[None]).reshape(R, D)
+        zs.append(xm @ dev(p["W" + d]))
+    zx16 = torch.stack(zs, dim=1).reshape(R, 8 * H).half().contiguous()          # [R, 2, 4H]
+    bias = dev(np.concatenate([p["bf"], p["bb"]]))
+    U = dev(np.stack([p["Uf"], p["Ub"]]))
+    UT16 = dev(np.stack([p["Uf"].T, p["Ub"].T])).half().contiguous()
+    f = dict(h16=torch.zeros(R, 2 * H, dtype=torch.float16, device="cuda"),
+             hT16=torch.zeros(2 * H, R, dtype=torch.bfloat16, device="cuda"),
+             gates16=torch.zeros(R, 8 * H, dtype=torch.float16, device="cuda"),
+             cell16=torch.zeros(R, 2 * H, dtype=torch.float16, device="cuda"),
+             hm16=torch.zeros(2, R, 2 * H, dtype=torch.float16, device="cuda"),
+             hmT16=torch.zeros(2, 2 * H, R, dtype=torch.bfloat16, device="cuda"),
+             hT16u=torch.zeros(2 * H, R, dtype=torch.bfloat16, device="cuda"))
+    flags = torch.zeros(lib.asr_lstm_flags_bytes() // 4, dtype=torch.int32, device="cuda")
+    kw = {}
+    if with_masks:
+        mu_d, mn_d = dev(mU), dev(mNext)
+        kw = dict(mask_u=ptr(mu_d).value, mask_next=ptr(mn_d).value, hm16=ptr(f["hm16"]).value, hmT16=ptr(f["hmT16"]).value,
+                  hT16u=ptr(f["hT16u"]).value)
+    a = LstmFwdArgs(T=T, N=N, H=H, training=1, zx16=ptr(zx16).value, bias=ptr(bias).value, U=ptr(U).value,
+                    U16=ptr(UT16).value, h16=ptr(f["h16"]).value, hT16=ptr(f["hT16"]).value,
+                    gates16=ptr(f["gates16"]).value, cell16=ptr(f["cell16"]).value, flags=ptr(flags).value, **kw)
+    lib.asr_lstm_forward(C.byref(a), cur_stream())
+    torch.cuda.synchronize()
+    assert int(flags[64]) == 0, "persistent-kernel watchdog fired"
+    dh = dev(np.ascontiguousarray(dout_ntd.transpose(1, 0, 2))).reshape(R, 2 * H)
+    b = dict(dz16=torch.zeros(R, 8 * H, dtype=torch.bfloat16, device="cuda"),
+             dzT16=torch.zeros(8 * H, R, dtype=torch.bfloat16, device="cuda"),
+             dbias=torch.zeros(8 * H, dtype=torch.float32, device="cuda"))
+    U16 = U.to(torch.bfloat16).contiguous()
+    ba = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates16=ptr(f["gates16"]).value, cell16=ptr(f["cell16"]).value,
+                     U=ptr(U).value, U16=ptr(U16).value, dz16=ptr(b["dz16"]).value, dzT16=ptr(b["dzT16"]).value,
+                     dbias=ptr(b["dbias"]).value, flags=ptr(flags).value, mask_u=kw.get("mask_u"))
+    lib.asr_lstm_backward(C.byref(ba), cur_stream())
+    torch.cuda.synchronize()
+    assert int(flags[64]) == 0, "persistent-kernel watchdog fired"
+    return f, b, dict(mW=mW, mU=mU, mNext=mNext)
+
+
+@pytest.mark.parametrize("masks", [False, True])
+@pytest.mark.parametrize("N,T,D,H", [(32, 60, 26, 512), (16, 33, 26, 256), (16, 21, 26, 128), (8, 7, 12, 384), (64, 9, 26, 512)])
+def test_fp16_storage_tma_engine_vs_oracle(masks, N, T, D, H):
+    """csrc/lstm_tc4.cu: activations 1e-3 norm-wise, saved gates / cell 1e-3 (fp16 storage), dz 1e-2, every TMA-stored
+    layout (row-major fp16, the two B_W-masked copies, the transposed bf16 copies, dz and dz^T) in the right place."""
+    rng = np.random.RandomState(H + T + N)
     p = _params(rng, D, H, scale=1.5)
     x = rng.randn(N, T, D).astype(np.float32)
-    ref, caches, _, _ = _oracle(p, x, np.zeros((N, T, 2 * H), np.float32))
-    fwd, _ = _device_fwd(p, x, engine=engine)
-    h32 = fwd["h32"].cpu().numpy().reshape(T, N, 2 * H).transpose(1, 0, 2)
-    assert norm_err(h32, ref) < 1e-3, norm_err(h32, ref)
-    c = fwd["cell"].cpu().numpy().reshape(T, N, 2, H)
+    dout = (rng.randn(N, T, 2 * H) * 0.1).astype(np.float32)
+    f, b, m = _fp16_storage_fwd_bwd(p, x, dout, with_masks=masks, seed=N)
+    lp = dict(Wf=p["Wf"], Uf=p["Uf"], bf=p["bf"], Wb=p["Wb"], Ub=p["Ub"], bb=p["bb"])
+    om_ = None if not masks else dict(Wf=m["mW"]["f"], Wb=m["mW"]["b"], Uf=m["mU"][0], Ub=m["mU"][1])
+    ref, caches = ol.bilstm_forward(x, lp, om_, dtype=np.float64)
+    h = f["h16"].float().cpu().numpy().reshape(T, N, 2 * H).transpose(1, 0, 2)
+    assert norm_err(h, ref) < 1e-3, norm_err(h, ref)
+    g = f["gates16"].float().cpu().numpy().reshape(T, N, 2, 4 * H)
+    c = f["cell16"].float().cpu().numpy().reshape(T, N, 2, H)
     for d in range(2):
+        assert norm_err(g[:, :, d].transpose(1, 0, 2), caches[d]["gates"]) < 1e-3
         assert norm_err(c[:, :, d].transpose(1, 0, 2), caches[d]["cs"]) < 1e-3
-    hT = fwd["hT16"].float().cpu().numpy().reshape(2 * H, T, N).transpose(2, 1, 0)
-    assert norm_err(hT, ref) < 8e-3
+    hT = f["hT16"].float().cpu().numpy().reshape(2 * H, T, N).transpose(2, 1, 0)
+    refU = ref if not masks else ref * np.concatenate([m["mU"][0], m["mU"][1]], axis=1)[:, None, :]
+    assert norm_err(hT, refU) < 8e-3
+    if masks:
+        hm = f["hm16"].float().cpu().numpy().reshape(2, T, N, 2 * H).transpose(0, 2, 1, 3)
+        hmT = f["hmT16"].float().cpu().numpy().reshape(2, 2 * H, T, N).transpose(0, 3, 2, 1)
+        hTu = f["hT16u"].float().cpu().numpy().reshape(2 * H, T, N).transpose(2, 1, 0)
+        for i in range(2):
+            assert norm_err(hm[i], ref * m["mNext"][i][:, None, :]) < 1e-3
+            assert norm_err(hmT[i], ref * m["mNext"][i][:, None, :]) < 8e-3
+        assert norm_err(hTu, ref) < 8e-3
+    dzs, dbs = [], []
+    for d in range(2):
+        _, _, _, db, dz = ol.lstm_backward(dout[:, :, d * H:(d + 1) * H].astype(np.float64), caches[d])
+        dzs.append(dz)
+        dbs.append(db)
+    ref_dz = np.concatenate(dzs, axis=2)
+    dz = b["dz16"].float().cpu().numpy().reshape(T, N, 8 * H).transpose(1, 0, 2)
+    assert norm_err(dz, ref_dz) < 1e-2, norm_err(dz, ref_dz)
+    dzT = b["dzT16"].float().cpu().numpy().reshape(8 * H, T, N).transpose(2, 1, 0)
+    assert norm_err(dzT, ref_dz) < 1e-2
+    assert norm_err(b["dbias"].cpu().numpy(), np.concatenate(dbs)) < 1e-2

@@ -69,6 +69,8 @@ def test_fit_generator_loop_consumes_exactly_the_epochs_and_aggregates_on_read_b
         return torch.tensor([k + 1.0, k, 0.0, 0.5])
 
     monkeypatch.setattr(m, "_train_stats", stats, raising=False)
+    checks = []
+    monkeypatch.setattr(m, "check_status", lambda: checks.append(1), raising=False)   # the per-epoch watchdog read-back
     log = []
     ends = []
 
@@ -82,7 +84,7 @@ def test_fit_generator_loop_consumes_exactly_the_epochs_and_aggregates_on_read_b
     g = _gen(4, log)
     hist = m.fit_generator(g, samples_per_epoch=12, nb_epoch=3, callbacks=[CB()], verbose=0, max_q_size=2, nb_worker=1)
     assert calls == [float(k) for k in range(9)] and log == list(range(9))
-    assert [e for e, _ in ends] == [0, 1, 2]
+    assert [e for e, _ in ends] == [0, 1, 2] and len(checks) == 3
     np.testing.assert_allclose(hist["ctc_loss"], [1.0, 4.0, 7.0])          # batch means 0,1,2 | 3,4,5 | 6,7,8
     np.testing.assert_allclose(hist["loss"], [2.0, 5.0, 8.0])
     np.testing.assert_allclose(hist["decoder_ler"], [0.5, 0.5, 0.5])

@@ -20,6 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from asr_study_b200.core import models as core_models                     # noqa: E402
 from asr_study_b200.core.ctc_utils import ctc_dummy_loss, decoder_dummy_loss  # noqa: E402
 from asr_study_b200.core import metrics                                     # noqa: E402
+from asr_study_b200.core.callbacks import LR_SCHEDULES, MetaCheckpoint      # noqa: E402
 from asr_study_b200.datasets.dataset_generator import DatasetGenerator      # noqa: E402
 from asr_study_b200.utils import generic_utils as utils                     # noqa: E402
 from asr_study_b200.utils.hparams import HParams                            # noqa: E402
@@ -64,11 +65,22 @@ def main(argv=None):
 
     meta, epoch_offset = None, 0
     if args.load:
+        # train.py:107-122: the saved training arguments are the defaults, flags given on this command line win
+        defaults = build_parser().parse_args([])
+        given = {k: v for k, v in vars(args).items() if v != getattr(defaults, k)}
         model, meta = core_models.CTCModel.load(args.load, device="cuda:%d" % local)
+        merged = dict(meta.get("training_args", {}))
+        merged.update(given)
+        for k, v in merged.items():
+            if hasattr(args, k):
+                setattr(args, k, v)
         epoch_offset = len(meta.get("epochs", []))
+        if "lr" in given:
+            model.optimizer.lr = float(args.lr)
     else:
         model_fn = utils.get_from_module("core.models", args.model)
-        model = model_fn(**(HParams().parse(args.model_params).values()), device="cuda:%d" % local)
+        model = model_fn(**(HParams().parse(args.model_params).values()), device="cuda:%d" % local,
+                         **({"seed": int(args.seed)} if args.seed is not None else {}))
         if args.opt.strip().lower() == "sgd":
             opt = core_models.SGD(lr=args.lr, momentum=args.momentum, clipnorm=args.clipnorm)
         else:
@@ -78,7 +90,8 @@ def main(argv=None):
     if world > 1:
         import torch.distributed as dist
         # called on per-layer slices of the flat gradient bucket as they complete (overlaps the BPTT recurrences)
-        model.set_data_parallel(lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True), world)
+        model.set_data_parallel(lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True), world,
+                                rank=int(os.environ.get("RANK", "0")))
 
     output_dir = args.save or os.path.join("results", "%s_%s" % (args.model, datetime.datetime.now()))
     os.makedirs(output_dir, exist_ok=True)
@@ -98,28 +111,32 @@ def main(argv=None):
             test_flow = data_gen.flow_from_fname(args.dataset[2])
     print(str(vars(args)))
 
-    class Ckpt(object):                                        # MetaCheckpoint (core/callbacks.py:8-56), .pkl payload
-        def __init__(self, path):
-            self.path, self.epochs = path, list((meta or {}).get("epochs", []))
-
-        def set_model(self, m):
-            self.model = m
-
-        def on_epoch_end(self, epoch, logs):
-            self.epochs.append(epoch)
-            if int(os.environ.get("RANK", "0")) == 0:
-                self.model.save(self.path, meta={"training_args": vars(args), "epochs": self.epochs,
-                                                 "logs": self.model.history})
+    # train.py:153-170: model / best checkpoints (+ meta) and the optional learning-rate schedule
+    callback_list = [MetaCheckpoint(os.path.join(output_dir, "model.npz"), training_args=args, meta=meta),
+                     MetaCheckpoint(os.path.join(output_dir, "best.npz"), monitor="val_decoder_ler", save_best_only=True,
+                                    mode="min", training_args=args, meta=meta)]
+    if args.lr_schedule:
+        fn = LR_SCHEDULES.get(str(args.lr_schedule).lower().strip())
+        if fn is None:
+            raise ValueError("Learning rate schedule unrecognized")
+        callback_list.append(fn(**HParams().parse(args.lr_params).values()))
 
     model.fit_generator(train_flow, samples_per_epoch=train_flow.len, nb_epoch=args.num_epochs,
                         validation_data=valid_flow, nb_val_samples=valid_flow.len if valid_flow else 0, max_q_size=10,
-                        nb_worker=1, callbacks=[Ckpt(os.path.join(output_dir, "model.pkl"))], verbose=1,
-                        initial_epoch=epoch_offset)
+                        nb_worker=1, callbacks=callback_list, verbose=1, initial_epoch=epoch_offset)
     if test_flow is not None and test_flow.len:
+        # train.py:219-233: the best checkpoint, reloaded in 'eval' mode (beam search instead of the greedy decoder)
+        best = os.path.join(output_dir, "best.npz")
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()                                      # rank 0 wrote it
+        if os.path.exists(best):
+            model, _ = core_models.CTCModel.load(best, device="cuda:%d" % local, mode="eval")
         m = model.evaluate_generator(test_flow, test_flow.len, max_q_size=10, nb_worker=1)
         msg = "Total loss: %.4f\nCTC Loss: %.4f\nLER: %.2f%%" % (m[0], m[1], m[3] * 100)
-        with open(os.path.join(output_dir, "results.txt"), "w") as f:
-            f.write(msg)
+        if int(os.environ.get("RANK", "0")) == 0:
+            with open(os.path.join(output_dir, "results.txt"), "w") as f:
+                f.write(msg)
         print(msg)
     return model
 
