@@ -142,10 +142,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         } else if (p.dtype_out == 1) {
           __half* cp = reinterpret_cast<__half*>(p.C) + o;
-          for (int j = 0; j < nc; ++j) cp[j] = __float2half_rn(v[j]);
+          if (nc == 4 && ((reinterpret_cast<uintptr_t>(cp) & 7) == 0)) {     // one 8-byte store per thread
+            const __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
+            *reinterpret_cast<uint2*>(cp) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+          } else {
+            for (int j = 0; j < nc; ++j) cp[j] = __float2half_rn(v[j]);
+          }
         } else {
           __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + o;
-          for (int j = 0; j < nc; ++j) cp[j] = __float2bfloat16_rn(v[j]);
+          if (nc == 4 && ((reinterpret_cast<uintptr_t>(cp) & 7) == 0)) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+            *reinterpret_cast<uint2*>(cp) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+          } else {
+            for (int j = 0; j < nc; ++j) cp[j] = __float2bfloat16_rn(v[j]);
+          }
         }
       }
       __syncwarp();

@@ -47,6 +47,16 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) {
 __device__ __forceinline__ void st_volatile_v2(uint2* p, uint2 v) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
+// fp16 image of a hard_sigmoid gate that keeps its saturation state: BPTT reads d hard_sigmoid = 0.2 on the open
+// interval (0, 1) and 0 on the clips off the STORED value, so a gate of 0.9999 must not round to 1.0 (nor 1e-9 to 0):
+// inside the interval the image is clamped to the nearest fp16 inside it (0x3BFF = 0.99951, 0x0001 = 6e-8)
+__device__ __forceinline__ __half gate_to_half(float g) {
+  __half h = __float2half_rn(g);
+  const unsigned short bits = __half_as_ushort(h);
+  if (g < 1.0f && bits == 0x3C00u) h = __ushort_as_half((unsigned short)0x3BFFu);
+  if (g > 0.0f && bits == 0x0000u) h = __ushort_as_half((unsigned short)0x0001u);
+  return h;
+}
 __device__ __forceinline__ void spin_until(long long t_end) {
   while (clock64() < t_end) {}
 }
@@ -183,6 +193,20 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     long long t_pub = clock64();
 
     for (int s = 0; s < T; ++s) {
+      // zx_t landed in the ring S - 1 steps ago: into registers now, under the flight time of the exchange
+      if (!tc::mbar_wait(full + (s % S), (uint32_t)((s / S) & 1), WATCHDOG_CYCLES)) {
+        atomicExch(status, 1);
+        s_dead = 1;
+        break;
+      }
+      float zxv[NPT][4];
+      {
+        const __half* zt = reinterpret_cast<const __half*>(ring + (s % S) * 4 * TILE);
+#pragma unroll
+        for (int i = 0; i < NPT; ++i)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) zxv[i][g] = __half2float(zt[((warp * NPT + i) * 4 + g) * 32 + lane]) + bias[g];
+      }
       float z[NPT][4];
       if (s > 0) {
         // the first probe leaves ~probe_delay cycles after the publish: a probe that races the peers' stores costs a
@@ -271,13 +295,6 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 #pragma unroll
           for (int g = 0; g < 4; ++g) z[i][g] = 0.0f;
       }
-      // zx_t: landed in the ring S - 1 steps ago
-      if (!tc::mbar_wait(full + (s % S), (uint32_t)((s / S) & 1), WATCHDOG_CYCLES)) {
-        atomicExch(status, 1);
-        s_dead = 1;
-        break;
-      }
-      const __half* zt = reinterpret_cast<const __half*>(ring + (s % S) * 4 * TILE);
       float gi[NPT], gf[NPT], gg[NPT], go[NPT], hv[NPT];
       uint2* xo = xb + (size_t)(s & 1) * WORDS;
 #pragma unroll
@@ -285,7 +302,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         const int n = warp * NPT + i;
         float pre[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pre[g] = z[i][g] + __half2float(zt[(n * 4 + g) * 32 + lane]) + bias[g];
+        for (int g = 0; g < 4; ++g) pre[g] = z[i][g] + zxv[i][g];
         gi[i] = asr::hard_sigmoid(pre[0]);
         gf[i] = asr::hard_sigmoid(pre[1]);
         gg[i] = asr::tanh_fast(pre[2]);
@@ -320,10 +337,10 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       for (int i = 0; i < NPT; ++i) {
         const int n = warp * NPT + i;
         if (a.training) {
-          gt[(n * 4 + 0) * 32 + lane] = __float2half_rn(gi[i]);
-          gt[(n * 4 + 1) * 32 + lane] = __float2half_rn(gf[i]);
+          gt[(n * 4 + 0) * 32 + lane] = gate_to_half(gi[i]);
+          gt[(n * 4 + 1) * 32 + lane] = gate_to_half(gf[i]);
           gt[(n * 4 + 2) * 32 + lane] = __float2half_rn(gg[i]);
-          gt[(n * 4 + 3) * 32 + lane] = __float2half_rn(go[i]);
+          gt[(n * 4 + 3) * 32 + lane] = gate_to_half(go[i]);
           ct[n * 32 + lane] = __float2half_rn(c_state[i]);
         }
         if (a.h16) ht[n * 32 + lane] = __float2half_rn(hv[i]);
@@ -499,6 +516,36 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     long long t_pub = clock64();
 
     for (int s = 0; s < T; ++s) {
+      // inputs of this step (slot s % S) and c of the step the forward pass ran BEFORE it (= the next BPTT step, slot
+      // (s + 1) % S): into registers now, under the flight time of the exchange
+      if (!tc::mbar_wait(full + (s % S), (uint32_t)((s / S) & 1), WATCHDOG_CYCLES) ||
+          (s + 1 < T && !tc::mbar_wait(full + ((s + 1) % S), (uint32_t)(((s + 1) / S) & 1), WATCHDOG_CYCLES))) {
+        atomicExch(status, 1);
+        s_dead = 1;
+        break;
+      }
+      float gi[NPT], gf[NPT], gg[NPT], go[NPT], cc[NPT], cp[NPT], dhx[NPT];
+      {
+        const uint8_t* in = ring + (s % S) * IN_BYTES;
+        const __half* gt = reinterpret_cast<const __half*>(in);
+        const __half* ct = reinterpret_cast<const __half*>(in + 4 * TILE);
+        const float* dht = reinterpret_cast<const float*>(in + 5 * TILE);
+        const float* dh2t = reinterpret_cast<const float*>(in + 7 * TILE);
+        const __half* cpt = reinterpret_cast<const __half*>(ring + ((s + 1) % S) * IN_BYTES + 4 * TILE);
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) {
+          const int n = warp * NPT + i;
+          gi[i] = __half2float(gt[(n * 4 + 0) * 32 + lane]);
+          gf[i] = __half2float(gt[(n * 4 + 1) * 32 + lane]);
+          gg[i] = __half2float(gt[(n * 4 + 2) * 32 + lane]);
+          go[i] = __half2float(gt[(n * 4 + 3) * 32 + lane]);
+          cc[i] = __half2float(ct[n * 32 + lane]);
+          cp[i] = (s + 1 < T) ? __half2float(cpt[n * 32 + lane]) : 0.0f;
+          const float dho = dht[n * 32 + lane];
+          const float dho2 = has_dh2 ? dh2t[n * 32 + lane] : 0.0f;
+          dhx[i] = fmaf(dho2, md1[i], dho * md0[i]);         // dL/d(output): the two masked dX partials of the layer above
+        }
+      }
       float dh_rec[NPT];
 #pragma unroll
       for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
@@ -541,75 +588,27 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
           dh_rec[2 * pp + 1] = mu[2 * pp + 1] * s1;
         }
       }
-      // inputs of this step (slot s % S) and c of the step the forward pass ran BEFORE it (= the next BPTT step, slot (s + 1) % S)
-      if (!tc::mbar_wait(full + (s % S), (uint32_t)((s / S) & 1), WATCHDOG_CYCLES) ||
-          (s + 1 < T && !tc::mbar_wait(full + ((s + 1) % S), (uint32_t)(((s + 1) / S) & 1), WATCHDOG_CYCLES))) {
-        atomicExch(status, 1);
-        s_dead = 1;
-        break;
-      }
-      const uint8_t* in = ring + (s % S) * IN_BYTES;
-      const __half* gt = reinterpret_cast<const __half*>(in);
-      const __half* ct = reinterpret_cast<const __half*>(in + 4 * TILE);
-      const float* dht = reinterpret_cast<const float*>(in + 5 * TILE);
-      const float* dh2t = reinterpret_cast<const float*>(in + 7 * TILE);
-      const __half* cpt = reinterpret_cast<const __half*>(ring + ((s + 1) % S) * IN_BYTES + 4 * TILE);
-      // staging buffer for dz (free once the TMA stores of step s - 2 have read it)
-      const int b = s & 1;
-      if (s >= 2 && !tc::mbar_wait(sfree + b, (uint32_t)(((s >> 1) - 1) & 1), WATCHDOG_CYCLES)) {
-        atomicExch(status, 1);
-        s_dead = 1;
-        break;
-      }
-      uint8_t* st = stage + b * STAGE_BYTES;
-      __nv_bfloat16* dzt = reinterpret_cast<__nv_bfloat16*>(st);
-      __nv_bfloat16* dzTt = reinterpret_cast<__nv_bfloat16*>(st + 4 * TILE);
       float dz[NPT][4];
 #pragma unroll
       for (int i = 0; i < NPT; ++i) {
         const int n = warp * NPT + i;
-        const float gi = __half2float(gt[(n * 4 + 0) * 32 + lane]), gf = __half2float(gt[(n * 4 + 1) * 32 + lane]);
-        const float gg = __half2float(gt[(n * 4 + 2) * 32 + lane]), go = __half2float(gt[(n * 4 + 3) * 32 + lane]);
-        const float cc = __half2float(ct[n * 32 + lane]);
-        const float cp = (s + 1 < T) ? __half2float(cpt[n * 32 + lane]) : 0.0f;
-        const float dho = dht[n * 32 + lane];
-        const float dho2 = has_dh2 ? dh2t[n * 32 + lane] : 0.0f;
-        const float dh = fmaf(dho2, md1[i], fmaf(dho, md0[i], dh_rec[i]));
-        const float tch = asr::tanh_fast(cc);
-        const float d_o = dh * tch * asr::hard_sigmoid_grad(go);
-        const float dc = dc_carry[i] + dh * go * (1.0f - tch * tch);
-        dz[i][0] = dc * gg * asr::hard_sigmoid_grad(gi);
-        dz[i][1] = dc * cp * asr::hard_sigmoid_grad(gf);
-        dz[i][2] = dc * gi * (1.0f - gg * gg);
+        const float dh = dhx[i] + dh_rec[i];
+        const float tch = asr::tanh_fast(cc[i]);
+        const float d_o = dh * tch * asr::hard_sigmoid_grad(go[i]);
+        const float dc = dc_carry[i] + dh * go[i] * (1.0f - tch * tch);
+        dz[i][0] = dc * gg[i] * asr::hard_sigmoid_grad(gi[i]);
+        dz[i][1] = dc * cp[i] * asr::hard_sigmoid_grad(gf[i]);
+        dz[i][2] = dc * gi[i] * (1.0f - gg[i] * gg[i]);
         dz[i][3] = d_o;
-        dc_carry[i] = dc * gf;
+        dc_carry[i] = dc * gf[i];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const __nv_bfloat16 v16 = __float2bfloat16_rn(dz[i][g]);
           const int k = g * 32 + lane;                       // K index inside my 128 gate columns
-          *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = v16;
-          dzt[(n * 4 + g) * 32 + lane] = v16;
+          *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = __float2bfloat16_rn(dz[i][g]);
           db[g] += dz[i][g];
         }
       }
-      if (a.dzT16) {                                       // [4 gates][32 units][NB samples]
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          __nv_bfloat16* dst = dzTt + (g * 32 + lane) * NB + warp * NPT;
-          const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]);
-          if constexpr (NPT == 4) {
-            const __nv_bfloat162 p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&p0);
-            pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(dst) = pk;
-          } else {
-            *reinterpret_cast<__nv_bfloat162*>(dst) = p0;
-          }
-        }
-      }
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive(sfull + b);                          // dz staged; the input slots of this step are read
       if (s + 1 < T) {
         tc::named_bar_sync(1, CTHREADS);                   // the whole B operand (all samples) is in shared memory
         if (s_dead) break;
@@ -647,6 +646,38 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         tc::tcgen05_fence_before();
         t_pub = clock64();
       }
+      // side outputs (dz for the dW / dU / dX GEMMs) -> staging buffer s & 1, off the chain: after the send
+      const int b = s & 1;
+      if (s >= 2 && !tc::mbar_wait(sfree + b, (uint32_t)(((s >> 1) - 1) & 1), WATCHDOG_CYCLES)) {
+        atomicExch(status, 1);
+        s_dead = 1;
+        break;
+      }
+      uint8_t* st = stage + b * STAGE_BYTES;
+      __nv_bfloat16* dzt = reinterpret_cast<__nv_bfloat16*>(st);
+      __nv_bfloat16* dzTt = reinterpret_cast<__nv_bfloat16*>(st + 4 * TILE);
+#pragma unroll
+      for (int i = 0; i < NPT; ++i)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dzt[((warp * NPT + i) * 4 + g) * 32 + lane] = __float2bfloat16_rn(dz[i][g]);
+      if (a.dzT16) {                                       // [4 gates][32 units][NB samples]
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __nv_bfloat16* dst = dzTt + (g * 32 + lane) * NB + warp * NPT;
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(dz[0][g], dz[1][g]);
+          if constexpr (NPT == 4) {
+            const __nv_bfloat162 p1 = __floats2bfloat162_rn(dz[2][g], dz[3][g]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(dst) = pk;
+          } else {
+            *reinterpret_cast<__nv_bfloat162*>(dst) = p0;
+          }
+        }
+      }
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(sfull + b);                          // dz staged; the input slots of this step were read long ago
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);
