@@ -324,6 +324,14 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
 // Rows are stored un-normalised for ONE frame (the row maximum is published next to the row and subtracted by
 // the readers), and the running sum of maxima is the fp64 offset: alpha_t(s) = stored + offA[t].
 constexpr int PF = 4;         // emission prefetch distance of the multi-warp lattice (frames)
+// warp maximum in ONE instruction (REDUX.MAX over an order-preserving integer image of the floats) instead of a
+// five-stage shuffle tree: the row maximum of the lattice sits on the 999-step dependent chain
+__device__ __forceinline__ int f2ord(float x) {
+  const int i = __float_as_int(x);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float warp_max_redux(float v) { return ord2f(__reduce_max_sync(0xffffffffu, f2ord(v))); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -381,7 +389,7 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
     {
       if (s < S) w_alpha[s] = a;
       (rowA + 2)[s] = a;
-      const float wm = asr::warp_max(a);
+      const float wm = warp_max_redux(a);
       if (lane == 0) mxA[warp] = wm;
       if (tid == 0) w_offA[0] = 0.0;
     }
@@ -411,7 +419,7 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
       off += (M > NEG) ? (double)M : 0.0;
       if (s < S) w_alpha[(size_t)t * s_max + s] = a;
       (rowA + (t & 1) * 132 + 2)[s] = a;
-      const float wm = asr::warp_max(a);
+      const float wm = warp_max_redux(a);
       if (lane == 0) mxA[(t & 1) * 4 + warp] = wm;
       if (tid == 0) w_offA[t] = off;
       named_bar_sync(1, 128);
@@ -431,7 +439,7 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
     {
       if (s < S) w_beta[(size_t)(len - 1) * s_max + s] = b;
       (rowB + ((len - 1) & 1) * 132)[s] = b;
-      const float wm = asr::warp_max(b);
+      const float wm = warp_max_redux(b);
       if (lane == 0) mxB[((len - 1) & 1) * 4 + w4] = wm;
       if (tid == 128) w_offB[len - 1] = 0.0;
     }
@@ -459,7 +467,7 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
       off += (M > NEG) ? (double)M : 0.0;
       if (s < S) w_beta[(size_t)t * s_max + s] = b;
       (rowB + (t & 1) * 132)[s] = b;
-      const float wm = asr::warp_max(b);
+      const float wm = warp_max_redux(b);
       if (lane == 0) mxB[(t & 1) * 4 + w4] = wm;
       if (tid == 128) w_offB[t] = off;
       named_bar_sync(2, 128);
