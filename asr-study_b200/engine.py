@@ -382,32 +382,42 @@ class AcousticEngine:
         return w
 
     # ---------------------------------------------------- weight operand prep
-    def _prep_weights(self, training):
-        """16-bit tensor-core operands derived from the fp32 masters (once per step)."""
+    def _prep_weights(self, training, first_only=False, skip_first=False):
+        """16-bit tensor-core operands derived from the fp32 masters (once per step).
+        first_only / skip_first split the work: what the first recurrent layer's forward pass needs (its W^T and U^T)
+        is made on the main stream, everything else (the other layers, every BPTT operand, the Dense pair) on the side
+        stream, where it runs on the SMs the first recurrence leaves idle (~20 small launches off the critical path)."""
         sp, P = self.spec, self.params
         Cc = sp.num_classes
         st = cur_stream()
         D = sp.proj_width or sp.num_features                        # width the first BiLSTM sees
         for l, H in enumerate(sp.hs):
             Dp = _pad8(D)
-            wt = self._buf(f"WcatT16.{l}", (8 * H, Dp), torch.float16, zero=True)     # [8H, D]  fwd B operand
-            for i, d in enumerate("fb"):
-                lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wt[i * 4 * H:]), Dp, D, 4 * H, F16, st)
-            if sp.layer_norm is not None:     # split-precision projection (fp16 rounding residuals), see _forward_general
-                wl = self._buf(f"WcatT16lo.{l}", (8 * H, Dp), torch.float16, zero=True)
+            fwd_ops = not (skip_first and l == 0)
+            rest = not first_only
+            if first_only and l > 0:
+                break
+            if fwd_ops:
+                wt = self._buf(f"WcatT16.{l}", (8 * H, Dp), torch.float16, zero=True)     # [8H, D]  fwd B operand
                 for i, d in enumerate("fb"):
-                    lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wl[i * 4 * H:]), Dp, D, 4 * H, F16_LO, st)
-            ut = self._buf(f"UT16.{l}", (2, 4 * H, H), torch.float16)                 # [2, 4H, H] U^T, fwd recurrence
-            for i, d in enumerate("fb"):
-                lib.asr_cast_transpose(ptr(P.p(f"l{l}.U{d}")), 4 * H, ptr(ut[i]), H, H, 4 * H, F16, st)
-            if training:
+                    lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wt[i * 4 * H:]), Dp, D, 4 * H, F16, st)
+                if sp.layer_norm is not None:     # split-precision projection (fp16 rounding residuals), see _forward_general
+                    wl = self._buf(f"WcatT16lo.{l}", (8 * H, Dp), torch.float16, zero=True)
+                    for i, d in enumerate("fb"):
+                        lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wl[i * 4 * H:]), Dp, D, 4 * H, F16_LO, st)
+                ut = self._buf(f"UT16.{l}", (2, 4 * H, H), torch.float16)                 # [2, 4H, H] U^T, fwd recurrence
+                for i, d in enumerate("fb"):
+                    lib.asr_cast_transpose(ptr(P.p(f"l{l}.U{d}")), 4 * H, ptr(ut[i]), H, H, 4 * H, F16, st)
+            if rest and training:
                 ub = self._buf(f"Ub16.{l}", (2, H, 4 * H), torch.bfloat16)             # [2, H, 4H] U, BPTT recurrence
                 lib.asr_cast_rows(ptr(P.p(f"l{l}.Uf")), 4 * H, ptr(ub), 4 * H, 2 * H, 4 * H, BF16, st)
-            if training and (l > 0 or sp.proj_width):
+            if rest and training and (l > 0 or sp.proj_width):
                 wc = self._buf(f"Wcat16.{l}", (D, 8 * H), torch.bfloat16)              # [D, 8H]  dX B operand
                 for i, d in enumerate("fb"):
                     lib.asr_cast_rows(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wc[:, i * 4 * H:]), 8 * H, D, 4 * H, BF16, st)
             D = 2 * H
+        if first_only:
+            return
         dp, H2 = _pad8(Cc), 2 * sp.hs[-1]
         wd = self._buf("WdT16", (Cc, _pad8(H2)), torch.float16, zero=True)             # [C, 2H (padded to 8)] logits B operand
         lib.asr_cast_transpose(ptr(P.p("dense.W")), Cc, ptr(wd), _pad8(H2), H2, Cc, F16, st)
@@ -510,12 +520,26 @@ class AcousticEngine:
         self._zmasks = zmasks if training else None
         self._zpacked = {}
         st = cur_stream()
-        self._prep_weights(training)
         feats_tm = feats_tm.contiguous()
         D0 = _pad8(Fd)
+        main = torch.cuda.current_stream()
+        prep_ev = None
+        if self.overlap and L > 1:
+            # operands of the first layer's forward pass here; everything else on the side stream under its recurrence
+            self._prep_weights(training, first_only=True)
+            self._side.wait_stream(main)                 # the previous step's optimiser update / readers are behind us
+            with torch.cuda.stream(self._side):
+                self._prep_weights(training, skip_first=True)
+                if training:
+                    lib.asr_cast_transpose(ptr(feats_tm), Fd, ptr(w["xT16"]), R, R, Fd, BF16, cur_stream())
+                prep_ev = torch.cuda.Event()
+                prep_ev.record(self._side)
+            feats_tm.record_stream(self._side)
+        else:
+            self._prep_weights(training)
+            if training:
+                lib.asr_cast_transpose(ptr(feats_tm), Fd, ptr(w["xT16"]), R, R, Fd, BF16, st)
         lib.asr_cast_rows(ptr(feats_tm), Fd, ptr(w["x16"]), D0, R, Fd, F16, st)
-        if training:
-            lib.asr_cast_transpose(ptr(feats_tm), Fd, ptr(w["xT16"]), R, R, Fd, BF16, st)
         x16, D = w["x16"], D0
         src, src_dt, src_ld, Dl = feats_tm, 2, Fd, Fd              # layer input before masking
         # with dropout the recurrence of layer l-1 writes the masked operand copies of layer l itself (fused side
@@ -524,6 +548,8 @@ class AcousticEngine:
         self._fused = fuse
         prev = None                                                 # fused outputs of the previous layer
         for l in range(L):
+            if l == 1 and prep_ev is not None:
+                main.wait_event(prep_ev)                   # the side-stream operand preparation (long finished by now)
             mask_u = None
             zx = w["zx"]
             if training and sp.mi is not None:             # the backward pass of MI re-reads every layer's Wx
@@ -908,7 +934,8 @@ class AcousticEngine:
         """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad.
         allreduce (data parallel): called on slices of the flat gradient bucket as soon as they are complete — layer
         l's slice right behind its dW/dU GEMMs, i.e. while the BPTT of layer l-1 runs — so the collective overlaps the
-        recurrences; the slices tile the bucket exactly once (still ONE logical all-reduce of the bucket per step).
+        recurrences, the Dense slice right behind its own GEMM at the start; the slices tile the bucket exactly once (still
+        ONE logical all-reduce of the bucket per step).
         Returns the handles (objects with .wait()) the callable returned, if any."""
         sp, P, w = self.spec, self.params, self._w
         handles = []
@@ -944,6 +971,8 @@ class AcousticEngine:
             lib.asr_mask_cast(ptr(w[f"h16.{top}"]), 0, 2 * H, ptr(ones), N, ptr(topT), BF16, R, R, 2 * H, 1, st)
         # dWd [2H, C] = topT [2H, R] . dlT [C, R]^T
         self._gemm(BF16, OUT_F32, 2 * H, Cc, R, topT, R, w["dlT16"], R, P.g("dense.W"), Cc)
+        if allreduce is not None:                       # the Dense slice is complete: reduce it under the whole BPTT
+            handles.append(allreduce(P.grad[P.offsets["dense.W"]:]))
         # dTop [R, 2H] = dl16 [R, Cpad] . Wd16 [2H, Cpad]^T
         dh, other = w["dhA"], w["dhB"]
         self._gemm(BF16, OUT_F32, R, 2 * H, cp, w["dl16"], cp, self._ws["Wd16"], cp, dh, 2 * H)
@@ -1000,9 +1029,9 @@ class AcousticEngine:
                                            C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, bg, sst)
                     else:
                         P.g(f"l{l}.U{d}").zero_()
-                if allreduce is not None and l > 0:     # layer l's gradients are complete on this stream: reduce them now
+                if allreduce is not None:               # layer l's gradients are complete on this stream: reduce them now
                     lo, hi = self._layer_slice(l)
-                    handles.append(allreduce(P.grad[lo:hi]))
+                    handles.append(allreduce(P.grad[(0 if l == 0 else lo):hi]))
             if l > 0 and masks is None:
                 # dX [R, 2H] = dz16 [R, 8H] . Wcat16 [2H, 8H]^T
                 self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w[f"dz16.{l}"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
@@ -1024,9 +1053,6 @@ class AcousticEngine:
                     dh, other = other, dh
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self._side)
-        if allreduce is not None:                       # layer 0 and the Dense layer: the two ends of the bucket
-            handles.append(allreduce(P.grad[:self._layer_slice(0)[1]]))
-            handles.append(allreduce(P.grad[P.offsets["dense.W"]:]))
         return handles
 
     # -------------------------------------------------------------- optimiser

@@ -9,8 +9,11 @@ N > 1: data parallel (configs[2] shape), one NCCL all-reduce of the flat gradien
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference        # CPU arm: oracle port of the reference path on the host cores
 
-Prints ONE JSON line (see the task contract): value = device-resident throughput,
-e2e = through the public API with host pcm (pinned) -> H2D -> step -> D2H loss every step.
+Prints ONE JSON line (see the task contract): value = device-resident throughput; e2e = through the reference-facing
+plugin surface: a DatasetIterator (datasets/dataset_generator.py contract: host pcm in, host feature batches out, on
+Keras' generator thread) feeding CTCModel.train_on_batch (host features in, host metrics out), every copy inside the timed
+region; e2e_engine = the engine-level variant (pinned host pcm -> H2D -> step -> D2H loss).  At N = 1 the line also
+carries `infer` (BASELINE configs[4]: 10 k clips, beam 100, LER parity on 256 clips) and `cpu_baseline`.
 """
 from __future__ import annotations
 
@@ -107,29 +110,43 @@ def cpu_step(pcm, labels, params, state, dropout=0.2):
     return float(ctc.mean())
 
 
+CPU_SAMPLE = 32          # both CPU legs time the same thing: one full step on all 32 clips of the C2 batch
+
+
 def cpu_arm(n_sample, steps, warmup):
+    """The oracle port on ALL host cores whatever the launcher exported: torch.distributed.run sets OMP_NUM_THREADS=1
+    for its children, which would pin numpy's BLAS to one thread; the pool size is set here, at run time."""
+    from threadpoolctl import threadpool_limits
+
     from oracle import model as om
+    cores = os.cpu_count() or 1
     params = om.init_params(F, H, L, C, seed=4321)
     pcm, labels = synth_batch(n_sample, 1234)
     state = {}
-    for _ in range(warmup):
-        cpu_step(pcm, labels, params, state)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_step(pcm, labels, params, state)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
+    with threadpool_limits(limits=cores):
+        for _ in range(warmup):
+            cpu_step(pcm, labels, params, state)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_step(pcm, labels, params, state)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
     return n_sample / dt, dt
+
+
+def cpu_sample_text(n_sample, dt):
+    return (f"all {n_sample} clips of one C2 step (full 10 s, T=999): oracle port incl. MFCC + BPTT + clip + Adam, numpy BLAS "
+            f"pool set to all {os.cpu_count()} cores by threadpoolctl (launcher-independent), {dt:.1f} s per step")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 32
+    n_sample = CPU_SAMPLE
     steps, warmup = max(1, min(args.steps, 2)), 0
     val, dt = cpu_arm(n_sample, steps, warmup)
     cores = os.cpu_count()
-    sample = f"all {n_sample} clips of one step (full 10 s, T=999), oracle port incl. MFCC+BPTT+clip+Adam, numpy BLAS threads = all cores"
+    sample = cpu_sample_text(n_sample, dt)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "utt/s", "n_gpus": args.gpus, "steps": steps,
            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -151,7 +168,9 @@ def run_ours(args):
     import torch.distributed as dist
 
     from asr_study_b200._lib import lib
-    from asr_study_b200.engine import AcousticEngine, ModelSpec, pack_labels
+    from asr_study_b200.core import models
+    from asr_study_b200.datasets.dataset_generator import DatasetIterator
+    from asr_study_b200.engine import pack_labels
     from asr_study_b200.preprocessing import audio
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -171,8 +190,12 @@ def run_ours(args):
     off_dev = off_host.to(dev)
     flat, loff, mx = pack_labels(labels, dev)
     feat = audio.MFCC(num_cep=13, d=True, dd=(F == 39))
-    eng = AcousticEngine(ModelSpec(F, H, L, C, weight_decay=1e-4, dropout=args.dropout, zoneout=args.zoneout,
-                                   mi=(1.0, 0.5, 0.5) if args.mi else None), device=dev, seed=4321)
+    # the reference's own model factory and optimiser set-up (core/models.py:217-281, train.py:133-143)
+    model = models.brsmv1(num_features=F, num_hiddens=H, num_layers=L, num_classes=C, dropout=args.dropout,
+                          zoneout=args.zoneout, mi=[1.0, 0.5, 0.5] if args.mi else None, weight_decay=1e-4,
+                          device=str(dev), seed=4321)
+    model.compile(optimizer=models.Adam(lr=1e-3, clipnorm=400.0))
+    eng = model.engine
     loss_host = torch.empty(nb, dtype=torch.float32).pin_memory()
     loss_bufs = [loss_host, torch.empty(nb, dtype=torch.float32).pin_memory()]
     loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
@@ -181,6 +204,9 @@ def run_ours(args):
     def allreduce(g):                  # called on per-layer slices of the gradient bucket as they complete (engine.backward)
         if world > 1:
             return dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
+
+    if world > 1:
+        model.set_data_parallel(allreduce, world, rank=rank)
 
     # input pipeline: batch k+1's H2D copy + fused MFCC launch run on a side stream while batch k trains
     # (asr_study_b200/datasets/prefetch.py); every step still featurises its own batch inside the timed region
@@ -215,6 +241,21 @@ def run_ours(args):
             loss_evs[(k - 1) & 1].synchronize()
             e2e_state["last"] = float(loss_bufs[(k - 1) & 1].mean())
         return loss_bufs[k & 1]
+
+    # ---- e2e through the plugin surface: DatasetIterator (host pcm -> host feature batch, one fused K1 launch per batch,
+    # on a generator worker thread like Keras' fit_generator, max_q_size 10) -> CTCModel.train_on_batch (host batch in,
+    # [loss, ctc_loss, decoder_loss, decoder_ler] out as Python floats: one device->host read per step)
+    from asr_study_b200.core.models import _GeneratorFeed
+    flow = DatasetIterator([pcm_np[i] for i in range(nb)], [np.asarray(l, np.int32) for l in labels], batch_size=nb,
+                           shuffle=False, input_parser=feat, label_parser=None, rank=0, world_size=1)
+    plugin = {"feed": None, "last": None}
+
+    def plugin_start(total_steps):
+        plugin["feed"] = _GeneratorFeed(flow, total_steps * nb, 10, 1, dev)
+
+    def step_plugin():
+        x, _y = plugin["feed"].get()
+        plugin["last"] = model.train_on_batch(x)
 
     def barrier():
         if world > 1:
@@ -251,8 +292,17 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    plugin_start(args.steps + 2)
+    for _ in range(2):
+        step_plugin()
+    ms_plugin = timed(step_plugin, args.steps)
+    plugin["feed"].close()
+    model.check_status()
     value = gb * args.steps / (ms / 1e3)
-    e2e = gb * args.steps / (ms_e2e / 1e3)
+    e2e_engine = gb * args.steps / (ms_e2e / 1e3)
+    e2e = gb * args.steps / (ms_plugin / 1e3)
+    feat_bytes = int(nb * T_FRAMES * F * 4)
+    dp_check = dp_equivalence(model, feat, nb, world, rank, dev, torch, dist) if world > 1 else None
 
     # per-kernel-class device time (instrumented pass, outside the timed region)
     kern = kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch) if rank == 0 else {}
@@ -262,20 +312,22 @@ def run_ours(args):
         step_tf = value * GFLOP_TRAIN_PER_UTT / 1e3 / world                       # TFLOP/s per GPU
         gf = 2 * 2.0 * T_FRAMES * nb * H * 4 * H / 1e9                           # recurrent matmul of ONE launch (2 dirs)
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath))
         # dominant kernel = the backward recurrence (largest share of the step, profiles/ncu_summary_*.md)
         ms_bwd = kern.get("lstm_bwd_ms", 0.0) / L
         ms_fwd = kern.get("lstm_fwd_ms", 0.0) / L
-        roof = {"bound": "tensor", "kernel": "lstmtc2::bwd3_kernel (persistent BiLSTM BPTT, one launch per layer)",
+        roof = {"bound": "tensor", "kernel": "lstmtc4::bwd_kernel (persistent BiLSTM BPTT, one launch per layer)",
                 "achieved": gf / ms_bwd if ms_bwd else None, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                 "frac": (gf / ms_bwd / pk["tf_burst"]) if ms_bwd else None,
                 "peak_source": pk["src"] + " bf16_tflops (burst; kernel timed alone with CUDA events)",
                 "flop_per_launch": gf * 1e9, "ms_per_launch": ms_bwd,
                 "traffic": (traffic or {}).get("lstm_bwd_bytes_per_launch"),
                 "mma_precision": "bf16 operands, fp32 accumulate (TS-mode tcgen05.mma, U tile resident in TMEM)",
-                "note": "latency-bound by design at N=32: 999 dependent steps per launch; see profiles/lstm_phases_r1.md",
+                "note": "latency-bound by design at N=32: 999 dependent steps per launch; see profiles/lstm_phases_r2.md",
                 "others": {
                     "lstm_fwd": {"achieved": gf / ms_fwd if ms_fwd else None, "ms_per_launch": ms_fwd,
                                  "frac": (gf / ms_fwd / pk["tf_burst"]) if ms_fwd else None,
@@ -297,22 +349,76 @@ def run_ours(args):
                           "l2_flush": "per-step working set ~4 GB >> 126 MB L2 (inputs larger than L2)",
                           "input_pipeline": "prefetch: H2D + MFCC of batch k+1 on a side stream during step k" if args.prefetch
                           else "in line"},
-               "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": int(pcm_host.numel() * 4),
-                       "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+               "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": int(pcm_host.numel() * 4) + feat_bytes,
+                       "d2h_bytes_per_step": feat_bytes + 16, "ms_per_step": ms_plugin / args.steps,
+                       "path": "DatasetIterator (host pcm -> K1 -> host [N,T,F] batch, generator thread, queue 10) -> "
+                               "CTCModel.train_on_batch (host batch -> device -> step -> 4 metrics read back per step)",
+                       "last_metrics": plugin["last"]},
+               "e2e_engine": {"value": e2e_engine, "unit": "utt/s", "h2d_bytes_per_step": int(pcm_host.numel() * 4),
+                              "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
+                              "path": "pinned host pcm -> H2D + K1 one step ahead on a side stream -> engine.train_step -> "
+                                      "per-utterance loss D2H, read one step late"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_ms": kern,
+               **({"data_parallel_check": dp_check} if dp_check is not None else {}),
                "final_loss_mean": float(loss_bufs[(e2e_state["k"] - 1) & 1].mean())}
     if world > 1:
         dist.barrier()
     if rank == 0:
         if args.cpu_baseline and world == 1:            # the CPU port beside the GPU number: rank 0 at N = 1 only
-            n_sample = 16
-            v, dt = cpu_arm(n_sample, 1, 0)
+            if args.infer:                               # BASELINE configs[4] inside the default line (driver-visible)
+                del model, eng
+                torch.cuda.empty_cache()
+                out["infer"] = run_infer(args, quiet=True)
+            v, dt = cpu_arm(CPU_SAMPLE, 1, 0)
             out["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"{n_sample} of the 32 clips, 1 step (full T=999), oracle port "
-                                             f"(numpy, BLAS threads = all cores), {dt:.1f} s"}
+                                   "sample": cpu_sample_text(CPU_SAMPLE, dt)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dp_equivalence(model, feat, nb, world, rank, dev, torch, dist):
+    """Two checks of the data-parallel path on the hardware (outside the timed region, reported in the N > 1 line):
+    replica_checksum_spread  max over ranks of |sum(params_rank) - sum(params_0)| after the timed steps — the replicas
+                             apply the same reduced gradient with the same kernels and must stay bit-identical: 0.0;
+    dp_vs_big_batch_grad     the gradient of ONE global batch computed data-parallel (each rank its 32 utterances, the
+                             bucket all-reduced in per-layer slices) against the same global batch computed by rank 0
+                             alone as one big batch (dropout off on both sides): max |d| / max |ref| over the bucket."""
+    import dataclasses
+
+    from asr_study_b200.engine import AcousticEngine, pack_labels
+    eng = model.engine
+    sums = torch.stack([eng.params.flat.double().sum(), eng.params.flat.double().abs().sum()])
+    gathered = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(gathered, sums)
+    spread = max(float((g - gathered[0]).abs().max()) for g in gathered)
+    spec0 = dataclasses.replace(eng.user_spec, dropout=0.0)
+    e2 = AcousticEngine(spec0, device=dev, init_params=eng.params.export("flat"))
+    gb = nb * world
+
+    def grads(pcm_np, labels, allreduce):
+        pcm = torch.from_numpy(pcm_np.reshape(-1)).to(dev)
+        off = (torch.arange(pcm_np.shape[0] + 1, dtype=torch.int64) * pcm_np.shape[1]).to(dev)
+        x, lens = feat.batch(pcm, off, t_max=T_FRAMES, time_major=True)
+        flat, loff, mx = pack_labels(labels, dev)
+        logits = e2.forward(x, training=True)
+        _, dl = e2.ctc(logits, lens, flat, loff, mx, grad_scale=1.0 / gb)
+        for h in e2.backward(dl, allreduce=allreduce):
+            if h is not None and hasattr(h, "wait"):
+                h.wait()
+        torch.cuda.synchronize()
+        return e2.params.grad.clone()
+
+    pcm_r, lab_r = synth_batch(nb, 1234 + 1000 * rank)
+    g_dp = grads(pcm_r, lab_r, lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True))
+    err = None
+    if rank == 0:
+        parts = [synth_batch(nb, 1234 + 1000 * r) for r in range(world)]
+        g_big = grads(np.concatenate([p[0] for p in parts]), sum((p[1] for p in parts), []), None)
+        err = float((g_dp - g_big).abs().max() / g_big.abs().max())
+    dist.barrier()
+    return {"replica_checksum_spread": spread, "dp_vs_big_batch_grad": err,
+            "note": "spread must be 0.0; the gradient difference is summation order + 16-bit operand rounding of different tilings"}
 
 
 def kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch):
@@ -357,7 +463,7 @@ def kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch):
     return {k: round(v, 4) for k, v in res.items()}
 
 
-def run_infer(args):
+def run_infer(args, quiet=False):
     """configs[4] (C5): MFCC -> 3xBiLSTM-512 forward -> CTC beam search (width 100) over synthetic 10 s clips on one
     B200; prints clips/s and checks LER parity of the device decode against the oracle's TF-order beam search on a
     sample of the same logits (identical label sequences => identical LER)."""
@@ -367,6 +473,7 @@ def run_infer(args):
     from asr_study_b200.engine import AcousticEngine, ModelSpec
     from asr_study_b200.preprocessing import audio
     from oracle import ctc as oc
+    from oracle import ctc_beam_c as occ                 # the C restatement of oc.beam_decode (tests hold it to the Python one)
     from oracle.model import synth_clip, synth_labels
 
     dev = torch.device("cuda:0")
@@ -378,10 +485,18 @@ def run_infer(args):
     # totals collide exactly, so the result hangs on tie-breaking order.  Scale the Dense kernel so the posteriors are
     # as peaky as a trained CTC model's (the regime config 5 is about); --sharpen sets the factor.
     eng.params.p("dense.W").mul_(args.sharpen)
-    pcm_np = np.stack([synth_clip(777, i, SECONDS, FS) for i in range(nb)])
-    pcm_host = torch.from_numpy(pcm_np.reshape(-1)).pin_memory()
+    # distinct synthetic clips: enough forward batches that the LER-parity sample holds no clip twice
+    n_distinct = max(1, (min(args.ler_sample, args.clips) + nb - 1) // nb)
+    pcm_nps = [np.stack([synth_clip(777, j * nb + i, SECONDS, FS) for i in range(nb)]) for j in range(n_distinct)]
+    pcm_hosts = [torch.from_numpy(p.reshape(-1)).pin_memory() for p in pcm_nps]
+    pcm_np, pcm_host = pcm_nps[0], pcm_hosts[0]
     off = (torch.arange(nb + 1, dtype=torch.int64) * pcm_np.shape[1]).to(dev)
-    truth = synth_labels(778, nb, 50)
+    truth = synth_labels(778, nb * n_distinct, 50)
+    fwd_count = {"i": 0}
+
+    def next_pcm():
+        fwd_count["i"] += 1
+        return pcm_hosts[(fwd_count["i"] - 1) % n_distinct]
 
     G = max(1, args.decode_group)
     nb_fwd = nb
@@ -404,7 +519,7 @@ def run_infer(args):
     if args.prefetch:                                     # same device input pipeline as the training bench
         from asr_study_b200.datasets.prefetch import DeviceFeaturePrefetcher
         pre = DeviceFeaturePrefetcher(feat, dev, nb_fwd, pcm_np.shape[1], T_FRAMES)
-        pre.submit(pcm_host, off)                         # primed (untimed); every timed batch still copies + featurises one
+        pre.submit(next_pcm(), off)                       # primed (untimed); every timed batch still copies + featurises one
 
     def batch():
         """G forward batches (host pcm -> H2D -> MFCC -> BiLSTM) then one beam-search launch over all G * nb utterances
@@ -420,9 +535,9 @@ def run_infer(args):
         for g in range(G):
             if pre is not None:                           # H2D + MFCC of the NEXT forward batch on the prefetcher's stream
                 x, lens = pre.get()
-                pre.submit(pcm_host, off)
+                pre.submit(next_pcm(), off)
             else:
-                pcm = pcm_host.to(dev, non_blocking=True)
+                pcm = next_pcm().to(dev, non_blocking=True)
                 x, lens = feat.batch(pcm, off, t_max=T_FRAMES, time_major=True)
             logits = eng.forward(x, training=False)
             big[:, g * nb_fwd:(g + 1) * nb_fwd].copy_(logits)
@@ -461,12 +576,18 @@ def run_infer(args):
     ms = e0.elapsed_time(e1)
     logits, lens, out, out_len = bigs[p], big_lens[p], outs_h[p], lens_h[p]
     launches = (lib.asr_launch_count() - l0) // nbatches
-    # LER parity on a sample: oracle beam on the SAME logits
+    # LER parity on a sample: the oracle's TF-order beam search on the SAME logits (the last decoded group)
     k = min(args.ler_sample, nb)
     lg = logits[:, :k].transpose(0, 1).contiguous().cpu().numpy()
-    ref = oc.beam_decode(lg, [T_FRAMES] * k, beam_width=W)
+    t_or = time.perf_counter()
+    ref = occ.beam_decode(lg, [T_FRAMES] * k, beam_width=W)
+    t_or = time.perf_counter() - t_or
     got = [[int(v) for v in out[i, :int(out_len[i])]] for i in range(k)]
     same = sum(int(a == b) for a, b in zip(got, ref))
+    # utterance u of a decoded group is clip (first forward batch of the group + u // 64) % n_distinct, u % 64: G and the
+    # number of distinct batches are both powers of two here, so groups start at distinct-batch 0
+    assert (G * nb_fwd) % (n_distinct * nb_fwd) == 0 or n_distinct % G == 0
+    truth = [truth[((u // nb_fwd) % n_distinct) * nb_fwd + u % nb_fwd] for u in range(k)]
     res = {"metric": "clips/sec (inference: MFCC -> 3xBiLSTM-512 fwd -> CTC beam search width %d)" % W,
            "value": nb * nbatches / (ms / 1e3), "unit": "clips/s", "n_gpus": 1, "clips": nb * nbatches,
            "ms_per_batch": ms / nbatches, "batch": nb, "forward_batch": nb_fwd, "higher_is_better": True, "data": "synthetic",
@@ -475,13 +596,15 @@ def run_infer(args):
                       "decode": ("beam search of group k on a second stream under the forward passes of group k+1" if overlap
                                  else "in line: forward passes, then the beam search, then the next group")},
            "gpu_launches": int(launches),
-           "ler_parity": {"sample": k, "identical_label_sequences": same,
+           "ler_parity": {"sample": k, "identical_label_sequences": same, "oracle": "oracle/ctc_beam.c (%.1f s)" % t_or,
                           "ler_device_vs_truth": oc.ler(truth[:k], got), "ler_oracle_vs_truth": oc.ler(truth[:k], ref),
                           "ler_rel_diff": abs(oc.ler(truth[:k], got) - oc.ler(truth[:k], ref)) / max(oc.ler(truth[:k], ref), 1e-12),
                           "note": "sequences differ only where fp32 beam totals tie exactly (random-init posteriors): TF breaks "
                                   "ties by heap order, which neither restatement can pin without TF; tests/test_gpu_beam.py "
                                   "has the identical-sequence cases"}}
-    print(json.dumps(res), flush=True)
+    if not quiet:
+        print(json.dumps(res), flush=True)
+    return res
 
 
 def main():
@@ -498,9 +621,10 @@ def main():
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="featurise each batch in line instead of one step ahead on the side stream")
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train = C2/C3 (default), infer = C5")
-    ap.add_argument("--clips", type=int, default=1024)
+    ap.add_argument("--clips", type=int, default=10240, help="infer mode / sub-record: BASELINE configs[4] asks for 10 k clips")
+    ap.add_argument("--no-infer", dest="infer", action="store_false", help="skip the configs[4] sub-record of the default line")
     ap.add_argument("--beam_width", type=int, default=100)
-    ap.add_argument("--ler_sample", type=int, default=4)
+    ap.add_argument("--ler_sample", type=int, default=256)
     ap.add_argument("--sharpen", type=float, default=60.0, help="infer mode: factor on the random-init Dense kernel")
     ap.add_argument("--decode_group", type=int, default=16,
                     help="infer mode: forward batches decoded by ONE beam-search launch (one warp per utterance: the "

@@ -189,3 +189,24 @@ def test_ler():
     assert oc.edit_distance([], [1, 2]) == 2
     assert abs(oc.ler([[1, 2, 3, 4]], [[1, 2, 4]]) - 0.25) < 1e-12
     assert abs(oc.ler([[1, 2], [3]], [[1, 2], [4]]) - 0.5) < 1e-12
+
+
+def test_c_beam_oracle_matches_the_python_oracle():
+    """oracle/ctc_beam.c (used for the C5 label-error-rate parity on hundreds of full-length clips) against the Python
+    restatement it transcribes — itself pinned on TensorFlow's known answer above: identical label sequences on
+    near-uniform, peaky and tie-heavy posteriors, several widths, ragged lengths, merge_repeated on and off."""
+    from oracle import ctc_beam_c as occ
+    rng = np.random.RandomState(11)
+    for (N, T, C, W, sharp) in [(4, 30, 6, 1, 1.0), (4, 40, 28, 5, 3.0), (3, 50, 28, 25, 8.0), (2, 60, 28, 100, 0.3),
+                                (3, 25, 5, 400, 2.0)]:
+        lg = (rng.randn(N, T, C) * sharp).astype(np.float32)
+        lg[0] = np.round(lg[0])                                   # exact ties between classes / beams
+        lens = [T, max(1, T // 2), T - 3, T][:N]
+        for merge in (True, False):
+            ref = oc.beam_decode(lg, lens, beam_width=W, merge_repeated=merge)
+            got = occ.beam_decode(lg, lens, beam_width=W, merge_repeated=merge)
+            assert got == ref, (N, T, C, W, sharp, merge)
+    d, p, logits = _tf_beam_case()                                # and TensorFlow's own known answer, directly
+    assert occ.beam_decode(logits, [d["seq_len"]], beam_width=d["beam_width"]) == [d["top_path_width_2"]]
+    for W in (3, 16, 100):
+        assert occ.beam_decode(logits, [d["seq_len"]], beam_width=W) == [d["second_path_width_2"]]
