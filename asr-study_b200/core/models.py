@@ -117,6 +117,7 @@ class CTCModel(object):
         self.world_size = 1
         self.history = {}
         self._noise_offset = 0
+        self._stage = {}
 
     # ---- Keras-facing plumbing --------------------------------------------------
     def compile(self, loss=None, optimizer=None, metrics=None, loss_weights=None, **kw):
@@ -148,21 +149,41 @@ class CTCModel(object):
 
     # ---- batches ------------------------------------------------------------------
     def _device_batch(self, x, x_len, labels, training):
-        x = np.asarray(x, dtype=np.float32)
+        """host batch (the DatasetIterator contract: x f32 [N, Tmax, F] zero-padded, lengths, sparse labels) -> device
+        operands of the engine: time-major features [T, Np, F] (Np = N padded to the 16-sample tile), lengths, packed
+        labels.  One pinned staging buffer per shape, asynchronous copies, the batch-major -> time-major permutation done
+        by the copy engine on the device (no host transpose): ~0.3 ms of host time per C2 batch instead of ~2.5 ms."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
         N, T, F = x.shape
         Np = (N + _PAD - 1) // _PAD * _PAD
-        xt = torch.zeros(T, Np, F, dtype=torch.float32, device=self.device)
-        xt[:, :N] = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 0, 2))).to(self.device)
+        key = (N, T, F)
+        st = self._stage.get(key)
+        if st is None:
+            if len(self._stage) > 8:
+                self._stage.clear()                         # real corpora: a new Tmax per batch; keep the cache small
+            st = self._stage[key] = dict(host=torch.empty(N, T, F, dtype=torch.float32).pin_memory(),
+                                         dev=torch.empty(N, T, F, dtype=torch.float32, device=self.device),
+                                         xt=torch.zeros(T, Np, F, dtype=torch.float32, device=self.device),
+                                         lens_h=torch.zeros(Np, dtype=torch.int32).pin_memory(),
+                                         lens=torch.zeros(Np, dtype=torch.int32, device=self.device))
+        if "ev" in st:
+            st["ev"].synchronize()                           # the previous asynchronous copies out of the pinned buffers
+        st["host"].numpy()[...] = x                          # pageable -> pinned (one memcpy), then async DMA
+        st["lens_h"].zero_()
+        st["lens_h"].numpy()[:N] = np.asarray(x_len).reshape(-1)[:N]
+        st["dev"].copy_(st["host"], non_blocking=True)
+        st["lens"].copy_(st["lens_h"], non_blocking=True)
+        st.setdefault("ev", torch.cuda.Event()).record()
+        xt = st["xt"]
+        xt[:, :N].copy_(st["dev"].permute(1, 0, 2))          # layout copy on the device; the padding columns stay zero
         if training and self.input_std_noise > 0:           # GaussianNoise(std), core/models.py:67,251 (train phase only)
             self._noise_offset = self.engine.add_gaussian_noise(xt, N, self.input_std_noise, self._noise_offset)
-        lens = np.zeros(Np, np.int32)
-        lens[:N] = np.asarray(x_len).reshape(-1)[:N]
         rows = _label_rows(labels)
         packed = None
         if rows is not None:
             rows = rows + [np.zeros(0, np.int32)] * (Np - N)
             packed = pack_labels(rows, self.device)
-        return xt, torch.as_tensor(lens, device=self.device), packed, N
+        return xt, st["lens"], packed, N
 
     def _decode(self, logits, lens, with_len=False):
         if self.decoder["is_greedy"]:
@@ -301,13 +322,15 @@ class CTCModel(object):
                 k += 1
                 if done_ev[p] is not None:                 # the search two groups back no longer reads this buffer pair
                     main.wait_event(done_ev[p])
-                prepared = [self._device_batch(x[0], x[2], x[1], False) for x in batches]
-                Tmax = max(int(b[0].shape[0]) for b in prepared)
-                Ntot = sum(int(b[0].shape[1]) for b in prepared)
+                shapes = [np.asarray(x[0]).shape for x in batches]
+                Tmax = max(int(sh[1]) for sh in shapes)
+                Ntot = sum((int(sh[0]) + _PAD - 1) // _PAD * _PAD for sh in shapes)
                 big = eng._buf("eval_logits%d" % p, (Tmax, Ntot, C), torch.float32)
                 big_len = eng._buf("eval_len%d" % p, (Ntot,), torch.int32)
                 rows, real, c0 = [], [], 0
-                for x, (xt, lens, (flat, off, mx), N) in zip(batches, prepared):
+                for x in batches:
+                    # staged one at a time: batches of one shape share their pinned / device staging buffers
+                    xt, lens, (flat, off, mx), N = self._device_batch(x[0], x[2], x[1], False)
                     logits = eng.forward(xt, training=False)
                     loss, _ = eng.ctc(logits, lens, flat, off, mx, want_grad=False)
                     losses.append(loss[:N].clone())

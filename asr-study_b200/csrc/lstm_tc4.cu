@@ -31,6 +31,17 @@ constexpr uint32_t D_COL = 0, A_COL = 64;
 constexpr long long WATCHDOG_CYCLES = 2000000000LL;
 constexpr int S = 4;                                       // input ring depth (loads run S - 1 steps ahead)
 
+#ifdef ASR_LSTM_PROFILE
+// per-phase clock64() accumulators of thread 0 of CTA (0,0,0), dumped behind the header (profiles/prof_lstm_phases_r2.py)
+#define PROF_DECL long long pt0 = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF(i) do { const long long now = clock64(); pacc[i] += now - pt0; pt0 = now; } while (0)
+#define PROF_DUMP(base) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int i = 0; i < 8; ++i) reinterpret_cast<long long*>(flags + 1024)[(base) + i] = pacc[i]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_DUMP(base)
+#endif
+
 struct FwdMaps { CUtensorMap zx, gates, cell, h, hm, hT, hmT, hTu; };
 struct BwdMaps { CUtensorMap gates, cell, dh, dh2, dz, dzT; };
 
@@ -191,8 +202,10 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     }
     uint2* xb = xbuf + (size_t)(dir * G + grp) * 2 * WORDS;
     long long t_pub = clock64();
+    PROF_DECL;
 
     for (int s = 0; s < T; ++s) {
+      PROF(7);
       // zx_t landed in the ring S - 1 steps ago: into registers now, under the flight time of the exchange
       if (!tc::mbar_wait(full + (s % S), (uint32_t)((s / S) & 1), WATCHDOG_CYCLES)) {
         atomicExch(status, 1);
@@ -207,6 +220,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 #pragma unroll
           for (int g = 0; g < 4; ++g) zxv[i][g] = __half2float(zt[((warp * NPT + i) * 4 + g) * 32 + lane]) + bias[g];
       }
+      PROF(0);
       float z[NPT][4];
       if (s > 0) {
         // the first probe leaves ~probe_delay cycles after the publish: a probe that races the peers' stores costs a
@@ -245,6 +259,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
             }
           }
         } while (!ok);
+        PROF(1);
 #pragma unroll
         for (int q = 0; q < QPT; ++q) {
           const int f = q * 32 + lane;
@@ -264,11 +279,13 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
           }
           tc::umma_commit(mma_bar);
         }
+        PROF(2);
         if (!tc::mbar_wait(mma_bar, (uint32_t)((s - 1) & 1), WATCHDOG_CYCLES)) {
           atomicExch(status, 1);
           s_dead = 1;
         }
         tc::tcgen05_fence_after();
+        PROF(3);
         {
           uint32_t r0[NB], r1[NB], r2[NB], r3[NB];
           const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
@@ -289,6 +306,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         for (int i = 0; i < NPT; ++i)
 #pragma unroll
           for (int g = 0; g < 4; ++g) z[i][g] = sZ[(g * NB + warp * NPT + i) * 32 + lane];
+        PROF(4);
       } else {
 #pragma unroll
         for (int i = 0; i < NPT; ++i)
@@ -320,6 +338,7 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         }
       }
       t_pub = clock64();
+      PROF(5);
       // side outputs -> staging buffer s & 1 (free once the TMA stores of step s - 2 have read it)
       const int b = s & 1;
       if (s >= 2 && !tc::mbar_wait(sfree + b, (uint32_t)(((s >> 1) - 1) & 1), WATCHDOG_CYCLES)) {
@@ -376,7 +395,9 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(sfull + b);
+      PROF(6);
     }
+    PROF_DUMP(0);
   }
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -514,8 +535,10 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     }
     uint2* xb = xbuf + (size_t)(dir * G + grp) * 2 * NCTA * SLOT;     // [(dir,grp)][parity][dst][pair][src][unit]
     long long t_pub = clock64();
+    PROF_DECL;
 
     for (int s = 0; s < T; ++s) {
+      PROF(7);
       // inputs of this step (slot s % S) and c of the step the forward pass ran BEFORE it (= the next BPTT step, slot
       // (s + 1) % S): into registers now, under the flight time of the exchange
       if (!tc::mbar_wait(full + (s % S), (uint32_t)((s / S) & 1), WATCHDOG_CYCLES) ||
@@ -546,6 +569,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
           dhx[i] = fmaf(dho2, md1[i], dho * md0[i]);         // dL/d(output): the two masked dX partials of the layer above
         }
       }
+      PROF(0);
       float dh_rec[NPT];
 #pragma unroll
       for (int i = 0; i < NPT; ++i) dh_rec[i] = 0.0f;
@@ -588,6 +612,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
           dh_rec[2 * pp + 1] = mu[2 * pp + 1] * s1;
         }
       }
+      PROF(1);
       float dz[NPT][4];
 #pragma unroll
       for (int i = 0; i < NPT; ++i) {
@@ -609,6 +634,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         }
       }
       tc::fence_proxy_async_smem();
+      PROF(2);
       if (s + 1 < T) {
         tc::named_bar_sync(1, CTHREADS);                   // the whole B operand (all samples) is in shared memory
         if (s_dead) break;
@@ -626,6 +652,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
           s_dead = 1;
         }
         tc::tcgen05_fence_after();
+        PROF(3);
         // send: my warp's rows of block b belong to CTA 4b + warp
         uint32_t rb[NBLK][NB];
         const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
@@ -645,6 +672,7 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         }
         tc::tcgen05_fence_before();
         t_pub = clock64();
+        PROF(4);
       }
       // side outputs (dz for the dW / dU / dX GEMMs) -> staging buffer s & 1, off the chain: after the send
       const int b = s & 1;
@@ -678,7 +706,9 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(sfull + b);                          // dz staged; the input slots of this step were read long ago
+      PROF(5);
     }
+    PROF_DUMP(8);
 #pragma unroll
     for (int g = 0; g < 4; ++g) atomicAdd(a.dbias + (size_t)dir * K4 + g * H + u, db[g]);
   }
