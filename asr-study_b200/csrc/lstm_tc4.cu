@@ -11,8 +11,8 @@
 // The exchange itself (LL ring through L2, per-warp MMA issue, U resident in TMEM) is lstm_tc2.cu's, unchanged — see the
 // measurements in profiles/lstm_phases_r2.md for what was tried on it this round.
 //
-// Grid = (H/32 CTAs, 2 directions, batch groups), cooperative launch, 160 threads: warps 0-3 compute (one TMEM lane
-// quarter = one gate each), warp 4 drives the TMA engine.
+// Grid = (H/32 CTAs, 2 directions, batch groups), cooperative launch; forward: 288 threads (eight compute warps + the DMA
+// warp), BPTT: 160 threads (four compute warps, one TMEM lane quarter each, + the DMA warp).
 // Semantics: core/layers.py:432-469 under Keras-1 Bidirectional, default branch + variational dropout masks.
 #include "common.cuh"
 #include "tc.cuh"
@@ -73,68 +73,80 @@ __device__ __forceinline__ void spin_until(long long t_end) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward
+// forward: EIGHT compute warps (+ the DMA warp).  The per-step work of a CTA that sits on the chain between "the last LL
+// word landed" and "my words are published" — staging the B operand, the accumulator read-out, the gate math, the LL
+// sends — is per-thread work of a handful of dependent instructions; with four warps (one per scheduler) it issues at one
+// instruction per ~5 cycles.  Eight warps halve every thread's share (one sample per thread at NB = 8) and give each
+// scheduler a second warp to hide latencies under: 1.56 -> 1.44 ms per layer at C2 (profiles/lstm_phases_r2.md).  Warp w:
+// TMEM lane quarter q = w & 3 (hardware restriction), sample half hs = w >> 2; eight accumulators, one per issuing warp.
+// (The BPTT kernel below stays at four compute warps: its eight-warp variant measured 3-6 % slower — the reduce-scatter
+// receive then needs a cross-warp combine — and was removed.)
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int CTHREADS8 = 256;
+constexpr int THREADS8 = 288;
+constexpr uint32_t A_COL8 = 128;                           // eight accumulators of NM columns in front of the U slice
+
 template <int H, int NB>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS8, 1)
 fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf, int grp0, int probe_delay,
-           const __grid_constant__ FwdMaps M) {
+            const __grid_constant__ FwdMaps M) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int KC = H / 64;
   constexpr int B_CHUNK = NM * 128;
   constexpr int WORDS = NB * H / 2;                      // LL words per (dir, group, parity)
-  constexpr int NPT = NB / 4;
-  constexpr int TILE = NB * 64;                          // bytes of one [NB x 32] 16-bit tile
-  static_assert(H % 64 == 0 && (NPT == 2 || NPT == 4), "shape");
+  constexpr int NPT = NB / 8;                            // samples per thread
+  constexpr int NH = NB / 2;                             // samples per accumulator read-out half
+  constexpr int TILE = NB * 64;
+  static_assert(H % 128 == 0 && H <= 768 && (NPT == 1 || NPT == 2), "shape");
   const int T = a.T, N = a.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z, G = gridDim.z;
   const int u0 = cta * UPC, n0 = (grp0 + grp) * NB;
 
-  uint8_t* sB = smem;                                    // KC chunks of [NM rows x 128 B], SW128 K-major
+  uint8_t* sB = smem;
   float* sZ = reinterpret_cast<float*>(sB + KC * B_CHUNK);   // [4 gates][NB][32 units]
-  uint8_t* ring = reinterpret_cast<uint8_t*>(sZ + 4 * NB * 32);             // S x [NB][4][32] fp16 (zx_t)
-  uint8_t* stage = ring + S * 4 * TILE;                  // 2 x {gates 4 TILE, cell, h, hm0, hm1, hT, hmT0, hmT1, hTu}
+  uint8_t* ring = reinterpret_cast<uint8_t*>(sZ + 4 * NB * 32);
+  uint8_t* stage = ring + S * 4 * TILE;
   constexpr int STAGE_BYTES = 12 * TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 2 * STAGE_BYTES);
-  uint64_t* mma_bar = bars;                              // 1
-  uint64_t* full = bars + 1;                             // S: zx tile of step s landed
-  uint64_t* sfull = full + S;                            // 2: staging buffer written by the 128 compute threads
-  uint64_t* sfree = sfull + 2;                           // 2: staging buffer read out by the TMA stores
+  uint64_t* mma_bar = bars;
+  uint64_t* full = bars + 1;
+  uint64_t* sfull = full + S;
+  uint64_t* sfree = sfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + 2);
   __shared__ volatile int s_dead;
 
   if (tid == 0) {
-    tc::mbar_init(mma_bar, 4);
+    tc::mbar_init(mma_bar, 8);
     for (int k = 0; k < S; ++k) tc::mbar_init(full + k, 1);
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(sfull + b, CTHREADS); tc::mbar_init(sfree + b, 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(sfull + b, CTHREADS8); tc::mbar_init(sfree + b, 1); }
     tc::fence_mbar_init();
     s_dead = 0;
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < KC * B_CHUNK / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < KC * B_CHUNK / 16; i += THREADS8) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   if (*tmem_slot != 0u) { if (tid == 0) atomicExch(flags + STATUS_IDX, 2); }
-  constexpr uint32_t tmem = 0u;                          // whole TMEM allocated -> base column 0 (see lstm_tc2.cu)
+  constexpr uint32_t tmem = 0u;
   int* status = flags + STATUS_IDX;
-  const int row_of_step_mul = N;
+  const int q = warp & 3, hs = (warp >> 2) & 1;
 
-  if (warp < 4) {
-    // one-time: U^T slice -> TMEM (lane r = g*32 + j holds row g*H + u0 + j, two fp16 K elements per column)
+  if (warp < 8) {
+    // one-time: U^T slice -> TMEM; warp (q, hs) writes column half hs of lane quarter q
     const uint4* urow = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.U16) +
-                                                       ((size_t)dir * 4 * H + (size_t)warp * H + u0 + lane) * H);
+                                                       ((size_t)dir * 4 * H + (size_t)q * H + u0 + lane) * H);
 #pragma unroll 1
-    for (int c = 0; c < H / 2; c += 32) {
+    for (int c = hs * (H / 4); c < (hs + 1) * (H / 4); c += 32) {
       uint32_t r[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint4 v = __ldg(urow + c / 4 + q);
-        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+      for (int k = 0; k < 8; ++k) {
+        const uint4 v = __ldg(urow + c / 4 + k);
+        r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
       }
-      tc::tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + A_COL + c, r);
+      tc::tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + A_COL8 + c, r);
     }
     tc::tmem_st_wait();
   }
@@ -142,14 +154,13 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   __syncthreads();
   tc::tcgen05_fence_after();
 
-  if (warp == 4) {
-    // ------------------------------------------------ DMA warp: one thread drives the TMA engine
+  if (warp == 8) {
     if (lane == 0) {
       tc::tma_prefetch_desc(&M.zx);
       auto load = [&](int k) {
         const int slot = k % S, tk = dir ? (T - 1 - k) : k;
         tc::mbar_expect_tx(full + slot, 4 * TILE);
-        tc::tma_load_4d(ring + slot * 4 * TILE, &M.zx, full + slot, u0, 0, dir, tk * row_of_step_mul + n0);
+        tc::tma_load_4d(ring + slot * 4 * TILE, &M.zx, full + slot, u0, 0, dir, tk * N + n0);
       };
       for (int k = 0; k < S && k < T; ++k) load(k);
       for (int s = 0; s < T; ++s) {
@@ -178,14 +189,13 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         }
         if (a.training && a.hT16u) tc::tma_store_2d(&M.hTu, st + 11 * TILE, row0, col0);
         tc::bulk_commit();
-        if (s + S < T) load(s + S);                        // every compute thread has read slot s % S (it arrived on sfull after)
+        if (s + S < T) load(s + S);
         tc::bulk_wait_read<0>();
         tc::mbar_arrive(sfree + b);
       }
       tc::bulk_wait<0>();
     }
   } else {
-    // ------------------------------------------------ compute warps
     const uint32_t idesc = tc::umma_idesc_f16(128, NM, 0);
     const uint32_t sB_addr = tc::smem_u32(sB);
     const int u = u0 + lane;
@@ -195,10 +205,11 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
     float c_state[NPT], mu[NPT], mn0[NPT], mn1[NPT];
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
+      const int n = warp * NPT + i;
       c_state[i] = 0.0f;
-      mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + warp * NPT + i) * H + u] : 1.0f;
-      mn0[i] = a.mask_next ? a.mask_next[((size_t)0 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
-      mn1[i] = a.mask_next ? a.mask_next[((size_t)1 * N + n0 + warp * NPT + i) * 2 * H + dir * H + u] : 1.0f;
+      mu[i] = a.mask_u ? a.mask_u[((size_t)dir * N + n0 + n) * H + u] : 1.0f;
+      mn0[i] = a.mask_next ? a.mask_next[((size_t)0 * N + n0 + n) * 2 * H + dir * H + u] : 1.0f;
+      mn1[i] = a.mask_next ? a.mask_next[((size_t)1 * N + n0 + n) * 2 * H + dir * H + u] : 1.0f;
     }
     uint2* xb = xbuf + (size_t)(dir * G + grp) * 2 * WORDS;
     long long t_pub = clock64();
@@ -206,7 +217,6 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 
     for (int s = 0; s < T; ++s) {
       PROF(7);
-      // zx_t landed in the ring S - 1 steps ago: into registers now, under the flight time of the exchange
       if (!tc::mbar_wait(full + (s % S), (uint32_t)((s / S) & 1), WATCHDOG_CYCLES)) {
         atomicExch(status, 1);
         s_dead = 1;
@@ -223,31 +233,30 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       PROF(0);
       float z[NPT][4];
       if (s > 0) {
-        // the first probe leaves ~probe_delay cycles after the publish: a probe that races the peers' stores costs a
-        // second full L2 round trip (what the deferred side stores of lstm_tc2.cu bought as a by-product)
         if (probe_delay > 0) spin_until(t_pub + probe_delay);
+        // warp w polls (and stages) the K range [H/8 * w, H/8 * (w + 1)) of all NB samples
         const uint4* src = reinterpret_cast<const uint4*>(xb + (size_t)((s - 1) & 1) * WORDS);
         const uint32_t tag = (uint32_t)s;
-        constexpr int V4W = H / 16;
+        constexpr int V4W = H / 32;                        // 16-byte accesses (4 K columns) per (sample, warp K eighth)
         constexpr int QPT = NB * V4W / 32;
         static_assert((NB * V4W) % 32 == 0, "per-warp poll set must fill whole warp accesses");
         int vidx[QPT];
 #pragma unroll
-        for (int q = 0; q < QPT; ++q) {
-          const int f = q * 32 + lane;
-          vidx[q] = (f / V4W) * (H / 4) + warp * V4W + (f % V4W);
+        for (int k = 0; k < QPT; ++k) {
+          const int f = k * 32 + lane;
+          vidx[k] = (f / V4W) * (H / 4) + warp * V4W + (f % V4W);
         }
         uint4 w[QPT];
 #pragma unroll
-        for (int q = 0; q < QPT; ++q) w[q] = ld_volatile_v4(src + vidx[q]);
+        for (int k = 0; k < QPT; ++k) w[k] = ld_volatile_v4(src + vidx[k]);
         bool ok;
         long long t0 = 0;
         do {
           ok = true;
 #pragma unroll
-          for (int q = 0; q < QPT; ++q)
-            if (w[q].y != tag || w[q].w != tag) {
-              w[q] = ld_volatile_v4(src + vidx[q]);
+          for (int k = 0; k < QPT; ++k)
+            if (w[k].y != tag || w[k].w != tag) {
+              w[k] = ld_volatile_v4(src + vidx[k]);
               ok = false;
             }
           if (!ok) {
@@ -261,21 +270,21 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         } while (!ok);
         PROF(1);
 #pragma unroll
-        for (int q = 0; q < QPT; ++q) {
-          const int f = q * 32 + lane;
-          const int n = f / V4W, k = 4 * (warp * V4W + (f % V4W));
-          *reinterpret_cast<uint2*>(sB + (k >> 6) * B_CHUNK + tc::sw128_offset(n, k & 63)) = make_uint2(w[q].x, w[q].z);
+        for (int k = 0; k < QPT; ++k) {
+          const int f = k * 32 + lane;
+          const int n = f / V4W, kk = 4 * (warp * V4W + (f % V4W));
+          *reinterpret_cast<uint2*>(sB + (kk >> 6) * B_CHUNK + tc::sw128_offset(n, kk & 63)) = make_uint2(w[k].x, w[k].z);
         }
         tc::fence_proxy_async_smem();
         __syncwarp();
         if (tc::elect_one_sync()) {
           tc::tcgen05_fence_after();
-          constexpr int KBW = H / 16 / 4;
+          constexpr int KBW = H / 16 / 8;                    // MMAs (K = 16 each) per warp
 #pragma unroll
           for (int j = 0; j < KBW; ++j) {
             const int kb = warp * KBW + j;
             const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-            tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL + kb * 8, bd, idesc, j > 0);
+            tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL8 + kb * 8, bd, idesc, j > 0);
           }
           tc::umma_commit(mma_bar);
         }
@@ -287,20 +296,21 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
         tc::tcgen05_fence_after();
         PROF(3);
         {
-          uint32_t r0[NB], r1[NB], r2[NB], r3[NB];
-          const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
-          tc::tmem_ldn(tq, r0);
-          tc::tmem_ldn(tq + NM, r1);
-          tc::tmem_ldn(tq + 2 * NM, r2);
-          tc::tmem_ldn(tq + 3 * NM, r3);
+          // lane quarter q of all eight accumulators, sample half hs
+          uint32_t r[8][NH];
+          const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + D_COL + hs * NH;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) tc::tmem_ldn(tq + k * NM, r[k]);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int n = 0; n < NB; ++n)
-            sZ[(warp * NB + n) * 32 + lane] = (__uint_as_float(r0[n]) + __uint_as_float(r1[n])) +
-                                              (__uint_as_float(r2[n]) + __uint_as_float(r3[n]));
+          for (int n = 0; n < NH; ++n) {
+            const float v = ((__uint_as_float(r[0][n]) + __uint_as_float(r[1][n])) + (__uint_as_float(r[2][n]) + __uint_as_float(r[3][n]))) +
+                            ((__uint_as_float(r[4][n]) + __uint_as_float(r[5][n])) + (__uint_as_float(r[6][n]) + __uint_as_float(r[7][n])));
+            sZ[(q * NB + hs * NH + n) * 32 + lane] = v;
+          }
         }
         tc::tcgen05_fence_before();
-        tc::named_bar_sync(1, CTHREADS);
+        tc::named_bar_sync(1, CTHREADS8);
         if (s_dead) break;
 #pragma unroll
         for (int i = 0; i < NPT; ++i)
@@ -339,7 +349,6 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
       t_pub = clock64();
       PROF(5);
-      // side outputs -> staging buffer s & 1 (free once the TMA stores of step s - 2 have read it)
       const int b = s & 1;
       if (s >= 2 && !tc::mbar_wait(sfree + b, (uint32_t)(((s >> 1) - 1) & 1), WATCHDOG_CYCLES)) {
         atomicExch(status, 1);
@@ -368,18 +377,12 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
           hm1[n * 32 + lane] = __float2half_rn(hv[i] * mn1[i]);
         }
       }
-      // transposed bf16 tiles [32 units][NB samples]: the thread's NPT samples are contiguous
       auto storeT = [&](uint8_t* tile, const float (&m)[NPT]) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(tile) + lane * NB + warp * NPT;
-        const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0] * m[0], hv[1] * m[1]);
-        if constexpr (NPT == 4) {
-          const __nv_bfloat162 p1 = __floats2bfloat162_rn(hv[2] * m[2], hv[3] * m[3]);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&p0);
-          pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-          *reinterpret_cast<uint2*>(dst) = pk;
+        if constexpr (NPT == 2) {
+          *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(hv[0] * m[0], hv[1] * m[1]);
         } else {
-          *reinterpret_cast<__nv_bfloat162*>(dst) = p0;
+          *dst = __float2bfloat16_rn(hv[0] * m[0]);
         }
       };
       if (a.training && a.hT16) storeT(st + 8 * TILE, mu);
@@ -839,12 +842,12 @@ static int32_t launch_fwd(const asr_lstm_fwd_args* a, cudaStream_t st) {
   asr_lstm_fwd_args args = *a;
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
-  int delay = probe_delay_of(a->opts, 300);
+  int delay = probe_delay_of(a->opts, 0);
   for (int grp0 = 0; grp0 < Gall; grp0 += gm) {
     const int G = Gall - grp0 < gm ? Gall - grp0 : gm;
     ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + fwd_ring_bytes(H, NB, G), st));
     void* kargs[] = {&args, &flags, &xbuf, &grp0, &delay, &M};
-    ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H, NB>, dim3(H / UPC, 2, G), dim3(THREADS), kargs, smem, st));
+    ASR_CUDA(cudaLaunchCooperativeKernel((void*)fwd_kernel<H, NB>, dim3(H / UPC, 2, G), dim3(THREADS8), kargs, smem, st));
     asr::count_launch();
   }
   return ASR_OK;
@@ -873,7 +876,7 @@ static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
   asr_lstm_bwd_args args = *a;
   int* flags = a->flags;
   uint2* xbuf = reinterpret_cast<uint2*>(reinterpret_cast<char*>(a->flags) + HEADER_BYTES);
-  int delay = probe_delay_of(a->opts, 300);
+  int delay = probe_delay_of(a->opts, 0);
   for (int grp0 = 0; grp0 < Gall; grp0 += gm) {
     const int G = Gall - grp0 < gm ? Gall - grp0 : gm;
     ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + bwd_ring_bytes(H, NB, G), st));

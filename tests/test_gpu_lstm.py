@@ -196,7 +196,7 @@ def test_tensor_core_engine_T999_drift():
     assert norm_err(h, ref) < 1e-3, norm_err(h, ref)
 
 
-def _fp16_storage_fwd_bwd(p, x_ntd, dout_ntd, with_masks=False, seed=0):
+def _fp16_storage_fwd_bwd(p, x_ntd, dout_ntd, with_masks=False, seed=0, opts=0):
     """The 16-bit-storage / TMA engine (csrc/lstm_tc4.cu) through the C ABI: zx16 in, gates16 / cell16 saved, every side
     output a TMA tile store; optional variational-dropout masks with the fused masked copies."""
     from asr_study_b200._lib import LstmBwdArgs, LstmFwdArgs, lib, ptr, cur_stream
@@ -235,7 +235,7 @@ def _fp16_storage_fwd_bwd(p, x_ntd, dout_ntd, with_masks=False, seed=0):
                   hT16u=ptr(f["hT16u"]).value)
     a = LstmFwdArgs(T=T, N=N, H=H, training=1, zx16=ptr(zx16).value, bias=ptr(bias).value, U=ptr(U).value,
                     U16=ptr(UT16).value, h16=ptr(f["h16"]).value, hT16=ptr(f["hT16"]).value,
-                    gates16=ptr(f["gates16"]).value, cell16=ptr(f["cell16"]).value, flags=ptr(flags).value, **kw)
+                    gates16=ptr(f["gates16"]).value, cell16=ptr(f["cell16"]).value, flags=ptr(flags).value, opts=opts, **kw)
     lib.asr_lstm_forward(C.byref(a), cur_stream())
     torch.cuda.synchronize()
     assert int(flags[64]) == 0, "persistent-kernel watchdog fired"
@@ -246,7 +246,7 @@ def _fp16_storage_fwd_bwd(p, x_ntd, dout_ntd, with_masks=False, seed=0):
     U16 = U.to(torch.bfloat16).contiguous()
     ba = LstmBwdArgs(T=T, N=N, H=H, dh=ptr(dh).value, gates16=ptr(f["gates16"]).value, cell16=ptr(f["cell16"]).value,
                      U=ptr(U).value, U16=ptr(U16).value, dz16=ptr(b["dz16"]).value, dzT16=ptr(b["dzT16"]).value,
-                     dbias=ptr(b["dbias"]).value, flags=ptr(flags).value, mask_u=kw.get("mask_u"))
+                     dbias=ptr(b["dbias"]).value, flags=ptr(flags).value, mask_u=kw.get("mask_u"), opts=opts)
     lib.asr_lstm_backward(C.byref(ba), cur_stream())
     torch.cuda.synchronize()
     assert int(flags[64]) == 0, "persistent-kernel watchdog fired"
