@@ -52,6 +52,11 @@ LSTM_SHARED_SM, LSTM_PIN_FP32, LSTM_GROUP16 = 1, 2, 4
 GEMM_BACKGROUND, GEMM_TILE128 = 1, 2
 
 
+class ConvGeom(C.Structure):
+    _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("F", C.c_int32), ("C", C.c_int32), ("kt", C.c_int32), ("kf", C.c_int32),
+                ("st", C.c_int32), ("sf", C.c_int32), ("pt", C.c_int32), ("pf", C.c_int32)]
+
+
 class LstmVariant(C.Structure):
     _fields_ = [("mi_alpha", C.c_void_p), ("mi_beta1", C.c_void_p), ("mi_beta2", C.c_void_p),
                 ("ln_gain_uh", C.c_void_p), ("ln_bias_uh", C.c_void_p), ("ln_gain_wx", C.c_void_p),
@@ -111,6 +116,11 @@ SIGNATURES = {
     "asr_add_gaussian_noise": (_I32, [_P, _I64, _I32, _I64, _F, C.c_uint64, C.c_uint64, _P]),
     "asr_add_mask": (_I32, [_P, _P, _P, _I64, _P, _I64, _I32, _P]),
     "asr_mask_combine": (_I32, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),
+    "asr_conv_out_shape": (_I32, [C.POINTER(ConvGeom), _P, _P, _P, _P]),
+    "asr_conv_im2col": (_I32, [_P, _I32, C.POINTER(ConvGeom), _P, _I64, _P, _I64, _P]),
+    "asr_conv_col2im": (_I32, [_P, _I64, C.POINTER(ConvGeom), _P, _P]),
+    "asr_clipped_relu": (_I32, [_P, _I64, _F, _P, _P, _P]),
+    "asr_clipped_relu_backward": (_I32, [_P, _P, _I32, _I64, _I32, _F, _P, _P, _P, _P]),
 }
 
 

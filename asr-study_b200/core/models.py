@@ -216,12 +216,13 @@ class CTCModel(object):
         else:
             kw.update(momentum=o.momentum)
         loss = self.engine.train_step(xt, lens, flat, off, mx, global_batch=gb, allreduce=self.allreduce, **kw)
-        return self._stats(loss, self.engine.last_logits, lens, flat, off, mx, N)
+        return self._stats(loss, self.engine.last_logits, self.engine.out_lengths(lens), flat, off, mx, N)
 
     def test_on_batch(self, x, y=None):
         feats, labels, x_len = x[0], x[1], x[2]
         xt, lens, (flat, off, mx), N = self._device_batch(feats, x_len, labels, False)
         logits = self.engine.forward(xt, training=False)
+        lens = self.engine.out_lengths(lens)
         loss, _ = self.engine.ctc(logits, lens, flat, off, mx, want_grad=False)
         return [float(v) for v in self._stats(loss, logits, lens, flat, off, mx, N).tolist()]
 
@@ -230,7 +231,7 @@ class CTCModel(object):
         feats, x_len = x[0], x[1]
         xt, lens, _, N = self._device_batch(feats, x_len, None, False)
         logits = self.engine.forward(xt, training=False)
-        return self._decode(logits, lens)[:N].cpu().numpy()
+        return self._decode(logits, self.engine.out_lengths(lens))[:N].cpu().numpy()
 
     predict_on_batch = predict
 
@@ -323,7 +324,7 @@ class CTCModel(object):
                 if done_ev[p] is not None:                 # the search two groups back no longer reads this buffer pair
                     main.wait_event(done_ev[p])
                 shapes = [np.asarray(x[0]).shape for x in batches]
-                Tmax = max(int(sh[1]) for sh in shapes)
+                Tmax = max(eng.out_frames(int(sh[1])) for sh in shapes)
                 Ntot = sum((int(sh[0]) + _PAD - 1) // _PAD * _PAD for sh in shapes)
                 big = eng._buf("eval_logits%d" % p, (Tmax, Ntot, C), torch.float32)
                 big_len = eng._buf("eval_len%d" % p, (Ntot,), torch.int32)
@@ -332,6 +333,7 @@ class CTCModel(object):
                     # staged one at a time: batches of one shape share their pinned / device staging buffers
                     xt, lens, (flat, off, mx), N = self._device_batch(x[0], x[2], x[1], False)
                     logits = eng.forward(xt, training=False)
+                    lens = eng.out_lengths(lens)
                     loss, _ = eng.ctc(logits, lens, flat, off, mx, want_grad=False)
                     losses.append(loss[:N].clone())
                     T, Np = int(xt.shape[0]), int(xt.shape[1])
@@ -534,6 +536,18 @@ def eyben(num_features=39, num_hiddens=[78, 120, 27], num_classes=28, **kw):
             o = Bidirectional(LSTM(n, return_sequences=True, consume_less="gpu"))(o)
     o = TimeDistributed(Dense(num_classes))(o)
     return ctc_model(x, o, name="eyben", **kw)
+
+
+def deep_speech2(num_features=40, num_classes=28, num_hiddens=800, num_layers=5, dropout=0.2, weight_decay=1e-4,
+                 conv_front=((32, 11, 41, 2, 2), (32, 11, 21, 1, 2)), conv_clip=20.0, **kw):
+    """BASELINE configs[3]: DeepSpeech2-style 2 x Conv (32 channels, 41 x 11 and 21 x 11 frequency x time kernels,
+    strides (2, 2) and (2, 1), clipped ReLU at 20; batch normalisation left out) in front of num_layers x BiLSTM and the
+    Dense / CTC head of brsmv1.  NOT in the reference (README.md:118 lists Deep Speech 2 as future work): the conv
+    semantics are those of include/asr_b200.h and oracle/conv.py."""
+    spec = ModelSpec(int(num_features), int(num_hiddens), int(num_layers), int(num_classes), float(weight_decay),
+                     "deep_speech2", float(dropout), conv_front=tuple(tuple(int(v) for v in l) for l in conv_front),
+                     conv_clip=float(conv_clip))
+    return CTCModel(spec, **kw)
 
 
 def maas(*a, **k):

@@ -40,6 +40,7 @@ class DatasetIterator(object):
             seed = 1234                                       # the ranks must draw the same permutation
         self._rng = np.random.RandomState(None if seed is None else int(seed))
         self._order, self._pos = None, 0
+        self._gpu = None
 
     @property
     def len(self):
@@ -79,13 +80,36 @@ class DatasetIterator(object):
             inputs = [load_audio(i, p.fs) if isinstance(i, str) else i for i in inputs]
         if p is not None and hasattr(p, "batch") and str(p) != "raw":
             import torch
-            clips = [np.ascontiguousarray(np.asarray(c, dtype=np.float32).reshape(-1)) for c in inputs]
+            clips = [np.asarray(c, dtype=np.float32).reshape(-1) for c in inputs]
+            lens_s = [len(c) for c in clips]
             off = np.zeros(len(clips) + 1, np.int64)
-            off[1:] = np.cumsum([len(c) for c in clips])
+            off[1:] = np.cumsum(lens_s)
             dev = torch.device("cuda", torch.cuda.current_device())
-            feats, lens = p.batch(torch.from_numpy(np.concatenate(clips)).to(dev), torch.from_numpy(off).to(dev),
-                                  time_major=False)
-            return feats.cpu().numpy(), lens.cpu().numpy().astype(np.int64)
+            # the generator thread works on its OWN stream with pinned staging buffers: its copies and the K1 launch then
+            # overlap the training step on the model's streams instead of queueing in front of it on the default stream
+            st = self._gpu
+            if st is None or st["dev"] != dev:
+                st = self._gpu = dict(dev=dev, stream=torch.cuda.Stream(device=dev), pcm=None, out=None)
+            total = int(off[-1])
+            if st["pcm"] is None or st["pcm"].numel() < total:
+                st["pcm"] = torch.empty(total, dtype=torch.float32).pin_memory()
+            hp = st["pcm"][:total]
+            hn = hp.numpy()
+            for c, o in zip(clips, off[:-1]):
+                hn[o:o + len(c)] = c
+            with torch.cuda.stream(st["stream"]):
+                pcm_d = hp.to(dev, non_blocking=True)
+                off_d = torch.from_numpy(off).to(dev, non_blocking=True)
+                t_max = max(p.num_frames(n) for n in lens_s)
+                feats, lens = p.batch(pcm_d, off_d, t_max=t_max, time_major=False)
+                need = feats.numel()
+                if st["out"] is None or st["out"].numel() < need:
+                    st["out"] = torch.empty(need, dtype=torch.float32).pin_memory()
+                ho = st["out"][:need].view(feats.shape)
+                ho.copy_(feats, non_blocking=True)
+                lens_h = lens.to("cpu", non_blocking=False)
+            st["stream"].synchronize()
+            return ho.numpy().copy(), lens_h.numpy().astype(np.int64)
         if p is not None:
             inputs = [p(i) for i in inputs]
         lens = np.asarray([np.asarray(i).shape[0] for i in inputs])

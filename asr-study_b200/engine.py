@@ -18,8 +18,8 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from ._lib import (GEMM_BACKGROUND, GEMM_TILE128, LSTM_SHARED_SM, LstmBwdArgs, LstmFwdArgs, LstmVariant, LstmVariantGrads,
-                   cur_stream, lib, ptr)
+from ._lib import (GEMM_BACKGROUND, GEMM_TILE128, LSTM_SHARED_SM, ConvGeom, LstmBwdArgs, LstmFwdArgs, LstmVariant,
+                   LstmVariantGrads, cur_stream, lib, ptr)
 
 F16, BF16 = 0, 1
 F16_LO = 16          # fp16(v - fp16(v)): the low half of a split-precision operand (csrc/utils.cu)
@@ -82,6 +82,29 @@ class ModelSpec:
     layer_hiddens: tuple | None = None   # overrides num_hiddens / num_layers when set
     input_dense: int | None = None       # TimeDistributed(Dense(n)) in front of the first BiLSTM (no residual merges)
 
+    # convolutional front end of BASELINE configs[3] (DeepSpeech2-style; NOT in the reference): layers of
+    # (C_out, kt, kf, stride_t, stride_f), "same"-style zero padding (k - 1) // 2, bias, clipped ReLU at conv_clip
+    conv_front: tuple | None = None
+    conv_clip: float = 20.0
+
+    def conv_shapes(self, T=None):
+        """per conv layer: (C_in, F_in, C_out, F_out, K) and, when T is given, the output frame counts."""
+        out, C, F = [], 1, self.num_features
+        for (co, kt, kf, st, sf) in self.conv_front or ():
+            Fo = (F + 2 * ((kf - 1) // 2) - kf) // sf + 1
+            To = None if T is None else (T + 2 * ((kt - 1) // 2) - kt) // st + 1
+            out.append(dict(C_in=C, F_in=F, C_out=co, F_out=Fo, K=kt * kf * C, T_in=T, T_out=To))
+            C, F, T = co, Fo, To
+        return out
+
+    @property
+    def lstm_in(self) -> int:
+        """feature width the first BiLSTM (or its input projection) sees"""
+        if self.conv_front:
+            last = self.conv_shapes()[-1]
+            return last["F_out"] * last["C_out"]
+        return self.num_features
+
     @property
     def hs(self):
         return tuple(self.layer_hiddens) if self.layer_hiddens else (self.num_hiddens,) * self.num_layers
@@ -97,6 +120,9 @@ class ModelSpec:
     def general(self) -> bool:
         """switches only the general-cell path implements (layer norm needs whole-row statistics every step; the
         residual / projection / heterogeneous stacks use its per-layer operand plumbing)."""
+        if self.conv_front and (self.layer_norm is not None or self.residual is not None or self.input_dropout or
+                                self.input_dense or len(set(self.hs)) > 1 or self.zoneout or self.mi is not None):
+            raise NotImplementedError("the convolutional front end is built in front of the default BiLSTM stack only")
         return bool(self.layer_norm is not None or self.residual is not None or self.input_dropout or self.input_dense
                     or len(set(self.hs)) > 1)
 
@@ -123,7 +149,9 @@ class ParamBucket:
         self.logical_h = logical_h if (logical_h and logical_h != spec.num_hiddens) else None
         C = spec.num_classes
         shapes = []
-        D = spec.num_features
+        for i, cs in enumerate(spec.conv_shapes()):          # conv{i}.W [C_out, (kt, kf, c_in)], conv{i}.b [C_out]
+            shapes += [(f"conv{i}.W", (cs["C_out"], cs["K"])), (f"conv{i}.b", (cs["C_out"],))]
+        D = spec.lstm_in
         if spec.proj_width:
             shapes += [("proj.W", (D, spec.proj_width)), ("proj.b", (spec.proj_width,))]
             D = spec.proj_width
@@ -151,7 +179,7 @@ class ParamBucket:
         self.v = torch.zeros_like(self.flat)
         self.decay = torch.zeros(off, dtype=torch.uint8, device=device)
         for k in self.shapes:
-            if k.endswith((".Wf", ".Wb", ".Uf", ".Ub")) or k in ("dense.W", "proj.W"):
+            if k.endswith((".Wf", ".Wb", ".Uf", ".Ub")) or k in ("dense.W", "proj.W") or (k.startswith("conv") and k.endswith(".W")):
                 self._view(self.decay, k).fill_(1)
 
     def _view(self, flat, k):
@@ -278,7 +306,7 @@ class AcousticEngine:
         packed views W2 [2,N,D] / U2 [2,N,H] the kernels take.  One asr_dropout_mask launch fills all of them."""
         sp, p = self.spec, float(self.spec.dropout)
         hs = sp.hs
-        widths = [((sp.proj_width or sp.num_features) if l == 0 else 2 * hs[l - 1]) for l in range(len(hs))]
+        widths = [((sp.proj_width or sp.lstm_in) if l == 0 else 2 * hs[l - 1]) for l in range(len(hs))]
         total = sum(2 * N * (D + H) for D, H in zip(widths, hs))
         flat = self._buf("dropout_masks", (total,), torch.float32)
         lib.asr_dropout_mask(ptr(flat), total, p, self._mask_seed, self._mask_offset, cur_stream())
@@ -316,7 +344,12 @@ class AcousticEngine:
             q = u if u.shape == tuple(shape) else v
             return (1.1 * q.reshape(shape)).astype(np.float32)
 
-        D = spec.num_features
+        for i, cs in enumerate(spec.conv_shapes()):
+            fan_in, fan_out = cs["K"], cs["K"] // cs["C_in"] * cs["C_out"]
+            lim = np.sqrt(6.0 / (fan_in + fan_out))
+            out[f"conv{i}.W"] = rng.uniform(-lim, lim, size=(cs["C_out"], cs["K"])).astype(np.float32)
+            out[f"conv{i}.b"] = np.zeros(cs["C_out"], np.float32)
+        D = spec.lstm_in
         if spec.proj_width:
             out["proj.W"] = glorot((D, spec.proj_width))
             out["proj.b"] = np.zeros(spec.proj_width, np.float32)
@@ -357,7 +390,7 @@ class AcousticEngine:
         H, L, Cc = sp.hs[0], len(sp.hs), sp.num_classes
         R = T * N
         w = {}
-        D0 = _pad8(sp.num_features)
+        D0 = _pad8(sp.lstm_in)
         sdt = torch.float16 if self._fp16 else torch.float32       # zx / gates / cell storage (csrc/lstm_tc4.cu)
         w["x16"] = self._buf("x16", (R, D0), torch.float16, zero=True)
         w["zx"] = self._buf("zx", (R, 8 * H), sdt)
@@ -365,7 +398,7 @@ class AcousticEngine:
             w[f"h16.{l}"] = self._buf(f"h16.{l}", (R, 2 * H), torch.float16)
         w["logits"] = self._buf("logits", (T, N, Cc), torch.float32)
         if training:
-            w["xT16"] = self._buf("xT16", (sp.num_features, R), torch.bfloat16)
+            w["xT16"] = self._buf("xT16", (sp.lstm_in, R), torch.bfloat16)
             for l in range(L):
                 w[f"hT16.{l}"] = self._buf(f"hT16.{l}", (2 * H, R), torch.bfloat16)
                 w[f"gates.{l}"] = self._buf(f"gates.{l}", (R, 8 * H), sdt)
@@ -390,7 +423,7 @@ class AcousticEngine:
         sp, P = self.spec, self.params
         Cc = sp.num_classes
         st = cur_stream()
-        D = sp.proj_width or sp.num_features                        # width the first BiLSTM sees
+        D = sp.proj_width or sp.lstm_in                             # width the first BiLSTM sees
         for l, H in enumerate(sp.hs):
             Dp = _pad8(D)
             fwd_ops = not (skip_first and l == 0)
@@ -411,7 +444,7 @@ class AcousticEngine:
             if rest and training:
                 ub = self._buf(f"Ub16.{l}", (2, H, 4 * H), torch.bfloat16)             # [2, H, 4H] U, BPTT recurrence
                 lib.asr_cast_rows(ptr(P.p(f"l{l}.Uf")), 4 * H, ptr(ub), 4 * H, 2 * H, 4 * H, BF16, st)
-            if rest and training and (l > 0 or sp.proj_width):
+            if rest and training and (l > 0 or sp.proj_width or sp.conv_front):
                 wc = self._buf(f"Wcat16.{l}", (D, 8 * H), torch.bfloat16)              # [D, 8H]  dX B operand
                 for i, d in enumerate("fb"):
                     lib.asr_cast_rows(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wc[:, i * 4 * H:]), 8 * H, D, 4 * H, BF16, st)
@@ -429,6 +462,60 @@ class AcousticEngine:
         lib.asr_gemm_tn_ex(din, dout, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(Cm), ldc, ptr(bias), float(alpha), acc,
                            self.gemm_flags, cur_stream())
 
+    # ------------------------------------------------- convolutional front end (BASELINE configs[3])
+    def _conv_forward(self, x, training):
+        """x f32 [T, N, F] -> f32 [T', N, F' * C]: per layer im2col (fp16 patch matrix, + its bf16 transpose when
+        training) -> tcgen05 GEMM with the bias -> clipped ReLU.  Rows of every matrix are (t', n, f'), so the last
+        activation IS the time-major input of the first BiLSTM."""
+        sp, P, st = self.spec, self.params, cur_stream()
+        T, N, F = x.shape
+        cur, cur_dt, Cin = x, 2, 1
+        self._conv = []
+        for i, (co, kt, kf, s_t, s_f) in enumerate(sp.conv_front):
+            g = ConvGeom(T=T, N=N, F=F, C=Cin, kt=kt, kf=kf, st=s_t, sf=s_f, pt=(kt - 1) // 2, pf=(kf - 1) // 2)
+            To, Fo, K = (T + 2 * g.pt - kt) // s_t + 1, (F + 2 * g.pf - kf) // s_f + 1, kt * kf * Cin
+            Kp, M = _pad8(K), To * N * Fo
+            patches = self._buf(f"conv{i}.patch", (M, Kp), torch.float16)
+            patchesT = self._buf(f"conv{i}.patchT", (K, M), torch.bfloat16) if training else None
+            lib.asr_conv_im2col(ptr(cur), cur_dt, C.byref(g), ptr(patches), Kp, ptr(patchesT), M, st)
+            w16 = self._buf(f"conv{i}.W16", (co, Kp), torch.float16, zero=True)
+            lib.asr_cast_rows(ptr(P.p(f"conv{i}.W")), K, ptr(w16), Kp, co, K, F16, st)
+            z = self._buf(f"conv{i}.z", (M, co), torch.float32)
+            self._gemm(F16, OUT_F32, M, co, Kp, patches, Kp, w16, Kp, z, co, bias=P.p(f"conv{i}.b"))
+            last = i == len(sp.conv_front) - 1
+            y16 = self._buf(f"conv{i}.y16", (M, co), torch.float16)
+            y32 = self._buf("conv.out32", (M, co), torch.float32) if last else None
+            lib.asr_clipped_relu(ptr(z), M * co, float(sp.conv_clip), ptr(y32), ptr(y16), st)
+            self._conv.append(dict(geom=g, M=M, K=K, Kp=Kp, co=co, patchesT=patchesT, y16=y16))
+            cur, cur_dt, T, F, Cin = y16, 0, To, Fo, co
+        return y32.view(T, N, F * Cin)
+
+    def _conv_backward(self, dx):
+        """dx f32 [T' * N, F' * C] (dL/d input of the first BiLSTM) -> conv{i}.W / conv{i}.b gradients."""
+        import ctypes
+        sp, P, st = self.spec, self.params, cur_stream()
+        g32 = dx
+        for i in range(len(sp.conv_front) - 1, -1, -1):
+            c = self._conv[i]
+            M, K, Kp, co = c["M"], c["K"], c["Kp"], c["co"]
+            g16 = self._buf(f"conv{i}.g16", (M, co), torch.bfloat16)
+            gT16 = self._buf(f"conv{i}.gT16", (co, M), torch.bfloat16)
+            gm = self._buf(f"conv{i}.gm32", (M, co), torch.float32)
+            lib.asr_clipped_relu_backward(ptr(g32), ptr(c["y16"]), 0, M, co, float(sp.conv_clip), ptr(g16), ptr(gT16), ptr(gm), st)
+            lib.asr_colsum(ptr(gm), co, M, co, ptr(P.g(f"conv{i}.b")), st)
+            # dW [C_out, K] = g^T [C_out, M] . patches^T [K, M]^T
+            self._gemm(BF16, OUT_F32, co, K, M, gT16, M, c["patchesT"], M, P.g(f"conv{i}.W"), K)
+            if i > 0:
+                # dPatches [M, Kp] = g [M, C_out] . W^T [Kp, C_out]^T, then the gather-form col2im
+                wt = self._buf(f"conv{i}.Wt16", (Kp, co), torch.bfloat16, zero=True)
+                lib.asr_cast_transpose(ptr(P.p(f"conv{i}.W")), K, ptr(wt), co, co, K, BF16, st)
+                dP = self._buf(f"conv{i}.dpatch", (M, Kp), torch.bfloat16)
+                self._gemm(BF16, OUT_BF16, M, Kp, co, g16, co, wt, co, dP, Kp)
+                gi = c["geom"]
+                dxin = self._buf(f"conv{i}.dx32", (gi.T * gi.N * gi.F, gi.C), torch.float32)
+                lib.asr_conv_col2im(ptr(dP), Kp, ctypes.byref(gi), ptr(dxin), st)
+                g32 = dxin
+
     # ---------------------------------------------------------------- forward
     def forward(self, feats_tm: torch.Tensor, training=False, masks=None, zmasks=None, input_mask=None) -> torch.Tensor:
         """feats_tm: f32 [T, N, F] time-major on device -> logits f32 [T, N, C].
@@ -437,6 +524,44 @@ class AcousticEngine:
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
         assert Fd == sp.num_features and feats_tm.is_cuda and feats_tm.dtype == torch.float32
+        if sp.conv_front:                               # [T, N, F] -> [T', N, F' * C] (utterances stay independent)
+            Np = self._padded_batch(self.out_frames(T), N)
+            if Np != N:
+                fp = self._buf("feats_pad_conv", (T, Np, Fd), torch.float32)
+                fp[:, :N].copy_(feats_tm)
+                fp[:, N:].zero_()
+                feats_tm = fp
+            feats_tm = self._conv_forward(feats_tm.contiguous(), training)
+            out = self._forward_padded(feats_tm, training, masks, zmasks, input_mask, N)
+            self._conv_pad = (N, Np) if Np != N else None
+            return out
+        return self._forward_padded(feats_tm, training, masks, zmasks, input_mask, None)
+
+    def out_frames(self, T):
+        """frames the BiLSTM stack sees for T input frames (the conv front end strides over time)"""
+        for (_, kt, _, st, _) in self.spec.conv_front or ():
+            T = (T + 2 * ((kt - 1) // 2) - kt) // st + 1
+        return T
+
+    def out_lengths(self, in_len):
+        """per-utterance frame counts behind the conv front end (index glue on a handful of integers)"""
+        for (_, kt, _, st, _) in self.spec.conv_front or ():
+            in_len = torch.div(in_len + 2 * ((kt - 1) // 2) - kt, st, rounding_mode="floor") + 1
+        return in_len.clamp_min(0).to(torch.int32) if self.spec.conv_front else in_len
+
+    def _forward_padded(self, feats_tm, training, masks, zmasks, input_mask, n_real):
+        sp, P = self.spec, self.params
+        T, N, Fd = feats_tm.shape
+        if n_real is not None:                          # conv path: the batch is already padded; callers see n_real samples
+            if self.logical_h:
+                masks, zmasks = self._widen_masks(masks, zmasks)
+            self._pad = (n_real, N) if n_real != N else None
+            if masks is not None and n_real != N:
+                masks = {l: {k: torch.cat([v, torch.ones(N - n_real, v.shape[1], dtype=v.dtype, device=v.device)])
+                             for k, v in m.items() if k in ("Wf", "Wb", "Uf", "Ub")} for l, m in masks.items()}
+            logits = self._forward(feats_tm, training, masks, zmasks, input_mask)
+            self.last_logits = logits[:, :n_real].contiguous() if n_real != N else logits
+            return self.last_logits
         if self.logical_h:                              # zero-padded width: widen caller-supplied masks (values irrelevant)
             masks, zmasks = self._widen_masks(masks, zmasks)
         # ragged batches (the last batch of an epoch, predict.py's batch of 1): the tensor-core recurrences work on
@@ -496,6 +621,7 @@ class AcousticEngine:
     def _forward(self, feats_tm, training, masks, zmasks, input_mask):
         sp, P = self.spec, self.params
         T, N, Fd = feats_tm.shape
+        assert Fd == sp.lstm_in
         # the persistent engines cover the reference's shapes; anything else (e.g. H = 800) runs on the general cell
         # (the persistent engines hand 2H-wide fp16 rows straight to the next GEMM: 2H must be a multiple of 8 — 16-byte
         # rows — e.g. graves2006(num_hiddens=50) is not; the general path pads its operand copies instead)
@@ -1000,7 +1126,7 @@ class AcousticEngine:
                             mask_dh=ptr(mask_dh).value if mask_dh is not None else None, **vz)
             lib.asr_lstm_backward(C.byref(a), st)
             dh2, mask_dh = None, None
-            D = sp.num_features if l == 0 else 2 * H
+            D = sp.lstm_in if l == 0 else 2 * H
             xT = w["xT16"] if l == 0 else w[f"hT16.{l - 1}"]
             hT = w[f"hT16.{l}"]
             dzT = w[f"dzT16.{l}"]
@@ -1031,8 +1157,23 @@ class AcousticEngine:
                         P.g(f"l{l}.U{d}").zero_()
                 if allreduce is not None:               # layer l's gradients are complete on this stream: reduce them now
                     lo, hi = self._layer_slice(l)
-                    handles.append(allreduce(P.grad[(0 if l == 0 else lo):hi]))
-            if l > 0 and masks is None:
+                    handles.append(allreduce(P.grad[(0 if (l == 0 and not sp.conv_front) else lo):hi]))
+            if l == 0 and sp.conv_front:
+                # dL/d(conv output) [R, D] = dz . Wcat^T (per direction with the fused dropout masks), then the conv backward
+                dx0 = self._buf("dx0", (R, D), torch.float32)
+                wc = self._views[f"Wcat16.{l}"]
+                if masks is None:
+                    self._gemm(BF16, OUT_F32, R, D, 8 * H, w[f"dz16.{l}"], 8 * H, wc, 8 * H, dx0, D)
+                else:
+                    part = [self._buf(f"dx0part.{i}", (R, D), torch.float32) for i in range(2)]
+                    for i in range(2):
+                        lib.asr_gemm_tn(BF16, OUT_F32, R, D, 4 * H, ptr(w[f"dz16.{l}"][:, i * 4 * H:]), 8 * H,
+                                        ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), D, None, 1.0, 0, st)
+                    mk = masks[l]
+                    lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
+                                         ptr(dx0), R, D, st)
+                self._conv_backward(dx0)
+            elif l > 0 and masks is None:
                 # dX [R, 2H] = dz16 [R, 8H] . Wcat16 [2H, 8H]^T
                 self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w[f"dz16.{l}"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
                            other, 2 * H)
@@ -1053,6 +1194,8 @@ class AcousticEngine:
                     dh, other = other, dh
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self._side)
+        if allreduce is not None and sp.conv_front:     # the conv front end's gradients: the head of the bucket
+            handles.append(allreduce(P.grad[:self._layer_slice(0)[0]]))
         return handles
 
     # -------------------------------------------------------------- optimiser
@@ -1089,6 +1232,7 @@ class AcousticEngine:
             main.wait_stream(caller)
         with torch.cuda.stream(main):
             logits = self.forward(feats_tm, training=True, masks=masks, zmasks=zmasks, input_mask=input_mask)
+            in_len = self.out_lengths(in_len)
             loss, dlogits = self.ctc(logits, in_len, labels_flat, label_off, max_label_len,
                                      grad_scale=1.0 / float(global_batch or N))
             for h in self.backward(dlogits, allreduce=allreduce):

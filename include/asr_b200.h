@@ -367,6 +367,34 @@ int32_t asr_add_gaussian_noise(float* x, int64_t rows, int32_t cols, int64_t ld,
 int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_t cols,
                    float* out, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Convolutional front end of BASELINE configs[3] (DeepSpeech2-style 2 x Conv in front of the BiLSTM stack; NOT in
+ * the reference — README.md:118 lists it as future work — so its semantics are this header's: cross-correlation with
+ * zero padding, bias, clipped ReLU min(max(z, 0), clip)).  Implicit GEMM: these entry points gather / scatter the patch
+ * matrix and apply the activation; the contractions are asr_gemm_tn calls.
+ * Activations are time-major [T, N, F, C]; patch rows are (t', n, f'), patch columns (kt, kf, c), K = kt * kf * C padded
+ * to a multiple of 8.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t T, N, F, C;       /* input frames, utterances, frequency bins, channels */
+  int32_t kt, kf;           /* kernel extent in time / frequency                   */
+  int32_t st, sf;           /* strides                                              */
+  int32_t pt, pf;           /* zero padding on both sides                           */
+} asr_conv_geom;
+
+int32_t asr_conv_out_shape(const asr_conv_geom* geom, int32_t* t_out, int32_t* f_out, int32_t* k, int32_t* k_padded);
+/* x: fp16 (x_dtype 0) or fp32 (2) [T, N, F, C]  ->  patches16 fp16 [T'*N*F', ld] (K padding zeroed) and, optionally,
+ * patchesT16 bf16 [K, ldT] (its transpose, the K-major operand of the weight-gradient GEMM) */
+int32_t asr_conv_im2col(const void* x, int32_t x_dtype, const asr_conv_geom* geom, void* patches16, int64_t ld,
+                        void* patchesT16, int64_t ldT, void* stream);
+/* dpatches16 bf16 [T'*N*F', ld]  ->  dx f32 [T, N, F, C] (gather form: no atomics) */
+int32_t asr_conv_col2im(const void* dpatches16, int64_t ld, const asr_conv_geom* geom, float* dx, void* stream);
+/* y = min(max(z, 0), clip) over n elements -> fp32 and / or fp16 copies */
+int32_t asr_clipped_relu(const float* z, int64_t n, float clip, float* y32, void* y16, void* stream);
+/* g = gout * [0 < y < clip] (y fp16 or fp32 [rows, cols]) -> bf16 [rows, cols], bf16 transposed [cols, rows], fp32 */
+int32_t asr_clipped_relu_backward(const float* gout, const void* y, int32_t y_dtype, int64_t rows, int32_t cols,
+                                  float clip, void* g16, void* gT16, float* g32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

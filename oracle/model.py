@@ -94,6 +94,42 @@ def loss_and_grads(params, x, x_len, labels, weight_decay=0.0, masks=None,
     return total, ctc, {k: np.asarray(v, dtype=dtype) for k, v in grads.items()}, logits
 
 
+def loss_and_grads_conv(params, x, x_len, labels, layers=None, clip=None, weight_decay=0.0, masks=None, dtype=np.float64,
+                        global_batch=None):
+    """BASELINE configs[3]: convolutional front end (oracle/conv.py; NOT in the reference) in front of the BiLSTM stack.
+    x [N, T, F] -> (total, ctc[N], grads incl. conv{i}.W / conv{i}.b, logits [N, T', C], x_len')."""
+    from . import conv as ocv
+    layers = layers or ocv.DS2_FRONT
+    clip = ocv.DS2_CLIP if clip is None else clip
+    y, cache = ocv.front_forward(params, x, layers, clip, dtype)
+    len2 = ocv.front_out_lengths(x_len, layers)
+    lstm_params = {k: v for k, v in params.items() if not k.startswith("conv")}
+    logits, (caches, top) = forward(lstm_params, y, masks, dtype)
+    N, T, C = logits.shape
+    gb = float(global_batch or N)
+    ctc, dlogits = octc.ctc_loss_grad(logits, len2, labels, dtype=dtype)
+    dlogits = (dlogits / gb).astype(dtype)
+    grads = {}
+    D = top.shape[2]
+    grads["dense.W"] = top.reshape(N * T, D).T @ dlogits.reshape(N * T, C)
+    grads["dense.b"] = dlogits.sum(axis=(0, 1))
+    dh = (dlogits.reshape(N * T, C) @ params["dense.W"].T.astype(dtype)).reshape(N, T, D)
+    for l in range(len(caches) - 1, -1, -1):
+        dh, g = olstm.bilstm_backward(dh, caches[l])
+        for k, v in g.items():
+            grads[f"l{l}.{k}"] = v
+    cg, _ = ocv.front_backward(params, dh, cache, layers, clip)
+    grads.update(cg)
+    reg = 0.0
+    if weight_decay:
+        for k in params:
+            if k.endswith((".Wf", ".Uf", ".Wb", ".Ub")) or k == "dense.W" or (k.startswith("conv") and k.endswith(".W")):
+                reg += weight_decay * float(np.sum(np.square(params[k], dtype=np.float64)))
+                grads[k] = grads[k] + 2.0 * weight_decay * params[k]
+    total = float(ctc.astype(np.float64).sum()) / gb + reg
+    return total, ctc, {k: np.asarray(v, dtype=dtype) for k, v in grads.items()}, logits, len2
+
+
 def global_norm(grads):
     return float(np.sqrt(sum(np.sum(np.square(g, dtype=np.float64)) for g in grads.values())))
 
