@@ -89,6 +89,38 @@ class _GeneratorFeed(object):
             self.thread.join(timeout=5.0)
 
 
+class LazyMetrics(object):
+    """[loss, ctc_loss, decoder_loss, decoder_ler] of one batch, as Keras' train_on_batch returns them — a sequence of
+    Python floats — whose device->host read-back is asynchronous: the four values are copied into pinned memory behind the
+    step on the step's own stream, and the host only waits for them when an element is actually read.  A loop that logs
+    the previous batch while the next one trains (what Keras' progress bar amounts to) therefore never drains the GPU."""
+
+    def __init__(self, dev_tensor):
+        self._host = torch.empty(dev_tensor.numel(), dtype=torch.float32).pin_memory()
+        self._host.copy_(dev_tensor, non_blocking=True)
+        self._ev = torch.cuda.Event()
+        self._ev.record()
+        self._vals = None
+
+    def result(self):
+        if self._vals is None:
+            self._ev.synchronize()
+            self._vals = [float(v) for v in self._host.tolist()]
+        return self._vals
+
+    def __len__(self):
+        return int(self._host.numel())
+
+    def __getitem__(self, i):
+        return self.result()[i]
+
+    def __iter__(self):
+        return iter(self.result())
+
+    def __repr__(self):
+        return repr(self.result())
+
+
 def _label_rows(labels):
     if labels is None:
         return None
@@ -203,7 +235,8 @@ class CTCModel(object):
 
     # ---- train / eval / predict ------------------------------------------------------
     def train_on_batch(self, x, y=None):
-        return [float(v) for v in self._train_stats(x).tolist()]
+        """host batch in, the four Keras metrics out (a float sequence, read back lazily: see LazyMetrics)"""
+        return LazyMetrics(self._train_stats(x))
 
     def _train_stats(self, x):
         feats, labels, x_len = x[0], x[1], x[2]

@@ -173,6 +173,7 @@ class ParamBucket:
             off += int(np.prod(s))
             off = (off + 3) // 4 * 4                       # keep every tensor 16-byte aligned
         self.numel = off
+        self.loads = 0
         self.flat = torch.zeros(off, dtype=torch.float32, device=device)
         self.grad = torch.zeros_like(self.flat)
         self.m = torch.zeros_like(self.flat)
@@ -210,6 +211,7 @@ class ParamBucket:
         raise KeyError(k)
 
     def load(self, params: dict, which="flat"):
+        self.loads += 1
         for k, v in params.items():
             v = np.asarray(v, dtype=np.float32)
             if self.logical_h:
@@ -269,6 +271,12 @@ class AcousticEngine:
         self._seed = int(seed)
         self._mask_seed, self._mask_offset = (seed + 17) * 0x9E3779B1 & 0xFFFFFFFFFFFFFFFF, 0
         self._l2 = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._prepared_for = None
+
+    @property
+    def params_version(self):
+        """changes whenever the fp32 masters may have changed (optimiser steps, loads): keys the cached 16-bit operands"""
+        return (self.step_count, self.params.loads)
 
     def set_rank(self, rank: int):
         """data parallel: same parameters on every rank (same init seed), different dropout / zoneout / noise streams."""
@@ -633,7 +641,10 @@ class AcousticEngine:
         H, L, Cc = sp.hs[0], len(sp.hs), sp.num_classes
         R = T * N
         # 16-bit storage of zx / gates / cell + TMA staging: the default tensor-core recurrence where it takes the shape
-        self._fp16 = bool(self.fp16_storage and not sp.elementwise and lib.asr_lstm_fp16_storage(T, N, H, self.lstm_opts))
+        # (not when the recurrences share their SMs with another kernel — the pipelined evaluator's beam search: the
+        # nine-warp TMA kernels lose more to the shared issue slots than the four-warp ones, 5 250 vs 6 395 clips/s at C5)
+        self._fp16 = bool(self.fp16_storage and not sp.elementwise and not self.shared_sm and
+                          lib.asr_lstm_fp16_storage(T, N, H, self.lstm_opts))
         zdt = OUT_F16 if self._fp16 else OUT_F32
         w = self._alloc(T, N, training)
         self._w, self._T, self._N = w, T, N
@@ -650,7 +661,9 @@ class AcousticEngine:
         D0 = _pad8(Fd)
         main = torch.cuda.current_stream()
         prep_ev = None
-        if self.overlap and L > 1:
+        if not training and self._prepared_for == (self.params_version, False):
+            pass                                         # inference on unchanged parameters: the 16-bit operands are in place
+        elif self.overlap and L > 1 and training:
             # operands of the first layer's forward pass here; everything else on the side stream under its recurrence
             self._prep_weights(training, first_only=True)
             self._side.wait_stream(main)                 # the previous step's optimiser update / readers are behind us
@@ -665,6 +678,7 @@ class AcousticEngine:
             self._prep_weights(training)
             if training:
                 lib.asr_cast_transpose(ptr(feats_tm), Fd, ptr(w["xT16"]), R, R, Fd, BF16, st)
+        self._prepared_for = (self.params_version, bool(training))
         lib.asr_cast_rows(ptr(feats_tm), Fd, ptr(w["x16"]), D0, R, Fd, F16, st)
         x16, D = w["x16"], D0
         src, src_dt, src_ld, Dl = feats_tm, 2, Fd, Fd              # layer input before masking
