@@ -351,7 +351,7 @@ def run_ours(args):
                                                          "peak_source": pk["src"] + " bf16_tflops_sustained"}}}
         out = {"metric": METRIC if args.config != "c4" else "utterances/sec (10 s, 40 log-mel, 2xConv + 5xBiLSTM-800, CTC)", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "fp16/bf16 tensor-core operands, fp32 accumulate+state",
+               "scaling": "weak", "vs_baseline": None, "dtype": ("fp16/bf16 tensor-core operands, fp32 saved activations" if args.fp32_storage else "fp16/bf16 tensor-core operands and saved activations") + ", fp32 accumulate / cell state / parameters",
                "data": "synthetic",
                "config": {"workload": ("C4 (BASELINE configs[3]): synthetic 16 kHz 10 s clips, 40 log-mel, DS2-style 2xConv (32 ch, 41x11 s(2,2) + "
                                        "21x11 s(2,1), clipped ReLU 20, no batch norm) -> 320 features x 500 frames, " if args.config == "c4" else "") +
