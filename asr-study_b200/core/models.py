@@ -205,7 +205,7 @@ class CTCModel(object):
         st["lens_h"].numpy()[:N] = np.asarray(x_len).reshape(-1)[:N]
         st["dev"].copy_(st["host"], non_blocking=True)
         st["lens"].copy_(st["lens_h"], non_blocking=True)
-        st.setdefault("ev", torch.cuda.Event()).record()
+        st.setdefault("ev", torch.cuda.Event())
         xt = st["xt"]
         xt[:, :N].copy_(st["dev"].permute(1, 0, 2))          # layout copy on the device; the padding columns stay zero
         if training and self.input_std_noise > 0:           # GaussianNoise(std), core/models.py:67,251 (train phase only)
@@ -213,8 +213,26 @@ class CTCModel(object):
         rows = _label_rows(labels)
         packed = None
         if rows is not None:
-            rows = rows + [np.zeros(0, np.int32)] * (Np - N)
-            packed = pack_labels(rows, self.device)
+            # packed sparse labels through the same pinned staging: a copy out of pageable memory would first wait for
+            # everything queued on the stream (the previous step), i.e. drain the pipeline once per batch
+            sizes = [len(r) for r in rows]
+            total = int(sum(sizes))
+            if st.get("lab_cap", -1) < max(total, 1):
+                cap = max(1024, 2 * total)
+                st.update(lab_cap=cap, lab_h=torch.zeros(cap, dtype=torch.int32).pin_memory(),
+                          lab=torch.zeros(cap, dtype=torch.int32, device=self.device),
+                          off_h=torch.zeros(Np + 1, dtype=torch.int32).pin_memory(),
+                          off=torch.zeros(Np + 1, dtype=torch.int32, device=self.device))
+            if total:
+                st["lab_h"].numpy()[:total] = np.concatenate(rows)
+            oh = st["off_h"].numpy()
+            oh[0] = 0
+            oh[1:N + 1] = np.cumsum(sizes)
+            oh[N + 1:] = total                                 # the padding utterances carry no labels
+            st["lab"].copy_(st["lab_h"], non_blocking=True)
+            st["off"].copy_(st["off_h"], non_blocking=True)
+            packed = (st["lab"][:max(total, 1)], st["off"], int(max(sizes) if sizes else 0))
+        st["ev"].record()                                    # covers every copy out of the pinned buffers above
         return xt, st["lens"], packed, N
 
     def _decode(self, logits, lens, with_len=False):
