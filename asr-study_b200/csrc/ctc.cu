@@ -1,13 +1,13 @@
 // K6 / K7 — CTC loss + gradient and best-path decode for sm_100a.
 //
-// asr_ctc_loss_grad: one CTA per utterance.
-//   phase 0  all warps: per-frame log-sum-exp of the logits (softmax normaliser)
-//   phase 1  warp 0 runs the alpha lattice forward in time, warp 1 runs the beta
-//            lattice backward, concurrently, in the log domain (lane = lattice
-//            state, log-sum-exp of the 3 predecessors), rows parked in an
-//            L2-resident workspace
-//   phase 2  all warps: per frame, reduce alpha+beta per class and write
-//            dloss/dlogits = softmax - occupancy
+// asr_ctc_loss_grad, label lengths <= 63 (2L+1 <= 128 lattice states) — three launches:
+//   ctc_lse_kernel         a warp per frame over all T * N frames: log-sum-exp of the logits (softmax normaliser)
+//   ctc_lattice_mw_kernel  one CTA per utterance: four warps run the alpha lattice forward in time, four the beta
+//                          lattice backward, concurrently, in the log domain (lane = lattice state, log-sum-exp of
+//                          the 3 predecessors, rows renormalised against fp64 offsets), rows parked in an
+//                          L2-resident workspace
+//   ctc_grad_mw_kernel     a warp per frame: reduce alpha+beta per class, write dloss/dlogits = softmax - occupancy
+// longer labels: ctc_loss_grad_kernel<16>, one CTA per utterance running the same three phases in one launch.
 // Replaces tf.nn.ctc_loss (core/ctc_utils.py:68-70): softmax inside, standard
 // merge-repeated topology, zero gradient for t >= seq_len.
 // asr_ctc_greedy replaces tf.nn.ctc_greedy_decoder (core/ctc_utils.py:42).
@@ -33,6 +33,15 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
+// per-utterance workspace, in floats: alpha[T][s_max], beta[T][s_max], lse[T] (f32, padded to an even count), then
+// offA[T], offB[T] and log p(l|x) (f64)
+__host__ __device__ __forceinline__ size_t ws_f32_part(int T, int s_max) {
+  return ((size_t)2 * T * s_max + T + 1) & ~(size_t)1;
+}
+__host__ __device__ __forceinline__ size_t ws_stride(int T, int s_max) {
+  return ws_f32_part(T, s_max) + 4 * (size_t)T + 2;
+}
+
 // NJ = states per lane (S <= 32*NJ)
 template <int NJ>
 __global__ void __launch_bounds__(CTC_THREADS)
@@ -51,8 +60,8 @@ ctc_loss_grad_kernel(const float* __restrict__ logits, int T, int N, int C,
   // per-utterance workspace: alpha[T][s_max], beta[T][s_max], lse[T] (f32) then offA[T], offB[T] (f64).
   // alpha/beta rows are stored RELATIVE to a per-frame offset (row max = 0) that is accumulated in
   // fp64, so fp32 resolution applies to O(1) magnitudes instead of O(T) log-probabilities.
-  const size_t fl_per = ((size_t)2 * T * s_max + T + 1) & ~(size_t)1;
-  float* w_alpha = ws + (size_t)n * (fl_per + 4 * (size_t)T);
+  const size_t fl_per = ws_f32_part(T, s_max);
+  float* w_alpha = ws + (size_t)n * ws_stride(T, s_max);
   float* w_beta = w_alpha + (size_t)T * s_max;
   float* w_lse = w_beta + (size_t)T * s_max;
   double* w_offA = reinterpret_cast<double*>(w_alpha + fl_per);
@@ -337,17 +346,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 __global__ void __launch_bounds__(CTC_THREADS)
-ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, const int* __restrict__ in_len,
-                        const int* __restrict__ labels, const int* __restrict__ label_off, int s_max, int blank,
-                        float grad_scale, float* __restrict__ loss, float* __restrict__ grad, float* __restrict__ ws) {
+ctc_lattice_mw_kernel(const float* __restrict__ logits, int T, int N, int C, const int* __restrict__ in_len,
+                      const int* __restrict__ labels, const int* __restrict__ label_off, int s_max, int blank,
+                      float* __restrict__ loss, float* __restrict__ ws) {
   extern __shared__ float sm[];
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int len = min(max(in_len[n], 0), T);
   const int l0 = label_off[n], L = label_off[n + 1] - l0;
   const int S = 2 * L + 1;
   const float NEG = -CUDART_INF_F;
-  const size_t fl_per = ((size_t)2 * T * s_max + T + 1) & ~(size_t)1;
-  float* w_alpha = ws + (size_t)n * (fl_per + 4 * (size_t)T);
+  const size_t fl_per = ws_f32_part(T, s_max);
+  float* w_alpha = ws + (size_t)n * ws_stride(T, s_max);
   float* w_beta = w_alpha + (size_t)T * s_max;
   float* w_lse = w_beta + (size_t)T * s_max;
   double* w_offA = reinterpret_cast<double*>(w_alpha + fl_per);
@@ -358,25 +367,13 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
   float* rowB = rowA + 2 * 132;                       // [2][132]: states at [0,128), 2 pads at [128,130)
   float* mxA = rowB + 2 * 132;                        // [2][4]
   float* mxB = mxA + 8;                               // [2][4]
-  float* acc = mxB + 8;                               // [CTC_WARPS][C]
   __shared__ double s_logp;
 
   for (int s = tid; s < 132; s += CTC_THREADS) ext[s] = (s < S && (s & 1)) ? labels[l0 + (s >> 1)] : blank;
-  for (int t = warp; t < len; t += CTC_WARPS) {
-    const float* row = logits + ((size_t)t * N + n) * C;
-    float m = NEG;
-    for (int k = lane; k < C; k += 32) m = fmaxf(m, row[k]);
-    m = asr::warp_max(m);
-    float sx = 0.0f;
-    for (int k = lane; k < C; k += 32) sx += expf(row[k] - m);
-    sx = asr::warp_sum(sx);
-    if (lane == 0) w_lse[t] = m + logf(sx);
-  }
   if (tid < 2) { rowA[tid] = NEG; rowA[132 + tid] = NEG; rowB[128 + tid] = NEG; rowB[132 + 128 + tid] = NEG; }
   __syncthreads();
-  if (len == 0) {
-    if (tid == 0) loss[n] = CUDART_INF_F;
-    for (int i = tid; i < T * C; i += CTC_THREADS) grad[((size_t)(i / C) * N + n) * C + (i % C)] = 0.0f;
+  if (len == 0) {                                     // no frames: infinite loss, and the gradient kernel writes zeros
+    if (tid == 0) { loss[n] = CUDART_INF_F; w_offB[T] = -(double)CUDART_INF; }
     return;
   }
 
@@ -475,51 +472,91 @@ ctc_loss_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, c
   }
   __syncthreads();
 
-  const double logp = s_logp;
-  if (tid == 0) loss[n] = (float)(-logp);
-  const bool feasible = logp > -(double)CUDART_INF;
-  float* my = acc + warp * C;
-  for (int t = warp; t < T; t += CTC_WARPS) {
-    float* g = grad + ((size_t)t * N + n) * C;
-    if (t >= len || !feasible) {
-      for (int k = lane; k < C; k += 32) g[k] = 0.0f;
-      continue;
-    }
-    const float* row = logits + ((size_t)t * N + n) * C;
-    const float z = w_lse[t];
-    const float kf = (float)(w_offA[t] + w_offB[t] - logp);
-    for (int k = lane; k < C; k += 32) my[k] = 0.0f;
-    float v[4], m = NEG;
+  if (tid == 0) {
+    loss[n] = (float)(-s_logp);
+    w_offB[T] = s_logp;
+  }
+}
+
+// ---- K6 at label lengths <= 63 runs as three launches: the two embarrassingly parallel phases (the per-frame softmax
+// normaliser before the lattice, softmax - occupancy after it) get the whole GPU — a warp per frame over T * N frames —
+// instead of the eight warps of the utterance's own CTA (which spent 19 % + 37 % of the fused kernel's time on them), and
+// only the 999-step dependent chain stays on one CTA per utterance.
+__global__ void __launch_bounds__(CTC_THREADS)
+ctc_lse_kernel(const float* __restrict__ logits, int T, int N, int C, const int* __restrict__ in_len, int s_max,
+               float* __restrict__ ws) {
+  const int lane = threadIdx.x & 31;
+  const long long f = (long long)blockIdx.x * CTC_WARPS + (threadIdx.x >> 5);      // frame (t, n) of the time-major logits
+  if (f >= (long long)T * N) return;
+  const int t = (int)(f / N), n = (int)(f % N);
+  if (t >= min(max(in_len[n], 0), T)) return;
+  const float* row = logits + (size_t)f * C;
+  float m = -CUDART_INF_F;
+  for (int k = lane; k < C; k += 32) m = fmaxf(m, row[k]);
+  m = asr::warp_max(m);
+  float sx = 0.0f;
+  for (int k = lane; k < C; k += 32) sx += expf(row[k] - m);
+  sx = asr::warp_sum(sx);
+  if (lane == 0) (ws + (size_t)n * ws_stride(T, s_max) + (size_t)2 * T * s_max)[t] = m + logf(sx);
+}
+
+__global__ void __launch_bounds__(CTC_THREADS)
+ctc_grad_mw_kernel(const float* __restrict__ logits, int T, int N, int C, const int* __restrict__ in_len,
+                   const int* __restrict__ labels, const int* __restrict__ label_off, int s_max, int blank,
+                   float grad_scale, float* __restrict__ grad, const float* __restrict__ ws) {
+  extern __shared__ float sm[];                         // [CTC_WARPS][C] per-class occupancy of the warp's frame
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long f = (long long)blockIdx.x * CTC_WARPS + warp;
+  if (f >= (long long)T * N) return;
+  const int t = (int)(f / N), n = (int)(f % N);
+  const float NEG = -CUDART_INF_F;
+  const int len = min(max(in_len[n], 0), T);
+  const float* w_alpha = ws + (size_t)n * ws_stride(T, s_max);
+  const float* w_beta = w_alpha + (size_t)T * s_max;
+  const float* w_lse = w_beta + (size_t)T * s_max;
+  const double* w_offA = reinterpret_cast<const double*>(w_alpha + ws_f32_part(T, s_max));
+  const double* w_offB = w_offA + T;
+  const double logp = w_offB[T];
+  float* g = grad + (size_t)f * C;
+  if (t >= len || !(logp > -(double)CUDART_INF)) {
+    for (int k = lane; k < C; k += 32) g[k] = 0.0f;
+    return;
+  }
+  const int l0 = label_off[n], S = 2 * (label_off[n + 1] - l0) + 1;
+  const float* row = logits + (size_t)f * C;
+  const float z = w_lse[t];
+  const float kf = (float)(w_offA[t] + w_offB[t] - logp);
+  float* my = sm + warp * C;
+  for (int k = lane; k < C; k += 32) my[k] = 0.0f;
+  float v[4], m = NEG;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int s = j * 32 + lane;
+    v[j] = (s < S) ? w_alpha[(size_t)t * s_max + s] + w_beta[(size_t)t * s_max + s] : NEG;
+    m = fmaxf(m, v[j]);
+  }
+  m = asr::warp_max(m);
+  __syncwarp();
+  float bsum = 0.0f;
+  if (m > NEG) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int s = j * 32 + lane;
-      v[j] = (s < S) ? w_alpha[(size_t)t * s_max + s] + w_beta[(size_t)t * s_max + s] : NEG;
-      m = fmaxf(m, v[j]);
-    }
-    m = asr::warp_max(m);
-    __syncwarp();
-    float bsum = 0.0f;
-    if (m > NEG) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int s = j * 32 + lane;
-        if (s < S) {
-          const float e = expf(v[j] - m);
-          if (s & 1) atomicAdd(my + ext[s], e);
-          else bsum += e;
-        }
+      if (s < S) {
+        const float e = expf(v[j] - m);
+        if (s & 1) atomicAdd(my + labels[l0 + (s >> 1)], e);
+        else bsum += e;
       }
     }
-    bsum = asr::warp_sum(bsum);
-    if (lane == 0) atomicAdd(my + blank, bsum);
-    __syncwarp();
-    for (int k = lane; k < C; k += 32) {
-      const float lp = row[k] - z;
-      float occ = 0.0f;
-      if (my[k] > 0.0f) occ = my[k] * expf(m + kf - lp);
-      g[k] = grad_scale * (expf(lp) - occ);
-    }
-    __syncwarp();
+  }
+  bsum = asr::warp_sum(bsum);
+  if (lane == 0) atomicAdd(my + blank, bsum);
+  __syncwarp();
+  for (int k = lane; k < C; k += 32) {
+    const float lp = row[k] - z;
+    float occ = 0.0f;
+    if (my[k] > 0.0f) occ = my[k] * expf(m + kf - lp);
+    g[k] = grad_scale * (expf(lp) - occ);
   }
 }
 
@@ -577,8 +614,7 @@ ctc_greedy_kernel(const float* __restrict__ logits, int T, int N, int C,
 extern "C" size_t asr_ctc_workspace_bytes(int32_t T, int32_t N, int32_t max_label_len) {
   if (T <= 0 || N <= 0 || max_label_len < 0) return 0;
   const size_t s_max = 2 * (size_t)max_label_len + 1;
-  const size_t fl_per = ((size_t)2 * T * s_max + T + 1) & ~(size_t)1;
-  return (size_t)N * (fl_per + 4 * (size_t)T) * sizeof(float);
+  return (size_t)N * ws_stride(T, (int)s_max) * sizeof(float);
 }
 
 extern "C" int32_t asr_ctc_loss_grad(const float* logits, int32_t T, int32_t N, int32_t C, const int32_t* in_len,
@@ -591,9 +627,14 @@ extern "C" int32_t asr_ctc_loss_grad(const float* logits, int32_t T, int32_t N, 
   const int s_max = 2 * max_label_len + 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (s_max <= 128) {
-    const size_t smem = (size_t)(132 + 4 * 132 + 16 + CTC_WARPS * C) * sizeof(float);
-    ctc_loss_grad_mw_kernel<<<N, CTC_THREADS, smem, st>>>(logits, T, N, C, in_len, labels, label_off, s_max, blank,
-                                                           grad_scale, loss, grad, (float*)ws);
+    const int frame_ctas = (int)(((long long)T * N + CTC_WARPS - 1) / CTC_WARPS);
+    ctc_lse_kernel<<<frame_ctas, CTC_THREADS, 0, st>>>(logits, T, N, C, in_len, s_max, (float*)ws);
+    ASR_LAUNCH_CHECK();
+    ctc_lattice_mw_kernel<<<N, CTC_THREADS, (size_t)(132 + 4 * 132 + 16) * sizeof(float), st>>>(
+        logits, T, N, C, in_len, labels, label_off, s_max, blank, loss, (float*)ws);
+    ASR_LAUNCH_CHECK();
+    ctc_grad_mw_kernel<<<frame_ctas, CTC_THREADS, (size_t)CTC_WARPS * C * sizeof(float), st>>>(
+        logits, T, N, C, in_len, labels, label_off, s_max, blank, grad_scale, grad, (const float*)ws);
   } else {
     const size_t smem = (size_t)(3 * 32 * 16 + 4 + CTC_WARPS * C) * sizeof(float);
     ctc_loss_grad_kernel<16><<<N, CTC_THREADS, smem, st>>>(logits, T, N, C, in_len, labels, label_off, s_max, blank,
