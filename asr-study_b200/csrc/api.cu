@@ -47,7 +47,9 @@ extern "C" int32_t asr_gemm_tn_ex(int32_t dtype_in, int32_t dtype_out, int32_t M
   ASR_CHECK_ARG(A && B && C, "asr_gemm_tn: null operand");
   ASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "asr_gemm_tn: bad shape %dx%dx%d", M, N, K);
   ASR_CHECK_ARG(dtype_in >= 0 && dtype_in <= 1 && dtype_out >= 0 && dtype_out <= 2, "asr_gemm_tn: bad dtype");
-  ASR_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K && ldc >= N,
+  // lda < K is allowed: rows of A then overlap (row m starts lda elements after row m-1), a Toeplitz view that turns a
+  // convolution over the leading axis into a plain GEMM without an im2col copy (engine.py:_conv_forward)
+  ASR_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= 8 && ldb >= K && ldc >= N,
                 "asr_gemm_tn: K, lda, ldb must be multiples of 8 (16-byte rows)");
   ASR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "asr_gemm_tn: operands must be 16-byte aligned");
   ASR_CHECK_ARG(!accumulate || dtype_out == 0, "asr_gemm_tn: accumulate needs fp32 C");

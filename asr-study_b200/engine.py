@@ -1144,68 +1144,81 @@ class AcousticEngine:
             xT = w["xT16"] if l == 0 else w[f"hT16.{l - 1}"]
             hT = w[f"hT16.{l}"]
             dzT = w[f"dzT16.{l}"]
-            main = torch.cuda.current_stream()
-            side = self._side if self.overlap else main
-            if side is not main:
-                side.wait_stream(main)                      # dz of this layer is complete
-            with torch.cuda.stream(side):
-                sst = cur_stream()
-                for i, d in enumerate("fb"):
-                    # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
-                    xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
-                    bg = GEMM_BACKGROUND if (side is not main and l > 0) else 0      # runs beside the next BPTT
-                    lib.asr_gemm_tn_ex(BF16, OUT_F32, D, 4 * H, R, ptr(xTd), R, ptr(dzT[i * 4 * H:]), R,
-                                       ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, bg, sst)
-                    # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
-                    if T > 1:
-                        Kk = (T - 1) * N
-                        hA = hT[i * H:(i + 1) * H]
-                        dzB = (self._views[f"duhT16.{l}"] if sp.mi is not None else dzT)[i * 4 * H:(i + 1) * 4 * H]
-                        if i == 0:   # forward direction: h_{t-1} with dz_t
-                            Ap, Bp = hA, dzB[:, N:]
-                        else:        # reverse direction: h_{t+1} with dz_t
-                            Ap, Bp = hA[:, N:], dzB
-                        lib.asr_gemm_tn_ex(BF16, OUT_F32, H, 4 * H, Kk, C.c_void_p(Ap.data_ptr()), R,
-                                           C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, bg, sst)
+            def input_gradient():
+                nonlocal dh, other, dh2, mask_dh
+                if l == 0 and sp.conv_front:
+                    # dL/d(conv output) [R, D] = dz . Wcat^T (per direction with the fused dropout masks), then the conv backward
+                    dx0 = self._buf("dx0", (R, D), torch.float32)
+                    wc = self._views[f"Wcat16.{l}"]
+                    if masks is None:
+                        self._gemm(BF16, OUT_F32, R, D, 8 * H, w[f"dz16.{l}"], 8 * H, wc, 8 * H, dx0, D)
                     else:
-                        P.g(f"l{l}.U{d}").zero_()
-                if allreduce is not None:               # layer l's gradients are complete on this stream: reduce them now
-                    lo, hi = self._layer_slice(l)
-                    handles.append(allreduce(P.grad[(0 if (l == 0 and not sp.conv_front) else lo):hi]))
-            if l == 0 and sp.conv_front:
-                # dL/d(conv output) [R, D] = dz . Wcat^T (per direction with the fused dropout masks), then the conv backward
-                dx0 = self._buf("dx0", (R, D), torch.float32)
-                wc = self._views[f"Wcat16.{l}"]
-                if masks is None:
-                    self._gemm(BF16, OUT_F32, R, D, 8 * H, w[f"dz16.{l}"], 8 * H, wc, 8 * H, dx0, D)
-                else:
-                    part = [self._buf(f"dx0part.{i}", (R, D), torch.float32) for i in range(2)]
-                    for i in range(2):
-                        lib.asr_gemm_tn(BF16, OUT_F32, R, D, 4 * H, ptr(w[f"dz16.{l}"][:, i * 4 * H:]), 8 * H,
-                                        ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), D, None, 1.0, 0, st)
-                    mk = masks[l]
-                    lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
-                                         ptr(dx0), R, D, st)
-                self._conv_backward(dx0)
-            elif l > 0 and masks is None:
-                # dX [R, 2H] = dz16 [R, 8H] . Wcat16 [2H, 8H]^T
-                self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w[f"dz16.{l}"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
-                           other, 2 * H)
-                dh, other = other, dh
-            elif l > 0:
-                # dX = (dz_f . Wf^T) * B_Wf + (dz_b . Wb^T) * B_Wb   (each direction's LSTM masked its own input)
-                part = [self._buf(f"dxpart.{i}", (R, 2 * H), torch.float32) for i in range(2)]
-                wc = self._views[f"Wcat16.{l}"]
-                for i in range(2):
-                    lib.asr_gemm_tn(BF16, OUT_F32, R, 2 * H, 4 * H, ptr(w[f"dz16.{l}"][:, i * 4 * H:]), 8 * H,
-                                    ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), 2 * H, None, 1.0, 0, st)
-                mk = masks[l]
-                if fuse:                            # the BPTT kernel of layer l-1 combines the partials with B_Wf / B_Wb
-                    dh, dh2, mask_dh = part[0], part[1], self._views[f"maskW.{l}"]
-                else:
-                    lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
-                                         ptr(other), R, 2 * H, st)
+                        part = [self._buf(f"dx0part.{i}", (R, D), torch.float32) for i in range(2)]
+                        for i in range(2):
+                            lib.asr_gemm_tn(BF16, OUT_F32, R, D, 4 * H, ptr(w[f"dz16.{l}"][:, i * 4 * H:]), 8 * H,
+                                            ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), D, None, 1.0, 0, st)
+                        mk = masks[l]
+                        lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
+                                             ptr(dx0), R, D, st)
+                    self._conv_backward(dx0)
+                elif l > 0 and masks is None:
+                    # dX [R, 2H] = dz16 [R, 8H] . Wcat16 [2H, 8H]^T
+                    self._gemm(BF16, OUT_F32, R, 2 * H, 8 * H, w[f"dz16.{l}"], 8 * H, self._ws[f"Wcat16.{l}"], 8 * H,
+                               other, 2 * H)
                     dh, other = other, dh
+                elif l > 0:
+                    # dX = (dz_f . Wf^T) * B_Wf + (dz_b . Wb^T) * B_Wb   (each direction's LSTM masked its own input)
+                    part = [self._buf(f"dxpart.{i}", (R, 2 * H), torch.float32) for i in range(2)]
+                    wc = self._views[f"Wcat16.{l}"]
+                    for i in range(2):
+                        lib.asr_gemm_tn(BF16, OUT_F32, R, 2 * H, 4 * H, ptr(w[f"dz16.{l}"][:, i * 4 * H:]), 8 * H,
+                                        ptr(wc[:, i * 4 * H:]), 8 * H, ptr(part[i]), 2 * H, None, 1.0, 0, st)
+                    mk = masks[l]
+                    if fuse:                            # the BPTT kernel of layer l-1 combines the partials with B_Wf / B_Wb
+                        dh, dh2, mask_dh = part[0], part[1], self._views[f"maskW.{l}"]
+                    else:
+                        lib.asr_mask_combine(ptr(part[0]), ptr(part[1]), ptr(mk["Wf"].contiguous()), ptr(mk["Wb"].contiguous()), N,
+                                             ptr(other), R, 2 * H, st)
+                        dh, other = other, dh
+
+            def weight_gradients():
+                main = torch.cuda.current_stream()
+                side = self._side if self.overlap else main
+                if side is not main:
+                    # behind the dX GEMMs above: they feed the next BPTT, and a background CTA that got its SM first holds it for
+                    # a whole K = T*N tile (the second dX GEMM ran 0.20 instead of 0.11 ms when both started together)
+                    side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    sst = cur_stream()
+                    for i, d in enumerate("fb"):
+                        # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
+                        xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
+                        bg = GEMM_BACKGROUND if (side is not main and l > 0) else 0      # runs beside the next BPTT
+                        lib.asr_gemm_tn_ex(BF16, OUT_F32, D, 4 * H, R, ptr(xTd), R, ptr(dzT[i * 4 * H:]), R,
+                                           ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, bg, sst)
+                        # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
+                        if T > 1:
+                            Kk = (T - 1) * N
+                            hA = hT[i * H:(i + 1) * H]
+                            dzB = (self._views[f"duhT16.{l}"] if sp.mi is not None else dzT)[i * 4 * H:(i + 1) * 4 * H]
+                            if i == 0:   # forward direction: h_{t-1} with dz_t
+                                Ap, Bp = hA, dzB[:, N:]
+                            else:        # reverse direction: h_{t+1} with dz_t
+                                Ap, Bp = hA[:, N:], dzB
+                            lib.asr_gemm_tn_ex(BF16, OUT_F32, H, 4 * H, Kk, C.c_void_p(Ap.data_ptr()), R,
+                                               C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, bg, sst)
+                        else:
+                            P.g(f"l{l}.U{d}").zero_()
+                    if allreduce is not None:               # layer l's gradients are complete on this stream: reduce them now
+                        lo, hi = self._layer_slice(l)
+                        handles.append(allreduce(P.grad[(0 if (l == 0 and not sp.conv_front) else lo):hi]))
+
+            if l == 0:              # nothing follows but the conv front end's backward pass: let it run beside these GEMMs
+                weight_gradients()
+                input_gradient()
+            else:                   # the dX GEMMs feed the next BPTT: first, alone on the machine
+                input_gradient()
+                weight_gradients()
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self._side)
         if allreduce is not None and sp.conv_front:     # the conv front end's gradients: the head of the bucket
