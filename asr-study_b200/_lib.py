@@ -57,6 +57,11 @@ class ConvGeom(C.Structure):
                 ("st", C.c_int32), ("sf", C.c_int32), ("pt", C.c_int32), ("pf", C.c_int32)]
 
 
+class ConvPlan(C.Structure):
+    _fields_ = [("t_out", C.c_int32), ("f_out", C.c_int32), ("rows", C.c_int32), ("t_padded", C.c_int32), ("k", C.c_int32),
+                ("k_padded", C.c_int32)]
+
+
 class LstmVariant(C.Structure):
     _fields_ = [("mi_alpha", C.c_void_p), ("mi_beta1", C.c_void_p), ("mi_beta2", C.c_void_p),
                 ("ln_gain_uh", C.c_void_p), ("ln_bias_uh", C.c_void_p), ("ln_gain_wx", C.c_void_p),
@@ -116,11 +121,13 @@ SIGNATURES = {
     "asr_add_gaussian_noise": (_I32, [_P, _I64, _I32, _I64, _F, C.c_uint64, C.c_uint64, _P]),
     "asr_add_mask": (_I32, [_P, _P, _P, _I64, _P, _I64, _I32, _P]),
     "asr_mask_combine": (_I32, [_P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),
-    "asr_conv_out_shape": (_I32, [C.POINTER(ConvGeom), _P, _P, _P, _P]),
-    "asr_conv_im2col": (_I32, [_P, _I32, C.POINTER(ConvGeom), _P, _I64, _P, _I64, _P]),
-    "asr_conv_col2im": (_I32, [_P, _I64, C.POINTER(ConvGeom), _P, _P]),
-    "asr_clipped_relu": (_I32, [_P, _I64, _F, _P, _P, _P]),
-    "asr_clipped_relu_backward": (_I32, [_P, _P, _I32, _I64, _I32, _F, _P, _P, _P, _P]),
+    "asr_conv_plan_for": (_I32, [C.POINTER(ConvGeom), C.POINTER(ConvPlan)]),
+    "asr_conv_pack": (_I32, [_P, C.POINTER(ConvGeom), _P, _P]),
+    "asr_conv_toeplitz": (_I32, [_P, _P, C.POINTER(ConvGeom), _I32, _P, _I64, _P, _P, _P]),
+    "asr_conv_act": (_I32, [_P, C.POINTER(ConvGeom), _I32, _F, _P, _I32, _I32, _P, _P]),
+    "asr_conv_act_backward": (_I32, [_P, _I64, _I64, _I64, _P, _I32, _I32, C.POINTER(ConvGeom), _I32, _F, _P, _P, _P, _P]),
+    "asr_conv_unfold_t": (_I32, [_P, C.POINTER(ConvGeom), _P, _I64, _P]),
+    "asr_conv_toeplitz_grad": (_I32, [_P, _I64, _P, C.POINTER(ConvGeom), _I32, _P, _P, _P]),
 }
 
 

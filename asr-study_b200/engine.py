@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from ._lib import (GEMM_BACKGROUND, GEMM_TILE128, LSTM_SHARED_SM, ConvGeom, LstmBwdArgs, LstmFwdArgs, LstmVariant,
+from ._lib import (GEMM_BACKGROUND, GEMM_TILE128, LSTM_SHARED_SM, ConvGeom, ConvPlan, LstmBwdArgs, LstmFwdArgs, LstmVariant,
                    LstmVariantGrads, cur_stream, lib, ptr)
 
 F16, BF16 = 0, 1
@@ -472,57 +472,86 @@ class AcousticEngine:
 
     # ------------------------------------------------- convolutional front end (BASELINE configs[3])
     def _conv_forward(self, x, training):
-        """x f32 [T, N, F] -> f32 [T', N, F' * C]: per layer im2col (fp16 patch matrix, + its bf16 transpose when
-        training) -> tcgen05 GEMM with the bias -> clipped ReLU.  Rows of every matrix are (t', n, f'), so the last
-        activation IS the time-major input of the first BiLSTM."""
+        """x f32 [T, N, F] -> f32 [T', N, F' * C].  Per layer ONE tcgen05 GEMM whose A operand is the overlapping-row view
+        of the zero-padded batch-major fp16 activations (csrc/conv.cu: no patch matrix), B the banded frequency-Toeplitz
+        image of the kernel, bias in the epilogue; then clipped ReLU, written straight into the next layer's padded
+        input (or, for the last layer, as the time-major input of the first BiLSTM)."""
         sp, P, st = self.spec, self.params, cur_stream()
         T, N, F = x.shape
-        cur, cur_dt, Cin = x, 2, 1
+        Cin = 1
         self._conv = []
+        layers = []
+        fresh = getattr(self, "_conv_key", None) != (T, N, F)   # a new shape re-uses the flat buffers with another layout:
+        self._conv_key = (T, N, F)                              # what is padding now may hold old activations
+        if fresh:
+            self._conv_zero_g = True
         for i, (co, kt, kf, s_t, s_f) in enumerate(sp.conv_front):
             g = ConvGeom(T=T, N=N, F=F, C=Cin, kt=kt, kf=kf, st=s_t, sf=s_f, pt=(kt - 1) // 2, pf=(kf - 1) // 2)
-            To, Fo, K = (T + 2 * g.pt - kt) // s_t + 1, (F + 2 * g.pf - kf) // s_f + 1, kt * kf * Cin
-            Kp, M = _pad8(K), To * N * Fo
-            patches = self._buf(f"conv{i}.patch", (M, Kp), torch.float16)
-            patchesT = self._buf(f"conv{i}.patchT", (K, M), torch.bfloat16) if training else None
-            lib.asr_conv_im2col(ptr(cur), cur_dt, C.byref(g), ptr(patches), Kp, ptr(patchesT), M, st)
-            w16 = self._buf(f"conv{i}.W16", (co, Kp), torch.float16, zero=True)
-            lib.asr_cast_rows(ptr(P.p(f"conv{i}.W")), K, ptr(w16), Kp, co, K, F16, st)
-            z = self._buf(f"conv{i}.z", (M, co), torch.float32)
-            self._gemm(F16, OUT_F32, M, co, Kp, patches, Kp, w16, Kp, z, co, bias=P.p(f"conv{i}.b"))
-            last = i == len(sp.conv_front) - 1
-            y16 = self._buf(f"conv{i}.y16", (M, co), torch.float16)
-            y32 = self._buf("conv.out32", (M, co), torch.float32) if last else None
-            lib.asr_clipped_relu(ptr(z), M * co, float(sp.conv_clip), ptr(y32), ptr(y16), st)
-            self._conv.append(dict(geom=g, M=M, K=K, Kp=Kp, co=co, patchesT=patchesT, y16=y16))
-            cur, cur_dt, T, F, Cin = y16, 0, To, Fo, co
-        return y32.view(T, N, F * Cin)
+            pl = ConvPlan()
+            lib.asr_conv_plan_for(C.byref(g), C.byref(pl))
+            layers.append((g, pl, co))
+            T, F, Cin = pl.t_out, pl.f_out, co
+        for i, (g, pl, co) in enumerate(layers):
+            W_in, W_out, M = g.F * g.C, pl.f_out * co, g.N * pl.rows
+            # padded input [N, t_padded, W_in] + slack for the windows of the scratch rows; zeroed once, padding never written
+            xp = self._buf(f"conv{i}.xp", (g.N * pl.t_padded * W_in + pl.k_padded + 64,), torch.float16, zero=True)
+            if i == 0:
+                if fresh:
+                    xp.zero_()
+                lib.asr_conv_pack(ptr(x), C.byref(g), ptr(xp), st)
+            wt = self._buf(f"conv{i}.wt16", (W_out, pl.k_padded), torch.float16)
+            w2 = self._buf(f"conv{i}.w2_16", (W_in, g.kt * W_out), torch.bfloat16) if (training and i > 0) else None
+            bt = self._buf(f"conv{i}.bias_t", (W_out,), torch.float32)
+            lib.asr_conv_toeplitz(ptr(P.p(f"conv{i}.W")), ptr(P.p(f"conv{i}.b")), C.byref(g), co, ptr(wt), pl.k_padded, ptr(w2),
+                                  ptr(bt), st)
+            z = self._buf(f"conv{i}.z", (M, W_out), torch.float32)
+            self._gemm(F16, OUT_F32, M, W_out, pl.k_padded, xp, g.st * W_in, wt, pl.k_padded, z, W_out, bias=bt)
+            last = i == len(layers) - 1
+            if last:                                   # fp16 copy in GEMM-row space (the backward mask) + the BiLSTM's input
+                y16, y_rows, y_row0 = self._buf(f"conv{i}.y16", (M, W_out), torch.float16), pl.rows, 0
+                y32 = self._buf("conv.out32", (pl.t_out, g.N, W_out), torch.float32)
+            else:                                      # the next layer's padded input
+                gn, pn = layers[i + 1][0], layers[i + 1][1]
+                y16 = self._buf(f"conv{i + 1}.xp", (g.N * pn.t_padded * W_out + pn.k_padded + 64,), torch.float16, zero=True)
+                y_rows, y_row0, y32 = pn.t_padded, gn.pt, None
+                if fresh:
+                    y16.zero_()
+            lib.asr_conv_act(ptr(z), C.byref(g), co, float(sp.conv_clip), ptr(y16), y_rows, y_row0, ptr(y32), st)
+            self._conv.append(dict(geom=g, plan=pl, co=co, xp=xp, w2=w2, y16=y16, y_rows=y_rows, y_row0=y_row0))
+        return y32
 
     def _conv_backward(self, dx):
-        """dx f32 [T' * N, F' * C] (dL/d input of the first BiLSTM) -> conv{i}.W / conv{i}.b gradients."""
-        import ctypes
+        """dx f32 [T' * N, F' * C] (dL/d input of the first BiLSTM, time-major) -> conv{i}.W / conv{i}.b gradients."""
         sp, P, st = self.spec, self.params, cur_stream()
-        g32 = dx
+        gout, g_ts, g_ns, g_row0 = dx, self._conv[-1]["geom"].N, 1, 0
         for i in range(len(sp.conv_front) - 1, -1, -1):
             c = self._conv[i]
-            M, K, Kp, co = c["M"], c["K"], c["Kp"], c["co"]
-            g16 = self._buf(f"conv{i}.g16", (M, co), torch.bfloat16)
-            gT16 = self._buf(f"conv{i}.gT16", (co, M), torch.bfloat16)
-            gm = self._buf(f"conv{i}.gm32", (M, co), torch.float32)
-            lib.asr_clipped_relu_backward(ptr(g32), ptr(c["y16"]), 0, M, co, float(sp.conv_clip), ptr(g16), ptr(gT16), ptr(gm), st)
-            lib.asr_colsum(ptr(gm), co, M, co, ptr(P.g(f"conv{i}.b")), st)
-            # dW [C_out, K] = g^T [C_out, M] . patches^T [K, M]^T
-            self._gemm(BF16, OUT_F32, co, K, M, gT16, M, c["patchesT"], M, P.g(f"conv{i}.W"), K)
+            g, pl, co = c["geom"], c["plan"], c["co"]
+            W_in, W_out, M = g.F * g.C, pl.f_out * co, g.N * pl.rows
+            # dL/dz in GEMM-row space behind kt - 1 zero rows (the mirrored input-gradient GEMM reads them), its transpose, f32
+            gbuf = self._buf(f"conv{i}.g16", ((g.kt - 1 + M) * W_out,), torch.bfloat16, zero=True)
+            if getattr(self, "_conv_zero_g", False):
+                gbuf.zero_()
+            g16 = gbuf[(g.kt - 1) * W_out:]
+            gT16 = self._buf(f"conv{i}.gT16", (W_out, M), torch.bfloat16)
+            g32 = self._buf(f"conv{i}.g32", (M, W_out), torch.float32)
+            lib.asr_conv_act_backward(ptr(gout), g_ts, g_ns, g_row0, ptr(c["y16"]), c["y_rows"], c["y_row0"], C.byref(g), co,
+                                      float(sp.conv_clip), ptr(g16), ptr(gT16), ptr(g32), st)
+            cs = self._buf(f"conv{i}.colsum", (W_out,), torch.float32)
+            lib.asr_colsum(ptr(g32), W_out, M, W_out, ptr(cs), st)
+            # d(banded matrix) [W_out, K] = g^T [W_out, M] . view(xp)^T [K, M]^T, then fold the bins back into the kernel
+            xuT = self._buf(f"conv{i}.xuT16", (pl.k, M), torch.bfloat16)
+            lib.asr_conv_unfold_t(ptr(c["xp"]), C.byref(g), ptr(xuT), M, st)
+            dwt = self._buf(f"conv{i}.dwt", (W_out, pl.k), torch.float32)
+            self._gemm(BF16, OUT_F32, W_out, pl.k, M, gT16, M, xuT, M, dwt, pl.k)
+            lib.asr_conv_toeplitz_grad(ptr(dwt), pl.k, ptr(cs), C.byref(g), co, ptr(P.g(f"conv{i}.W")), ptr(P.g(f"conv{i}.b")), st)
             if i > 0:
-                # dPatches [M, Kp] = g [M, C_out] . W^T [Kp, C_out]^T, then the gather-form col2im
-                wt = self._buf(f"conv{i}.Wt16", (Kp, co), torch.bfloat16, zero=True)
-                lib.asr_cast_transpose(ptr(P.p(f"conv{i}.W")), K, ptr(wt), co, co, K, BF16, st)
-                dP = self._buf(f"conv{i}.dpatch", (M, Kp), torch.bfloat16)
-                self._gemm(BF16, OUT_BF16, M, Kp, co, g16, co, wt, co, dP, Kp)
-                gi = c["geom"]
-                dxin = self._buf(f"conv{i}.dx32", (gi.T * gi.N * gi.F, gi.C), torch.float32)
-                lib.asr_conv_col2im(ptr(dP), Kp, ctypes.byref(gi), ptr(dxin), st)
-                g32 = dxin
+                # dL/d(padded input) [N * t_padded, W_in] = view(zero-padded g)[., (dkt', f', co)] . w2^T  (stride 1 in time)
+                assert g.st == 1, "the input gradient of a time-strided inner conv layer is not implemented"
+                dxp = self._buf(f"conv{i}.dxp", (M, W_in), torch.float32)
+                self._gemm(BF16, OUT_F32, M, W_in, g.kt * W_out, gbuf, W_out, c["w2"], g.kt * W_out, dxp, W_in)
+                gout, g_ts, g_ns, g_row0 = dxp, 1, pl.t_padded, g.pt
+        self._conv_zero_g = False
 
     # ---------------------------------------------------------------- forward
     def forward(self, feats_tm: torch.Tensor, training=False, masks=None, zmasks=None, input_mask=None) -> torch.Tensor:

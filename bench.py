@@ -316,7 +316,7 @@ def run_ours(args):
     # per-kernel-class device time (instrumented pass, outside the timed region)
     kern = kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch) if rank == 0 else {}
     if rank == 0 and args.config == "c4":
-        kern["note"] = "other_ms holds the conv front end's im2col / col2im / clipped-ReLU kernels beside casts and masks"
+        kern["note"] = "other_ms holds the conv front end's layout kernels (pack, weight expansion, activation, unfold-transpose) beside casts and masks; its GEMMs are in gemm_ms"
     pk = peaks()
     out = None
     if rank == 0:

@@ -107,7 +107,8 @@ int32_t asr_mfcc_forward_host(const asr_mfcc_plan* plan, const float* pcm_host,
  * A, B: 16-bit (dtype_in: 0 = fp16, 1 = bf16), K-major, lda/ldb in elements
  * (multiples of 8, 16-byte aligned rows).  C: dtype_out 0 = fp32, 1 = fp16,
  * 2 = bf16, row-major ldc.  bias (f32 [N]) optional.  accumulate != 0 adds
- * into fp32 C.
+ * into fp32 C.  lda < K is allowed: row m of A then starts lda elements after
+ * row m-1 and the rows overlap (the convolution view of the conv section below).
  * ------------------------------------------------------------------------- */
 int32_t asr_gemm_tn(int32_t dtype_in, int32_t dtype_out, int32_t M, int32_t N,
                     int32_t K, const void* A, int64_t lda, const void* B,
@@ -370,30 +371,54 @@ int32_t asr_colsum(const float* src, int64_t ld, int64_t rows, int32_t cols,
 /* ------------------------------------------------------------------------- *
  * Convolutional front end of BASELINE configs[3] (DeepSpeech2-style 2 x Conv in front of the BiLSTM stack; NOT in
  * the reference — README.md:118 lists it as future work — so its semantics are this header's: cross-correlation with
- * zero padding, bias, clipped ReLU min(max(z, 0), clip)).  Implicit GEMM: these entry points gather / scatter the patch
- * matrix and apply the activation; the contractions are asr_gemm_tn calls.
- * Activations are time-major [T, N, F, C]; patch rows are (t', n, f'), patch columns (kt, kf, c), K = kt * kf * C padded
- * to a multiple of 8.
+ * zero padding, bias, clipped ReLU min(max(z, 0), clip)).  Implicit GEMM without a patch matrix (csrc/conv.cu):
+ * activations are fp16 [N, t_padded, F * C], batch-major, the T valid frames of an utterance at rows [pt, pt + T) between
+ * zero rows; the convolution window of output frame (n, t') is kt * F * C CONTIGUOUS values starting at element
+ * (n * t_padded + st * t') * F * C, i.e. row n * rows + t' of a matrix with row stride st * F * C < its row length —
+ * asr_gemm_tn takes that view as its A operand (lda < K); the frequency taps are folded into a banded weight matrix.
+ * These entry points are the layout kernels around the GEMMs.
  * ------------------------------------------------------------------------- */
 typedef struct {
-  int32_t T, N, F, C;       /* input frames, utterances, frequency bins, channels */
+  int32_t T, N, F, C;       /* input frames, utterances, frequency bins, channels (st * F * C must be a multiple of 8) */
   int32_t kt, kf;           /* kernel extent in time / frequency                   */
   int32_t st, sf;           /* strides                                              */
   int32_t pt, pf;           /* zero padding on both sides                           */
 } asr_conv_geom;
 
-int32_t asr_conv_out_shape(const asr_conv_geom* geom, int32_t* t_out, int32_t* f_out, int32_t* k, int32_t* k_padded);
-/* x: fp16 (x_dtype 0) or fp32 (2) [T, N, F, C]  ->  patches16 fp16 [T'*N*F', ld] (K padding zeroed) and, optionally,
- * patchesT16 bf16 [K, ldT] (its transpose, the K-major operand of the weight-gradient GEMM) */
-int32_t asr_conv_im2col(const void* x, int32_t x_dtype, const asr_conv_geom* geom, void* patches16, int64_t ld,
-                        void* patchesT16, int64_t ldT, void* stream);
-/* dpatches16 bf16 [T'*N*F', ld]  ->  dx f32 [T, N, F, C] (gather form: no atomics) */
-int32_t asr_conv_col2im(const void* dpatches16, int64_t ld, const asr_conv_geom* geom, float* dx, void* stream);
-/* y = min(max(z, 0), clip) over n elements -> fp32 and / or fp16 copies */
-int32_t asr_clipped_relu(const float* z, int64_t n, float clip, float* y32, void* y16, void* stream);
-/* g = gout * [0 < y < clip] (y fp16 or fp32 [rows, cols]) -> bf16 [rows, cols], bf16 transposed [cols, rows], fp32 */
-int32_t asr_clipped_relu_backward(const float* gout, const void* y, int32_t y_dtype, int64_t rows, int32_t cols,
-                                  float clip, void* g16, void* gT16, float* g32, void* stream);
+typedef struct {
+  int32_t t_out, f_out;     /* output frames / bins                                                              */
+  int32_t rows;             /* GEMM rows per utterance (>= t_out, multiple of 8); rows t' >= t_out are scratch     */
+  int32_t t_padded;         /* frames per utterance of the padded input = st * rows (>= T + 2 pt)                 */
+  int32_t k, k_padded;      /* kt * F * C and its padding to a multiple of 8                                      */
+} asr_conv_plan;
+
+int32_t asr_conv_plan_for(const asr_conv_geom* geom, asr_conv_plan* plan);
+/* x f32 [T, N, F * C] time-major (what the feature kernel emits) -> xp16 fp16 [N, t_padded, F * C] rows [pt, pt + T); the
+ * caller zeroes the buffer once (plus k_padded elements of slack behind it), nothing writes the padding rows */
+int32_t asr_conv_pack(const float* x, const asr_conv_geom* geom, void* xp16, void* stream);
+/* w f32 [c_out, kt, kf, C], b f32 [c_out] -> wt16 fp16 [f_out * c_out, ldw]: the forward GEMM's B operand
+ * wt[(f', co), (dkt, f, c)] = w[co, dkt, f - sf * f' + pf, c] (0 outside the kernel and in the K padding);
+ * w2_16 (optional) bf16 [F * C, kt * f_out * c_out]: the input-gradient GEMM's B operand (taps mirrored in time);
+ * bias_t f32 [f_out * c_out]: the bias tiled over the output bins (the GEMM's bias argument) */
+int32_t asr_conv_toeplitz(const float* w, const float* b, const asr_conv_geom* geom, int32_t c_out, void* wt16,
+                          int64_t ldw, void* w2_16, float* bias_t, void* stream);
+/* z f32 [N * rows, f_out * c_out] (GEMM output) -> y = min(max(z, 0), clip) for t' < t_out: fp16 into rows
+ * [y_row0, y_row0 + t_out) of a [N, y_rows, f_out * c_out] buffer (the next layer's padded input) and / or f32 time-major
+ * [t_out, N, f_out * c_out] (the first BiLSTM's input) */
+int32_t asr_conv_act(const float* z, const asr_conv_geom* geom, int32_t c_out, float clip, void* y16, int32_t y_rows,
+                     int32_t y_row0, float* y32_tm, void* stream);
+/* g = gout * [0 < y < clip] in GEMM-row space (0 for t' >= t_out): g16 bf16 [N * rows, Wo], gT16 bf16 [Wo, N * rows],
+ * g32 f32 [N * rows, Wo] (each optional; Wo = f_out * c_out).  gout f32: element (n, t') at row
+ * t' * g_t_stride + n * g_n_stride + g_row0 (time-major: N, 1, 0; batch-major padded: 1, t_padded, pt); y16 as in asr_conv_act */
+int32_t asr_conv_act_backward(const float* gout, int64_t g_t_stride, int64_t g_n_stride, int64_t g_row0, const void* y16,
+                              int32_t y_rows, int32_t y_row0, const asr_conv_geom* geom, int32_t c_out, float clip,
+                              void* g16, void* gT16, float* g32, void* stream);
+/* out16 bf16 [k, ldT]: out[m, r] = xp16_flat[r * st * F * C + m] — the overlapping view transposed, the K-major operand
+ * of the weight-gradient GEMM dwt [Wo, k] = gT16 . out16^T */
+int32_t asr_conv_unfold_t(const void* xp16, const asr_conv_geom* geom, void* out16, int64_t ldT, void* stream);
+/* dwt f32 [Wo, ld] (gradient of the banded matrix), colsum f32 [Wo] (column sums of g32) -> dw f32 [c_out, kt, kf, C], db f32 [c_out] */
+int32_t asr_conv_toeplitz_grad(const float* dwt, int64_t ld, const float* colsum, const asr_conv_geom* geom, int32_t c_out,
+                               float* dw, float* db, void* stream);
 
 #ifdef __cplusplus
 }
