@@ -1102,9 +1102,9 @@ class AcousticEngine:
     def backward(self, dlogits: torch.Tensor, allreduce=None):
         """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad.
         allreduce (data parallel): called on slices of the flat gradient bucket as soon as they are complete — layer
-        l's slice right behind its dW/dU GEMMs, i.e. while the BPTT of layer l-1 runs — so the collective overlaps the
-        recurrences, the Dense slice right behind its own GEMM at the start; the slices tile the bucket exactly once (still
-        ONE logical all-reduce of the bucket per step).
+        l's [Wf|Wb] right behind its two dW GEMMs and the rest of the layer right behind its dU GEMMs, i.e. while the BPTT
+        of layer l-1 runs, the Dense slice right behind its own GEMM at the start — so only the last slice of layer 0 is
+        exposed; the slices tile the bucket exactly once (still ONE logical all-reduce of the bucket per step).
         Returns the handles (objects with .wait()) the callable returned, if any."""
         sp, P, w = self.spec, self.params, self._w
         handles = []
@@ -1219,12 +1219,19 @@ class AcousticEngine:
                     side.wait_stream(main)
                 with torch.cuda.stream(side):
                     sst = cur_stream()
+                    bg = GEMM_BACKGROUND if (side is not main and l > 0) else 0      # runs beside the next BPTT
+                    lo, hi = self._layer_slice(l)
+                    if l == 0 and not sp.conv_front:
+                        lo = 0
+                    mid = P.offsets[f"l{l}.Uf"]
                     for i, d in enumerate("fb"):
                         # dW_dir [D, 4H] = (x * B_W)^T [D, R] . dzT_dir [4H, R]^T
                         xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
-                        bg = GEMM_BACKGROUND if (side is not main and l > 0) else 0      # runs beside the next BPTT
                         lib.asr_gemm_tn_ex(BF16, OUT_F32, D, 4 * H, R, ptr(xTd), R, ptr(dzT[i * 4 * H:]), R,
                                            ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, bg, sst)
+                    if allreduce is not None:               # [Wf | Wb] is complete on this stream: reduce it under the dU GEMMs
+                        handles.append(allreduce(P.grad[lo:mid]))
+                    for i, d in enumerate("fb"):
                         # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
                         if T > 1:
                             Kk = (T - 1) * N
@@ -1238,9 +1245,8 @@ class AcousticEngine:
                                                C.c_void_p(Bp.data_ptr()), R, ptr(P.g(f"l{l}.U{d}")), 4 * H, None, 1.0, 0, bg, sst)
                         else:
                             P.g(f"l{l}.U{d}").zero_()
-                    if allreduce is not None:               # layer l's gradients are complete on this stream: reduce them now
-                        lo, hi = self._layer_slice(l)
-                        handles.append(allreduce(P.grad[(0 if (l == 0 and not sp.conv_front) else lo):hi]))
+                    if allreduce is not None:               # [Uf | Ub | biases (| switches)]: the rest of layer l's slice
+                        handles.append(allreduce(P.grad[mid:hi]))
 
             if l == 0:              # nothing follows but the conv front end's backward pass: let it run beside these GEMMs
                 weight_gradients()
