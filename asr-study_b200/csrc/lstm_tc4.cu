@@ -24,7 +24,7 @@ namespace lstmtc4 {
 constexpr int UPC = 32;
 constexpr int NM = 16;
 constexpr int CTHREADS = 128;                              // compute threads (4 warps)
-constexpr int THREADS = 160;                               // + the DMA warp
+constexpr int BTHREADS = 192;                              // BPTT: 4 compute warps + the DMA warp + a warp that only issues the MMAs
 constexpr int STATUS_IDX = 64;
 constexpr int HEADER_BYTES = 8192;
 constexpr uint32_t D_COL = 0, A_COL = 64;
@@ -412,13 +412,14 @@ fwd_kernel(asr_lstm_fwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
 // [H units x 128 own gate columns] slice of U in TMEM and reduce-scatters bf16 partials through the LL ring), H <= 512
 // ------------------------------------------------------------------------------------------------------------------
 template <int H, int NB>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(BTHREADS, 1)
 bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbuf, int grp0, int probe_delay,
            const __grid_constant__ BwdMaps M) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int K4 = 4 * H, NCTA = H / UPC;
   constexpr int NBLK = H / 128;
+  constexpr int HB = (NBLK + 1) / 2;                     // the accumulator blocks are committed in two halves
   static_assert(H % 128 == 0 && NBLK >= 1 && NBLK <= 4, "U slice: NBLK x 64 TMEM columns, one accumulator per block");
   constexpr int B_CHUNK = NM * 128;
   constexpr int NPT = NB / 4, PPT = NPT / 2, NP = NB / 2;
@@ -435,22 +436,24 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
   uint8_t* stage = ring + S * IN_BYTES;                  // 2 x {dz [NB][4][32] bf16, dzT [4][32][NB] bf16}
   constexpr int STAGE_BYTES = 8 * TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 2 * STAGE_BYTES);
-  uint64_t* mma_bar = bars;
-  uint64_t* full = bars + 1;
+  uint64_t* mma_bar = bars;                              // [4], two used: the first / second half of the M blocks
+  uint64_t* bready = bars + 4;                           // the B operand (dz_t of all samples) is staged: one arrival per compute warp
+  uint64_t* full = bars + 5;
   uint64_t* sfull = full + S;
   uint64_t* sfree = sfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + 2);
   __shared__ volatile int s_dead;
 
   if (tid == 0) {
-    tc::mbar_init(mma_bar, NBLK);                        // one tcgen05.commit per issuing warp
+    for (int b = 0; b < 4; ++b) tc::mbar_init(mma_bar + b, 1);
+    tc::mbar_init(bready, 4);
     for (int k = 0; k < S; ++k) tc::mbar_init(full + k, 1);
     for (int b = 0; b < 2; ++b) { tc::mbar_init(sfull + b, CTHREADS); tc::mbar_init(sfree + b, 1); }
     tc::fence_mbar_init();
     s_dead = 0;
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < 2 * B_CHUNK / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 2 * B_CHUNK / 16; i += BTHREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -524,9 +527,34 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       }
       tc::bulk_wait<0>();
     }
-  } else {
+  } else if (warp == 5) {
+    // MMA issue, off the compute warps: P = U[:, own gate columns] . dz_t, M block by M block (block b = the rows of CTAs
+    // 4b .. 4b+3), one tcgen05.commit per block, so the compute warps read out and SEND block b while the tensor pipe is
+    // on block b + 1 — the send of the last block is all that follows the last MMA
     const uint32_t idesc = tc::umma_idesc_f16(128, NM, 1);
     const uint32_t sB_addr = tc::smem_u32(sB);
+    for (int s = 0; s + 1 < T; ++s) {
+      if (!tc::mbar_wait(bready, (uint32_t)(s & 1), WATCHDOG_CYCLES) || s_dead) {
+        atomicExch(status, 1);
+        s_dead = 1;
+        break;
+      }
+      if (tc::elect_one_sync()) {
+        tc::tcgen05_fence_after();
+#pragma unroll
+        for (int b = 0; b < NBLK; ++b) {
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
+            tc::umma_ts(tmem + D_COL + b * NM, tmem + A_COL + b * 64 + kb * 8, bd, idesc, kb > 0);
+          }
+          if (b == HB - 1) tc::umma_commit(mma_bar + 0);          // first half of the blocks: read out and sent under the second
+          else if (b == NBLK - 1) tc::umma_commit(mma_bar + 1);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
     const int u = u0 + lane;
     float dc_carry[NPT], mu[NPT], md0[NPT], md1[NPT], db[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -639,40 +667,36 @@ bwd_kernel(asr_lstm_bwd_args a, int* __restrict__ flags, uint2* __restrict__ xbu
       tc::fence_proxy_async_smem();
       PROF(2);
       if (s + 1 < T) {
-        tc::named_bar_sync(1, CTHREADS);                   // the whole B operand (all samples) is in shared memory
-        if (s_dead) break;
-        if (warp < NBLK && tc::elect_one_sync()) {         // warp w issues M block w (units 128 w ..)
-          tc::tcgen05_fence_after();
-#pragma unroll
-          for (int kb = 0; kb < 8; ++kb) {
-            const uint64_t bd = tc::umma_desc_sw128(sB_addr + (kb >> 2) * B_CHUNK) + 2 * (kb & 3);
-            tc::umma_ts(tmem + D_COL + warp * NM, tmem + A_COL + warp * 64 + kb * 8, bd, idesc, kb > 0);
-          }
-          tc::umma_commit(mma_bar);
-        }
-        if (!tc::mbar_wait(mma_bar, (uint32_t)(s & 1), WATCHDOG_CYCLES)) {
-          atomicExch(status, 1);
-          s_dead = 1;
-        }
-        tc::tcgen05_fence_after();
-        PROF(3);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bready);            // my warp's samples of the B operand are in shared memory
         // send: my warp's rows of block b belong to CTA 4b + warp
-        uint32_t rb[NBLK][NB];
         const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + D_COL;
-#pragma unroll
-        for (int bb = 0; bb < NBLK; ++bb) tc::tmem_ldn(tq + bb * NM, rb[bb]);
-        tc::tmem_ld_wait();
         const uint32_t tg = (uint32_t)(s + 1);
         uint2* out = xb + (size_t)(s & 1) * NCTA * SLOT + (size_t)cta * 32 + lane;      // + dst*SLOT + pair*NCTA*32
 #pragma unroll
-        for (int np = 0; np < NP; ++np) {
+        for (int half = 0; half < (NBLK > 1 ? 2 : 1); ++half) {
+          const int b0 = half ? HB : 0, b1 = half ? NBLK : HB;
+          if (!tc::mbar_wait(mma_bar + half, (uint32_t)(s & 1), WATCHDOG_CYCLES)) {
+            atomicExch(status, 1);
+            s_dead = 1;
+          }
+          tc::tcgen05_fence_after();
+          if (half == 0) { PROF(3); }
+          uint32_t rb[HB][NB];
 #pragma unroll
-          for (int bb = 0; bb < NBLK; ++bb) {
-            const __nv_bfloat162 q = __floats2bfloat162_rn(__uint_as_float(rb[bb][2 * np]), __uint_as_float(rb[bb][2 * np + 1]));
-            st_volatile_v2(out + (size_t)(bb * 4 + warp) * SLOT + (size_t)np * NCTA * 32,
-                           make_uint2(*reinterpret_cast<const uint32_t*>(&q), tg));
+          for (int bb = b0; bb < b1; ++bb) tc::tmem_ldn(tq + bb * NM, rb[bb - b0]);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int np = 0; np < NP; ++np) {
+#pragma unroll
+            for (int bb = b0; bb < b1; ++bb) {
+              const __nv_bfloat162 q = __floats2bfloat162_rn(__uint_as_float(rb[bb - b0][2 * np]), __uint_as_float(rb[bb - b0][2 * np + 1]));
+              st_volatile_v2(out + (size_t)(bb * 4 + warp) * SLOT + (size_t)np * NCTA * 32,
+                             make_uint2(*reinterpret_cast<const uint32_t*>(&q), tg));
+            }
           }
         }
+        if (s_dead) break;
         tc::tcgen05_fence_before();
         t_pub = clock64();
         PROF(4);
@@ -881,7 +905,7 @@ static int32_t launch_bwd(const asr_lstm_bwd_args* a, cudaStream_t st) {
     const int G = Gall - grp0 < gm ? Gall - grp0 : gm;
     ASR_CUDA(cudaMemsetAsync(a->flags, 0, HEADER_BYTES + bwd_ring_bytes(H, NB, G), st));
     void* kargs[] = {&args, &flags, &xbuf, &grp0, &delay, &M};
-    ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd_kernel<H, NB>, dim3(NCTA, 2, G), dim3(THREADS), kargs, smem, st));
+    ASR_CUDA(cudaLaunchCooperativeKernel((void*)bwd_kernel<H, NB>, dim3(NCTA, 2, G), dim3(BTHREADS), kargs, smem, st));
     asr::count_launch();
   }
   return ASR_OK;
