@@ -332,7 +332,11 @@ def run_ours(args):
         # dominant kernel = the backward recurrence (largest share of the step, profiles/ncu_summary_*.md)
         ms_bwd = kern.get("lstm_bwd_ms", 0.0) / L
         ms_fwd = kern.get("lstm_fwd_ms", 0.0) / L
-        roof = {"bound": "tensor", "kernel": "lstmtc4::bwd_kernel (persistent BiLSTM BPTT, one launch per layer)",
+        c4 = args.config == "c4"
+        if c4:
+            traffic = None              # the captures under profiles/ are of the C2 kernels
+        roof = {"bound": "tensor", "kernel": ("lstmtc2::bwd3_kernel<832> (H = 800 zero-padded; persistent BiLSTM BPTT, one launch per layer)" if c4 else
+                                              "lstmtc4::bwd_kernel (persistent BiLSTM BPTT, one launch per layer)"),
                 "achieved": gf / ms_bwd if ms_bwd else None, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                 "frac": (gf / ms_bwd / pk["tf_burst"]) if ms_bwd else None,
                 "peak_source": pk["src"] + " bf16_tflops (burst; kernel timed alone with CUDA events)",
