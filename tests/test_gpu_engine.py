@@ -520,3 +520,31 @@ def test_conv_front_end_train_step_parity(dropout):
         assert norm_err(got[k], g) < bar, (k, norm_err(got[k], g))
         rel2 = float(np.linalg.norm(got[k] - g) / max(np.linalg.norm(g), 1e-30))
         assert rel2 < 3e-2, (k, rel2)
+
+
+def test_conv_front_end_inference_ragged_batches_and_changing_shapes():
+    """the conv front end re-uses its flat padded buffers across calls: a batch that is not a multiple of the tile (5
+    utterances, padded inside the engine) and then a SHORTER input on the same engine must not see what an earlier
+    layout left in today's padding rows; inference path (no gradient operands), logits against the fp64 oracle."""
+    from asr_study_b200.engine import AcousticEngine, ModelSpec
+    from oracle import conv as ocv
+    layers, clip = ((8, 5, 7, 2, 2), (8, 3, 5, 1, 2)), 2.0
+    F, H, L, C = 24, 128, 2, 28
+    rng = np.random.RandomState(3)
+    spec = ModelSpec(F, H, L, C, conv_front=layers, conv_clip=clip)
+    params = om.init_params(spec.lstm_in, H, L, C, seed=5)
+    params.update(ocv.init_front(rng, F, layers))
+    for k in params:
+        params[k] = (params[k] + 0.05 * rng.randn(*params[k].shape)).astype(np.float32)
+    eng = AcousticEngine(spec, init_params=params)
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    for N, T in ((5, 57), (8, 41), (3, 30), (5, 57)):
+        x = rng.randn(N, T, F).astype(np.float32)
+        got = eng.forward(dev(np.ascontiguousarray(x.transpose(1, 0, 2))), training=False)
+        torch.cuda.synchronize()
+        assert eng.lstm_status() == 0
+        y, _ = ocv.front_forward(p64, x, layers, clip)
+        ref = om.forward(p64, y, dtype=np.float64)[0]
+        got = got.cpu().numpy().transpose(1, 0, 2)[:N]
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        assert norm_err(got, ref) < 1e-3, (N, T, norm_err(got, ref))

@@ -198,3 +198,31 @@ def test_predict_cli_and_offline_featuriser(tmp_path):
     dl = Dummy(num_speakers=2, num_utterances_per_speaker=3, max_duration=0.6, min_duration=0.3, split=[.5, .25]).to_dict_list()
     first = [i for i, d in enumerate(dl["dataset"]) if d == "train"][0]
     assert np.abs(z["train/inputs"][0] - feat(dl["input"][first])).max() < 1e-5
+
+
+def test_deep_speech2_plugin_surface_small():
+    """configs[3] through the plugin surface in small: deep_speech2 factory -> compile -> train_on_batch (loss falls over
+    a few steps on one batch) -> predict on a ragged batch; label lengths follow the conv front end's time stride."""
+    from scipy import sparse
+
+    from asr_study_b200.core import models
+    rng = np.random.RandomState(0)
+    N, T, F = 6, 64, 40
+    model = models.deep_speech2(num_features=F, num_hiddens=128, num_layers=2, dropout=0.0,
+                                conv_front=((8, 5, 9, 2, 2), (8, 3, 5, 1, 2)), conv_clip=20.0, seed=3)
+    model.compile(optimizer=models.Adam(lr=2e-3, clipnorm=400.0))
+    x = rng.randn(N, T, F).astype(np.float32)
+    x_len = np.full(N, T, np.int32)
+    rows = [rng.randint(0, 26, size=rng.randint(2, 6)).astype(np.int32) for _ in range(N)]
+    coo = sparse.coo_matrix((np.concatenate(rows), (np.repeat(np.arange(N), [len(r) for r in rows]),
+                                                    np.concatenate([np.arange(len(r)) for r in rows]))),
+                            shape=(N, max(len(r) for r in rows)))
+    first = last = None
+    for _ in range(12):
+        out = model.train_on_batch([x, coo, x_len])
+        last = float(out[1])
+        first = last if first is None else first
+    assert np.isfinite(last) and last < 0.8 * first, (first, last)
+    model.check_status()
+    pred = model.predict([x[:5], x_len[:5]])
+    assert pred.shape[0] == 5 and pred.shape[1] == model.engine.out_frames(T) == 32
