@@ -1103,8 +1103,8 @@ class AcousticEngine:
         """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad.
         allreduce (data parallel): called on slices of the flat gradient bucket as soon as they are complete — layer
         l's [Wf|Wb] right behind its two dW GEMMs and the rest of the layer right behind its dU GEMMs, i.e. while the BPTT
-        of layer l-1 runs, the Dense slice right behind its own GEMM at the start — so only the last slice of layer 0 is
-        exposed; the slices tile the bucket exactly once (still ONE logical all-reduce of the bucket per step).
+        of layer l-1 runs, the Dense slice right behind its own GEMM at the start, layer 0 as one slice behind its GEMMs — the
+        only exposed one; the slices tile the bucket exactly once (still ONE logical all-reduce of the bucket per step).
         Returns the handles (objects with .wait()) the callable returned, if any."""
         sp, P, w = self.spec, self.params, self._w
         handles = []
@@ -1229,8 +1229,8 @@ class AcousticEngine:
                         xTd = xT if masks is None else self._views[f"xmT16.{l}.{i}"]
                         lib.asr_gemm_tn_ex(BF16, OUT_F32, D, 4 * H, R, ptr(xTd), R, ptr(dzT[i * 4 * H:]), R,
                                            ptr(P.g(f"l{l}.W{d}")), 4 * H, None, 1.0, 0, bg, sst)
-                    if allreduce is not None:               # [Wf | Wb] is complete on this stream: reduce it under the dU GEMMs
-                        handles.append(allreduce(P.grad[lo:mid]))
+                    if allreduce is not None and l > 0:     # [Wf | Wb] is complete on this stream: reduce it under the dU GEMMs
+                        handles.append(allreduce(P.grad[lo:mid]))  # (layer 0 is the exposed tail: one collective, one latency)
                     for i, d in enumerate("fb"):
                         # dU_dir [H, 4H] = h_prev^T . dz  with the one-step time shift of the recurrence
                         if T > 1:
@@ -1246,7 +1246,7 @@ class AcousticEngine:
                         else:
                             P.g(f"l{l}.U{d}").zero_()
                     if allreduce is not None:               # [Uf | Ub | biases (| switches)]: the rest of layer l's slice
-                        handles.append(allreduce(P.grad[mid:hi]))
+                        handles.append(allreduce(P.grad[(mid if l > 0 else lo):hi]))
 
             if l == 0:              # nothing follows but the conv front end's backward pass: let it run beside these GEMMs
                 weight_gradients()

@@ -1,5 +1,5 @@
 """The data-parallel hook: engine.backward hands the gradient bucket to `allreduce` in slices that tile it exactly
-once (the Dense layer first, then per layer [Wf|Wb] behind the dW GEMMs and the rest behind the dU GEMMs), and waits for returned handles."""
+once (the Dense layer first, then per layer [Wf|Wb] behind the dW GEMMs and the rest behind the dU GEMMs; layer 0 whole), and waits for returned handles."""
 import numpy as np
 import pytest
 import torch
@@ -39,6 +39,6 @@ def test_allreduce_slices_tile_the_bucket_once_and_scaling_matches():
 
     eng.train_step(x, lens, flat, off, mx, global_batch=2 * N, allreduce=fake_allreduce, lr=0.0, clipnorm=0.0)
     torch.cuda.synchronize()
-    assert bool((seen == 1).all()) and Handle.waited == 2 * L + 1
+    assert bool((seen == 1).all()) and Handle.waited == 2 * L
     # two identical ranks at global batch 2N give exactly the single-rank gradient at batch N
     torch.testing.assert_close(eng.params.grad, g_ref, rtol=1e-5, atol=1e-7)
