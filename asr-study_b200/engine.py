@@ -22,6 +22,7 @@ from ._lib import (GEMM_BACKGROUND, GEMM_TILE128, LSTM_SHARED_SM, ConvGeom, Conv
                    LstmVariantGrads, cur_stream, lib, ptr)
 
 F16, BF16 = 0, 1
+DP_SLICE_BYTES = 128 << 20     # gradient buckets above this are all-reduced in overlapped slices (engine.backward)
 F16_LO = 16          # fp16(v - fp16(v)): the low half of a split-precision operand (csrc/utils.cu)
 OUT_F32, OUT_F16, OUT_BF16 = 0, 1, 2
 
@@ -266,6 +267,7 @@ class AcousticEngine:
         self._main = torch.cuda.Stream(device=self.device, priority=-1)
         self._side = torch.cuda.Stream(device=self.device, priority=0)
         self.overlap = bool(overlap)
+        self.dp_slices = None         # data parallel: per-slice all-reduce hook (True) or one collective (False); None = by bucket size
         self.fp16_storage = bool(fp16_storage)
         self.shared_sm = False          # let other kernels' CTAs share SMs with the recurrences / pin the small GEMM tiling
         self._seed = int(seed)
@@ -1101,13 +1103,20 @@ class AcousticEngine:
 
     def backward(self, dlogits: torch.Tensor, allreduce=None):
         """dlogits f32 [T,N,C] (already scaled by 1/global_batch) -> fills params.grad.
-        allreduce (data parallel): called on slices of the flat gradient bucket as soon as they are complete — layer
-        l's [Wf|Wb] right behind its two dW GEMMs and the rest of the layer right behind its dU GEMMs, i.e. while the BPTT
-        of layer l-1 runs, the Dense slice right behind its own GEMM at the start, layer 0 as one slice behind its GEMMs — the
-        only exposed one; the slices tile the bucket exactly once (still ONE logical all-reduce of the bucket per step).
+        allreduce (data parallel): called ONCE, on the whole flat gradient bucket, behind the last GEMM of the backward
+        pass when the bucket is small (< DP_SLICE_BYTES; self.dp_slices = False forces it); for a large bucket (or with
+        self.dp_slices = True) it is called on slices of the bucket as soon as they are complete — the
+        Dense slice behind its own GEMM, layer l's [Wf|Wb] behind its two dW GEMMs and the rest of the layer behind its dU
+        GEMMs (while the BPTT of layer l-1 runs), layer 0 as one slice; the slices tile the bucket exactly once.  Measured on
+        2 and on 8 B200s the single collective wins for C2's 59 MB: the step is short enough that
+        NCCL's CTAs, the background GEMMs and the next BPTT's cooperative launch fight over the same 20 idle SMs.
         Returns the handles (objects with .wait()) the callable returned, if any."""
         sp, P, w = self.spec, self.params, self._w
         handles = []
+        # one collective for a bucket the links move in a fraction of a millisecond (C2: 59 MB), slices overlapped with the
+        # BPTT for a large one (configs[3]: 277 MB, 0.9 ms at 2 GPUs if left to the end) — both measured, DESIGN.md section 6
+        slices = self.dp_slices if self.dp_slices is not None else (P.numel * 4 > DP_SLICE_BYTES)
+        whole, allreduce = allreduce, (allreduce if slices else None)
         if getattr(self, "_pad", None):                 # forward() padded the batch: zero gradient rows for the padding
             n, npad = self._pad
             dl = self._buf("dlogits_pad", (dlogits.shape[0], npad, dlogits.shape[2]), torch.float32)
@@ -1116,8 +1125,8 @@ class AcousticEngine:
             dlogits = dl
         if self._use_general:
             self._backward_general(dlogits)
-            if allreduce is not None:
-                handles.append(allreduce(P.grad))
+            if whole is not None:
+                handles.append(whole(P.grad))
             return handles
         T, N = self._T, self._N
         H, L, Cc = sp.hs[0], len(sp.hs), sp.num_classes
@@ -1258,6 +1267,8 @@ class AcousticEngine:
             torch.cuda.current_stream().wait_stream(self._side)
         if allreduce is not None and sp.conv_front:     # the conv front end's gradients: the head of the bucket
             handles.append(allreduce(P.grad[:self._layer_slice(0)[0]]))
+        if whole is not None and allreduce is None:     # the default: one collective of the whole bucket
+            handles.append(whole(P.grad))
         return handles
 
     # -------------------------------------------------------------- optimiser

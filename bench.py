@@ -249,10 +249,13 @@ def run_ours(args):
     loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"k": 0, "last": None}
 
-    def allreduce(g):                  # called on per-layer slices of the gradient bucket as they complete (engine.backward)
+    def allreduce(g):                  # called by engine.backward: once on the whole gradient bucket (or per slice, --dp-mode slices)
         if world > 1:
+            if args.dp_mode == "none":             # experiment: no collective at all (what the ranks do when left alone)
+                return None
             return dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
 
+    eng.dp_slices = {"slices": True, "bucket": False}.get(args.dp_mode)      # auto / none: the engine decides by bucket size
     if world > 1:
         model.set_data_parallel(allreduce, world, rank=rank)
 
@@ -313,6 +316,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    rank_ms = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,6 +328,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            rank_ms["last"] = [round(float(v.item()) / steps, 4) for v in every]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
         return float(ms.item())
@@ -339,6 +347,7 @@ def run_ours(args):
     sampler.start()
     l0 = lib.asr_launch_count()
     ms = timed(lambda: step(pcm_dev), args.steps)
+    rank_ms_value = rank_ms.get("last")
     launches = (lib.asr_launch_count() - l0) // max(args.steps, 1)
     clocks = sampler.stop()
     for _ in range(2):
@@ -354,7 +363,7 @@ def run_ours(args):
     e2e_engine = gb * args.steps / (ms_e2e / 1e3)
     e2e = gb * args.steps / (ms_plugin / 1e3)
     feat_bytes = int(nb * T_FRAMES * F * 4)
-    dp_check = dp_equivalence(model, feat, nb, world, rank, dev, torch, dist) if world > 1 else None
+    dp_check = dp_equivalence(model, feat, nb, world, rank, dev, torch, dist) if (world > 1 and args.dp_mode != "none") else None
 
     # per-kernel-class device time (instrumented pass, outside the timed region)
     kern = kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch) if rank == 0 else {}
@@ -406,7 +415,7 @@ def run_ours(args):
                                       ": synthetic 16 kHz 10 s clips, %d %s, %dxBiLSTM-%d, Dense-28, CTC, " % (F, "log-mel" if args.config == "c4" else "MFCC", L, H) +
                                       "Adam(1e-3, clipnorm 400), l2 1e-4, variational dropout %g" % args.dropout
                                       + (", zoneout %g" % args.zoneout if args.zoneout else "") + (", MI" if args.mi else ""), "per_gpu_batch": nb,
-                          "global_batch": gb, "frames": T_FRAMES, "parallelism": f"dp{world}",
+                          "global_batch": gb, "frames": T_FRAMES, "parallelism": f"dp{world}" + ("" if args.dp_mode == "auto" else f" (--dp-mode {args.dp_mode})"),
                           "l2_flush": "per-step working set ~4 GB >> 126 MB L2 (inputs larger than L2)",
                           "input_pipeline": "prefetch: H2D + MFCC of batch k+1 on a side stream during step k" if args.prefetch
                           else "in line"},
@@ -422,6 +431,7 @@ def run_ours(args):
                                       "per-utterance loss D2H, read one step late"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_ms": kern,
                **({"data_parallel_check": dp_check} if dp_check is not None else {}),
+               **({"rank_ms_per_step": rank_ms_value} if rank_ms_value else {}),
                "final_loss_mean": float(loss_bufs[(e2e_state["k"] - 1) & 1].mean())}
     if world > 1:
         dist.barrier()
@@ -686,6 +696,10 @@ def main():
                     help="featurise each batch in line instead of one step ahead on the side stream")
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train = C2/C3 (default), infer = C5")
     ap.add_argument("--clips", type=int, default=10240, help="infer mode / sub-record: BASELINE configs[4] asks for 10 k clips")
+    ap.add_argument("--dp-mode", dest="dp_mode", default="auto", choices=["auto", "bucket", "slices", "none"],
+                    help="N > 1: 'auto' = the engine's rule (one all-reduce of the whole gradient bucket behind the backward pass "
+                         "below 128 MB, per-layer slices overlapped with the BPTT of the layer below above), 'bucket' / 'slices' "
+                         "force one of them, 'none' = no collective (experiment: the ranks diverge; timing only)")
     ap.add_argument("--no-infer", dest="infer", action="store_false", help="skip the configs[4] sub-record of the default line")
     ap.add_argument("--beam_width", type=int, default=100)
     ap.add_argument("--ler_sample", type=int, default=256)
