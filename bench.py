@@ -510,6 +510,7 @@ def kernel_breakdown(eng, feat, pcm_dev, off_dev, flat, loff, mx, gb, torch):
         res[name] = res.get(name, 0.0) + a.elapsed_time(b)
         return r
 
+    feat.batch(pcm_dev, off_dev, t_max=T_FRAMES, time_major=True)          # untimed: this thread's workspace / stream set-up
     x, lens = span("mfcc_ms", lambda: feat.batch(pcm_dev, off_dev, t_max=T_FRAMES, time_major=True))
     import asr_study_b200.engine as E
     keys = {"asr_lstm_forward": "lstm_fwd_ms", "asr_lstm_backward": "lstm_bwd_ms", "asr_gemm_tn": "gemm_ms",
