@@ -57,6 +57,11 @@ class ConvGeom(C.Structure):
                 ("st", C.c_int32), ("sf", C.c_int32), ("pt", C.c_int32), ("pf", C.c_int32)]
 
 
+class CastJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("ld_src", C.c_int64), ("dst16", C.c_void_p), ("ld_dst", C.c_int64), ("rows", C.c_int64),
+                ("cols", C.c_int32), ("dtype", C.c_int32), ("transpose", C.c_int32)]
+
+
 class ConvPlan(C.Structure):
     _fields_ = [("t_out", C.c_int32), ("f_out", C.c_int32), ("rows", C.c_int32), ("t_padded", C.c_int32), ("k", C.c_int32),
                 ("k_padded", C.c_int32)]
@@ -114,6 +119,7 @@ SIGNATURES = {
     "asr_sgd_step": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _P, _F, _F, _F, _P]),
     "asr_cast_rows": (_I32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
     "asr_cast_transpose": (_I32, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
+    "asr_cast_batch": (_I32, [C.POINTER(CastJob), _I32, _P]),
     "asr_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P]),
     "asr_mask_cast": (_I32, [_P, _I32, _I64, _P, _I32, _P, _I32, _I64, _I64, _I32, _I32, _P]),
     "asr_dropout_mask": (_I32, [_P, _I64, _F, C.c_uint64, C.c_uint64, _P]),

@@ -52,6 +52,58 @@ cast_transpose_kernel(const float* __restrict__ src, int64_t ld_src, T* __restri
   }
 }
 
+// every 16-bit operand copy of a step in ONE launch: up to CAST_JOBS jobs (asr_cast_rows / asr_cast_transpose semantics
+// each), the grid = the 32 x 32 tiles of all jobs back to back.  The ~20 per-tensor launches this replaces took 0.4 ms of
+// small-kernel time beside the first recurrence and slowed it by 0.15 ms.
+constexpr int CAST_JOBS = 32;
+struct CastBatch {
+  asr_cast_job job[CAST_JOBS];
+  int tile0[CAST_JOBS + 1];       // first tile of job i in the grid
+  int n;
+};
+
+template <typename T, bool LO>
+__device__ __forceinline__ void cast_tile(const asr_cast_job& j, int64_t r0, int c0, float (*tile)[33]) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  T* dst = reinterpret_cast<T*>(j.dst16);
+  if (j.transpose == 1) {
+    for (int k = ty; k < 32; k += 8) {
+      const int64_t r = r0 + k;
+      const int c = c0 + tx;
+      tile[k][tx] = (r < j.rows && c < j.cols) ? j.src[r * j.ld_src + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+      const int c = c0 + k;
+      const int64_t r = r0 + tx;
+      if (c < j.cols && r < j.rows) dst[(int64_t)c * j.ld_dst + r] = cvt2<T, LO>(tile[tx][k]);
+    }
+  } else {
+    // mode 0 zero-fills the K padding up to the next multiple of 8 like asr_cast_rows; mode 2 writes exactly cols columns
+    // (a column sub-block whose right neighbour is another job of the same launch: the fill would race with its data)
+    const int cp = j.transpose == 2 ? j.cols : (int)min((int64_t)((j.cols + 7) / 8 * 8), j.ld_dst);
+    for (int k = ty; k < 32; k += 8) {
+      const int64_t r = r0 + k;
+      const int c = c0 + tx;
+      if (r < j.rows && c < cp) dst[r * j.ld_dst + c] = cvt2<T, LO>(c < j.cols ? j.src[r * j.ld_src + c] : 0.0f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_batch_kernel(const __grid_constant__ CastBatch b) {
+  __shared__ float tile[32][33];
+  int i = 0;
+  while (i + 1 < b.n && (int)blockIdx.x >= b.tile0[i + 1]) ++i;
+  const asr_cast_job& j = b.job[i];
+  const int t = blockIdx.x - b.tile0[i];
+  const int tiles_c = (((j.cols + 7) / 8 * 8) + 31) / 32;
+  const int64_t r0 = (int64_t)(t / tiles_c) * 32;
+  const int c0 = (t % tiles_c) * 32;
+  if (j.dtype == 16) cast_tile<__half, true>(j, r0, c0, tile);
+  else if (j.dtype == 0) cast_tile<__half, false>(j, r0, c0, tile);
+  else cast_tile<__nv_bfloat16, false>(j, r0, c0, tile);
+}
+
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
   // each CTA: 32 columns x a slab of rows; 8 warps stride the rows; atomics to out (pre-zeroed)
@@ -166,6 +218,31 @@ extern "C" int32_t asr_cast_rows(const float* src, int64_t ld_src, void* dst16, 
     cast_rows_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst16, ld_dst,
                                                                             rows, cols);
   ASR_LAUNCH_CHECK();
+  return ASR_OK;
+}
+
+extern "C" int32_t asr_cast_batch(const asr_cast_job* jobs, int32_t n_jobs, void* stream) {
+  ASR_CHECK_ARG(jobs && n_jobs >= 1, "asr_cast_batch: no jobs");
+  for (int base = 0; base < n_jobs; base += CAST_JOBS) {
+    CastBatch b;
+    b.n = n_jobs - base < CAST_JOBS ? n_jobs - base : CAST_JOBS;
+    int tiles = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const asr_cast_job& j = jobs[base + i];
+      ASR_CHECK_ARG(j.src && j.dst16 && j.rows > 0 && j.cols > 0 && j.ld_src >= j.cols &&
+                        (j.transpose == 1 ? j.ld_dst >= j.rows : j.ld_dst >= j.cols) && (j.dtype == 0 || j.dtype == 1 || j.dtype == 16) &&
+                        j.transpose >= 0 && j.transpose <= 2,
+                    "asr_cast_batch: bad job %d", base + i);
+      b.job[i] = j;
+      b.tile0[i] = tiles;
+      const int64_t t = ((j.rows + 31) / 32) * ((((j.cols + 7) / 8 * 8) + 31) / 32);
+      ASR_CHECK_ARG(t < (1 << 24), "asr_cast_batch: job %d is too large", base + i);
+      tiles += (int)t;
+    }
+    b.tile0[b.n] = tiles;
+    cast_batch_kernel<<<tiles, 256, 0, (cudaStream_t)stream>>>(b);
+    ASR_LAUNCH_CHECK();
+  }
   return ASR_OK;
 }
 

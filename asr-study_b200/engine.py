@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from ._lib import (GEMM_BACKGROUND, GEMM_TILE128, LSTM_SHARED_SM, ConvGeom, ConvPlan, LstmBwdArgs, LstmFwdArgs, LstmVariant,
+from ._lib import (GEMM_BACKGROUND, GEMM_TILE128, LSTM_SHARED_SM, CastJob, ConvGeom, ConvPlan, LstmBwdArgs, LstmFwdArgs, LstmVariant,
                    LstmVariantGrads, cur_stream, lib, ptr)
 
 F16, BF16 = 0, 1
@@ -429,10 +429,17 @@ class AcousticEngine:
         """16-bit tensor-core operands derived from the fp32 masters (once per step).
         first_only / skip_first split the work: what the first recurrent layer's forward pass needs (its W^T and U^T)
         is made on the main stream, everything else (the other layers, every BPTT operand, the Dense pair) on the side
-        stream, where it runs on the SMs the first recurrence leaves idle (~20 small launches off the critical path)."""
+        stream beside the first recurrence; each of the two is ONE asr_cast_batch launch over its list of tensors."""
         sp, P = self.spec, self.params
         Cc = sp.num_classes
-        st = cur_stream()
+        jobs = []
+
+        def rows(src, ld_src, dst, ld_dst, n_rows, n_cols, dtype, exact=False):   # asr_cast_rows semantics; exact: no K-padding
+            jobs.append(CastJob(src.data_ptr(), ld_src, dst.data_ptr(), ld_dst, n_rows, n_cols, dtype, 2 if exact else 0))
+
+        def transpose(src, ld_src, dst, ld_dst, n_rows, n_cols, dtype):  # asr_cast_transpose semantics
+            jobs.append(CastJob(src.data_ptr(), ld_src, dst.data_ptr(), ld_dst, n_rows, n_cols, dtype, 1))
+
         D = sp.proj_width or sp.lstm_in                             # width the first BiLSTM sees
         for l, H in enumerate(sp.hs):
             Dp = _pad8(D)
@@ -443,30 +450,33 @@ class AcousticEngine:
             if fwd_ops:
                 wt = self._buf(f"WcatT16.{l}", (8 * H, Dp), torch.float16, zero=True)     # [8H, D]  fwd B operand
                 for i, d in enumerate("fb"):
-                    lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wt[i * 4 * H:]), Dp, D, 4 * H, F16, st)
+                    transpose(P.p(f"l{l}.W{d}"), 4 * H, wt[i * 4 * H:], Dp, D, 4 * H, F16)
                 if sp.layer_norm is not None:     # split-precision projection (fp16 rounding residuals), see _forward_general
                     wl = self._buf(f"WcatT16lo.{l}", (8 * H, Dp), torch.float16, zero=True)
                     for i, d in enumerate("fb"):
-                        lib.asr_cast_transpose(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wl[i * 4 * H:]), Dp, D, 4 * H, F16_LO, st)
+                        transpose(P.p(f"l{l}.W{d}"), 4 * H, wl[i * 4 * H:], Dp, D, 4 * H, F16_LO)
                 ut = self._buf(f"UT16.{l}", (2, 4 * H, H), torch.float16)                 # [2, 4H, H] U^T, fwd recurrence
                 for i, d in enumerate("fb"):
-                    lib.asr_cast_transpose(ptr(P.p(f"l{l}.U{d}")), 4 * H, ptr(ut[i]), H, H, 4 * H, F16, st)
+                    transpose(P.p(f"l{l}.U{d}"), 4 * H, ut[i], H, H, 4 * H, F16)
             if rest and training:
                 ub = self._buf(f"Ub16.{l}", (2, H, 4 * H), torch.bfloat16)             # [2, H, 4H] U, BPTT recurrence
-                lib.asr_cast_rows(ptr(P.p(f"l{l}.Uf")), 4 * H, ptr(ub), 4 * H, 2 * H, 4 * H, BF16, st)
+                rows(P.p(f"l{l}.Uf"), 4 * H, ub, 4 * H, 2 * H, 4 * H, BF16)
             if rest and training and (l > 0 or sp.proj_width or sp.conv_front):
                 wc = self._buf(f"Wcat16.{l}", (D, 8 * H), torch.bfloat16)              # [D, 8H]  dX B operand
                 for i, d in enumerate("fb"):
-                    lib.asr_cast_rows(ptr(P.p(f"l{l}.W{d}")), 4 * H, ptr(wc[:, i * 4 * H:]), 8 * H, D, 4 * H, BF16, st)
+                    # the two directions are column blocks of one matrix and the jobs of a launch run concurrently: no fill
+                    # past 4H (at 4H % 8 != 0 the forward block's padding would land on the backward block's first columns)
+                    rows(P.p(f"l{l}.W{d}"), 4 * H, wc[:, i * 4 * H:], 8 * H, D, 4 * H, BF16, exact=True)
             D = 2 * H
-        if first_only:
-            return
-        dp, H2 = _pad8(Cc), 2 * sp.hs[-1]
-        wd = self._buf("WdT16", (Cc, _pad8(H2)), torch.float16, zero=True)             # [C, 2H (padded to 8)] logits B operand
-        lib.asr_cast_transpose(ptr(P.p("dense.W")), Cc, ptr(wd), _pad8(H2), H2, Cc, F16, st)
-        if training:
-            wdb = self._buf("Wd16", (H2, dp), torch.bfloat16, zero=True)               # [2H, Cpad] dTop B operand
-            lib.asr_cast_rows(ptr(P.p("dense.W")), Cc, ptr(wdb), dp, H2, Cc, BF16, st)
+        if not first_only:
+            dp, H2 = _pad8(Cc), 2 * sp.hs[-1]
+            wd = self._buf("WdT16", (Cc, _pad8(H2)), torch.float16, zero=True)             # [C, 2H (padded to 8)] logits B operand
+            transpose(P.p("dense.W"), Cc, wd, _pad8(H2), H2, Cc, F16)
+            if training:
+                wdb = self._buf("Wd16", (H2, dp), torch.bfloat16, zero=True)               # [2H, Cpad] dTop B operand
+                rows(P.p("dense.W"), Cc, wdb, dp, H2, Cc, BF16)
+        if jobs:                                                    # one launch for the whole list (csrc/utils.cu)
+            lib.asr_cast_batch((CastJob * len(jobs))(*jobs), len(jobs), cur_stream())
 
     def _gemm(self, din, dout, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, alpha=1.0, acc=0):
         lib.asr_gemm_tn_ex(din, dout, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(Cm), ldc, ptr(bias), float(alpha), acc,

@@ -339,6 +339,16 @@ int32_t asr_cast_rows(const float* src, int64_t ld_src, void* dst16, int64_t ld_
 /* dst16[c, r] = cast(src[r, c])  (transpose), ld_dst >= rows */
 int32_t asr_cast_transpose(const float* src, int64_t ld_src, void* dst16, int64_t ld_dst,
                            int64_t rows, int32_t cols, int32_t dtype, void* stream);
+/* the same two operations for a whole list of tensors in one launch (the per-step 16-bit operand copies of every weight) */
+typedef struct {
+  const float* src; int64_t ld_src;
+  void* dst16;      int64_t ld_dst;
+  int64_t rows;     int32_t cols;
+  int32_t dtype;            /* 0 = fp16, 1 = bf16, 16 = fp16 rounding residual                 */
+  int32_t transpose;        /* 0: asr_cast_rows semantics, 1: asr_cast_transpose semantics, 2: rows without the K-padding
+                               fill (a column sub-block next to another job's: jobs of one launch run concurrently) */
+} asr_cast_job;
+int32_t asr_cast_batch(const asr_cast_job* jobs_host, int32_t n_jobs, void* stream);
 /* variational-dropout operand views (core/layers.py:439: x * B_W[0], mask constant over time):
  * rows are time-major r = t*n_batch + n; mask f32 [n_batch, cols] (already scaled by 1/(1-p)).
  * src_dtype: 0 = fp16, 1 = bf16, 2 = fp32.  dst16[r, c] = cast(src[r, c] * mask[r % n_batch, c]);

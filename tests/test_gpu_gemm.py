@@ -62,3 +62,46 @@ def test_gemm_strided_views_with_k_offset():
                     None, 1.0, 0, cur_stream())
     torch.cuda.synchronize()
     assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_cast_batch_matches_the_single_tensor_entries():
+    """asr_cast_batch: every job of a list (row casts with K padding into a column sub-block, transposes, the fp16 rounding
+    residual) in one launch, bit-identical to asr_cast_rows / asr_cast_transpose."""
+    from asr_study_b200._lib import CastJob, cur_stream, lib, ptr
+    g = torch.Generator(device="cuda").manual_seed(5)
+    specs = [(37, 26, 0, 0), (512, 2048, 1, 0), (100, 28, 0, 1), (26, 2048, 0, 1), (64, 72, 16, 1), (9, 13, 16, 0), (300, 40, 1, 1)]
+    jobs, checks = [], []
+    for rows, cols, dtype, tr in specs:
+        src = torch.randn(rows, cols + 3, device="cuda", generator=g)
+        tdt = torch.bfloat16 if dtype == 1 else torch.float16
+        ld = (rows + 8) if tr else ((cols + 7) // 8 * 8 + 8)
+        shape = (cols, ld) if tr else (rows, ld)
+        got = torch.full(shape, 7.0, dtype=tdt, device="cuda")
+        ref = torch.full(shape, 7.0, dtype=tdt, device="cuda")
+        jobs.append(CastJob(src.data_ptr(), cols + 3, got.data_ptr(), ld, rows, cols, dtype, tr))
+        fn = lib.asr_cast_transpose if tr else lib.asr_cast_rows
+        fn(ptr(src), cols + 3, ptr(ref), ld, rows, cols, dtype, cur_stream())
+        checks.append((src, got, ref))
+    lib.asr_cast_batch((CastJob * len(jobs))(*jobs), len(jobs), cur_stream())
+    torch.cuda.synchronize()
+    for src, got, ref in checks:
+        assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    # mode 2: two column blocks of one matrix whose width is not a multiple of 8, no padding fill across the seam
+    a, b = torch.randn(50, 108, device="cuda", generator=g), torch.randn(50, 108, device="cuda", generator=g)
+    out = torch.zeros(50, 216, dtype=torch.bfloat16, device="cuda")
+    two = [CastJob(a.data_ptr(), 108, out.data_ptr(), 216, 50, 108, 1, 2), CastJob(b.data_ptr(), 108, out[:, 108:].data_ptr(), 216, 50, 108, 1, 2)]
+    lib.asr_cast_batch((CastJob * 2)(*two), 2, cur_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out, torch.cat([a, b], 1).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("rows,ld,K,N", [(8192, 640, 7040, 320), (4096, 80, 448, 640), (300, 64, 512, 128)])
+def test_gemm_overlapping_rows_view(rows, ld, K, N):
+    """lda < K: row m of A starts lda elements after row m-1 (the convolution view of csrc/conv.cu) — the TMA tensor map
+    takes a global stride smaller than the box; against the same contraction on torch's unfold view."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    flat = (torch.randn(rows * ld + K + 64, device="cuda", generator=g) * 0.5).half()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    got = _gemm(0, 0, flat, B, M=rows, N=N, K=K, lda=ld, ldb=K)
+    ref = flat[:(rows - 1) * ld + K].unfold(0, K, ld).float() @ B.float().t()
+    assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5
