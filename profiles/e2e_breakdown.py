@@ -25,7 +25,7 @@ def main():
     import torch
 
     from asr_study_b200.core import models
-    from asr_study_b200.core.models import LazyMetrics, _GeneratorFeed
+    from asr_study_b200.core.models import _GeneratorFeed
     from asr_study_b200.datasets.dataset_generator import DatasetIterator
     from asr_study_b200.engine import pack_labels
     from asr_study_b200.preprocessing import audio
